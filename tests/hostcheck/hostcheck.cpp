@@ -1,0 +1,81 @@
+// hostcheck.cpp -- UNIT-TEST SHIM, not product code.
+// Compiles the scalar device functions of torchmd_b200/csrc/physics.cuh for the
+// host so tests/test_physics_host.py can compare them with the oracle on a machine
+// without a GPU.  Nothing in torchmd_b200 loads this library.
+#include "physics.cuh"
+
+using namespace tmd;
+
+extern "C" {
+
+float hc_squared_threshold(float rc) { return squared_threshold(rc); }
+
+// minimum image + squared distance + cutoff decision for n pairs
+void hc_decide(int n, const float* pi, const float* pj, const float* box, int periodic, float s_max,
+               float* w_out, float* s_out, int* in_out) {
+  for (int k = 0; k < n; ++k) {
+    Vec3 a = {pi[3 * k], pi[3 * k + 1], pi[3 * k + 2]}, b = {pj[3 * k], pj[3 * k + 1], pj[3 * k + 2]};
+    Vec3 L = {box[0], box[1], box[2]};
+    Vec3 iL = {1.0f / box[0], 1.0f / box[1], 1.0f / box[2]};
+    Vec3 d = delta_ref(a, b, periodic, L, iL);
+    w_out[3 * k] = d.x; w_out[3 * k + 1] = d.y; w_out[3 * k + 2] = d.z;
+    s_out[k] = norm2_ref(d.x, d.y, d.z);
+    in_out[k] = s_out[k] <= s_max;
+  }
+}
+
+// pair energies (4 terms) and dE/dr for n pairs at squared distance s
+void hc_pair_terms(int n, const float* s, const float* qq, const float* A, const float* B, unsigned terms,
+                   int has_cutoff, float cutoff, int has_switch, float switch_dist, int rfa, float krf, float crf,
+                   float* e_el, float* e_lj, float* e_rep, float* e_cg, float* dedr) {
+  PairParams pp{};
+  pp.terms = terms;
+  pp.has_cutoff = has_cutoff;
+  pp.cutoff = cutoff;
+  pp.has_switch = has_switch;
+  pp.switch_dist = switch_dist;
+  pp.inv_sw_width = has_switch ? 1.0f / (cutoff - switch_dist) : 0.f;
+  pp.rfa = rfa;
+  pp.krf = krf;
+  pp.crf = crf;
+  pp.two_krf = 2.0f * krf;
+  for (int k = 0; k < n; ++k) {
+    float a = 0, b = 0, c = 0, d = 0, rinv;
+    dedr[k] = pair_terms(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv);
+    e_el[k] = a; e_lj[k] = b; e_rep[k] = c; e_cg[k] = d;
+  }
+}
+
+void hc_bond(int n, const float* r, const float* k0, const float* r0, float* e, float* dedr) {
+  for (int k = 0; k < n; ++k) bond_term(r[k], k0[k], r0[k], e[k], dedr[k]);
+}
+
+void hc_angle(int n, const float* r21, const float* r23, const float* k0, const float* th0, float* e, float* f) {
+  for (int k = 0; k < n; ++k) {
+    Vec3 a = {r21[3 * k], r21[3 * k + 1], r21[3 * k + 2]}, b = {r23[3 * k], r23[3 * k + 1], r23[3 * k + 2]};
+    Vec3 f0, f1, f2;
+    e[k] = angle_term(a, b, k0[k], th0[k], f0, f1, f2);
+    float* o = f + 9 * k;
+    o[0] = f0.x; o[1] = f0.y; o[2] = f0.z; o[3] = f1.x; o[4] = f1.y; o[5] = f1.z; o[6] = f2.x; o[7] = f2.y; o[8] = f2.z;
+  }
+}
+
+void hc_torsion(int n, const float* r12, const float* r23, const float* r34, const int* term_ptr, const float* terms,
+                int amber, float* e, float* f) {
+  for (int k = 0; k < n; ++k) {
+    Vec3 a = {r12[3 * k], r12[3 * k + 1], r12[3 * k + 2]}, b = {r23[3 * k], r23[3 * k + 1], r23[3 * k + 2]},
+         c = {r34[3 * k], r34[3 * k + 1], r34[3 * k + 2]};
+    TorsionGeom g = torsion_geom(a, b, c);
+    float ee = 0, coef = 0;
+    for (int m = term_ptr[k]; m < term_ptr[k + 1]; ++m)
+      torsion_term(g.phi, terms[3 * m], terms[3 * m + 1], terms[3 * m + 2], amber, ee, coef);
+    Vec3 f0, f1, f2, f3;
+    torsion_forces(g, coef, f0, f1, f2, f3);
+    e[k] = ee;
+    float* o = f + 12 * k;
+    o[0] = f0.x; o[1] = f0.y; o[2] = f0.z; o[3] = f1.x; o[4] = f1.y; o[5] = f1.z;
+    o[6] = f2.x; o[7] = f2.y; o[8] = f2.z; o[9] = f3.x; o[10] = f3.y; o[11] = f3.z;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// context.cuh -- device-resident state of one tmd_ctx and small helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tmd_b200.h"
+#include "physics.cuh"
+
+namespace tmd {
+
+// Cell grid of one replica.  Filled on the host for periodic boxes
+// (tmd_set_box) and by k_bounds_grid on the device for non-periodic systems.
+struct Grid {
+  int n[3];         // cells per dimension
+  int reach[3];     // neighbour-cell reach per dimension (0 when n == 1)
+  int ncells;       // n[0]*n[1]*n[2]
+  int periodic;     // wrap cell indices / minimum image
+  float L[3];       // box lengths (periodic) -- 0 otherwise
+  float invL[3];    // 1/L
+  float origin[3];  // lower corner (non-periodic); 0 for periodic
+  float inv_w[3];   // 1 / cell width
+};
+
+// Flags/counters per replica (device ints).
+enum {
+  F_REBUILD0 = 0,  // rebuild request, even calls
+  F_REBUILD1 = 1,  // rebuild request, odd calls
+  F_OVERFLOW = 2,
+  F_NREBUILD = 3,
+  F_MAXNBR = 4,
+  F_BADCELL = 5,
+  F_COUNT = 8
+};
+
+struct DeviceState {
+  // sizes
+  int natoms, nrep;
+  int row_cap;      // neighbour entries reserved per atom
+  int max_cells;    // capacity of the cell arrays per replica
+  int nsub;         // cells per list radius
+  // per-atom static data (original order)
+  const float* q;        // charge * sqrt(coulomb constant)
+  const int* type;       // atom type id
+  const int* excl_ptr;   // CSR exclusions, original indices
+  const int* excl_idx;
+  // LJ tables
+  const float2* AB;      // (T*T) {A,B}
+  int ntypes;
+  // per replica dynamic data (index [rep*natoms + k])
+  float4* xq_s;          // sorted: raw x,y,z + scaled charge
+  int* type_s;           // sorted atom type
+  int* perm;             // sorted slot -> original atom
+  int* inv;              // original atom -> sorted slot
+  float4* pos_ref;       // positions at the last rebuild (original order)
+  int* cell_of;          // original atom -> cell
+  int* rank;             // slot inside the cell handed out by the counting pass
+  int* cell_count;       // [rep*(max_cells+1) + c]   zero outside rebuilds
+  int* cell_start;       // exclusive scan of the counts (ncells+1 entries)
+  int* nbr;              // [(rep*natoms + k)*row_cap + e]
+  int* nnbr;             // neighbours of sorted atom k
+  int* flags;            // [rep*F_COUNT + f]
+  Grid* grid;            // [rep]
+  float* bounds;         // [rep*6] min xyz, max xyz (non-periodic), as ordered ints
+  // list parameters
+  float rlist2;          // (cutoff+skin)^2 * (1+eps); +inf without cutoff
+  float rlist;           // cutoff + skin
+  float trigger2;        // (skin/2 - margin)^2 ; +inf without cutoff
+  PairParams pp;
+};
+
+struct BondedSet {
+  int n = 0;
+  int* idx = nullptr;    // (n,k)
+  float* prm = nullptr;  // (n,p)
+  int* term_ptr = nullptr;  // torsions only
+  float* terms = nullptr;
+  int amber = 1;
+};
+
+}  // namespace tmd
+
+struct tmd_ctx {
+  int device = 0;
+  int natoms = 0, nrep = 0;
+  tmd::DeviceState d{};
+  // owned device buffers behind the const pointers in d
+  float* q = nullptr;
+  int* type = nullptr;
+  int* excl_ptr = nullptr;
+  int* excl_idx = nullptr;
+  float2* AB = nullptr;
+  tmd::BondedSet bonds, angles, torsions[2], pairs14;
+  uint32_t bonded_mask = 0;   // which bonded energy terms are enabled
+  uint32_t pair_mask = 0;
+  double coulomb = 0.0, cutoff = -1.0, switch_dist = -1.0, skin = 0.0;
+  int rfa = 0;
+  bool have_atoms = false, have_nonbonded = false, have_box = false, have_excl = false;
+  bool periodic = false;
+  std::vector<float> box_host;       // (nrep,3)
+  std::vector<float> charges_host;   // unscaled charges
+  uint64_t call_index = 0;           // parity selects the rebuild flag
+  int64_t launches = 0;
+  int64_t force_calls = 0;
+  bool overflow_reported = false;
+  double* ke_scratch = nullptr;      // (nrep) doubles for the host entry
+  double* e_scratch = nullptr;       // (nrep, TMD_NUM_ENERGIES)
+};

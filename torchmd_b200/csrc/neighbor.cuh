@@ -1,0 +1,375 @@
+// neighbor.cuh -- cell list + Verlet neighbour list, built on the device.
+//
+// The reference has no neighbour search: it evaluates every pair of its static
+// all-pairs table and masks with dist <= cutoff each step (forces.py:264-269;
+// torchmd/neighbourlist.py is an unused stub whose fixed-width binning would
+// miss cross-boundary pairs).  Here:
+//
+//   k_prepare     every call: displacement test against the positions of the
+//                 last build (sets the rebuild flag) + refresh of the sorted
+//                 position/charge records the pair kernel gathers from.
+//   k_bounds/k_grid  (non-periodic only) bounding box -> cell grid.
+//   k_bin         cell index per atom + counting pass.
+//   k_scan        exclusive scan of the cell counts (one CTA per replica).
+//   k_place       counting-sort scatter.
+//   k_sort_pack   order every cell by original atom index (deterministic),
+//                 write the sorted records and the inverse permutation.
+//   k_build_list  full Verlet list: for every atom all partners within
+//                 cutoff+skin that are not excluded, one 128-byte-aligned row
+//                 per atom so a warp streams a row with coalesced loads.
+//
+// Every rebuild kernel returns immediately unless the replica's rebuild flag is
+// set, so the host can enqueue them unconditionally (no host round trip).
+#pragma once
+#include "context.cuh"
+
+namespace tmd {
+
+__device__ __forceinline__ int enc_float(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+__device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, float z) {
+  float p[3] = {x, y, z};
+  int c[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int ci;
+    if (g.periodic) {
+      float f = p[d] * g.invL[d];
+      f -= floorf(f);  // [0,1]
+      ci = (int)(f * (float)g.n[d]);
+    } else {
+      ci = (int)floorf((p[d] - g.origin[d]) * g.inv_w[d]);
+    }
+    c[d] = max(0, min(ci, g.n[d] - 1));
+  }
+  return (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+}
+
+// ---- every call ---------------------------------------------------------------
+__global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int parity) {
+  const int r = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int* fl = S.flags + r * F_COUNT;
+  if (i == 0) fl[F_REBUILD0 + (parity ^ 1)] = 0;  // nobody reads or sets that one now
+  if (i >= S.natoms) return;
+  const size_t a = (size_t)r * S.natoms + i;
+  const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
+  const float4 ref = S.pos_ref[a];
+  const float dx = x - ref.x, dy = y - ref.y, dz = z - ref.z;
+  const float d2 = dx * dx + dy * dy + dz * dz;
+  if (!(d2 <= S.trigger2)) {  // also true for NaN (= no list yet)
+    if (fl[F_REBUILD0 + parity] == 0) fl[F_REBUILD0 + parity] = 1;
+  }
+  const int k = S.inv[a];
+  S.xq_s[(size_t)r * S.natoms + k] = make_float4(x, y, z, S.q[i]);
+}
+
+// ---- rebuild: non-periodic bounding box -------------------------------------------
+__global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int parity) {
+  const int r = blockIdx.y;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (i < S.natoms) {
+    const size_t a = ((size_t)r * S.natoms + i) * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) lo[d] = hi[d] = pos[a + d];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    int* b = reinterpret_cast<int*>(S.bounds) + r * 6;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(b + d, enc_float(lo[d]));
+      atomicMax(b + 3 + d, enc_float(hi[d]));
+    }
+  }
+}
+
+__global__ void k_grid(DeviceState S, int parity) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.nrep) return;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  int* b = reinterpret_cast<int*>(S.bounds) + r * 6;
+  Grid g;
+  g.periodic = 0;
+  int cap = 1;
+  while ((cap + 1) * (cap + 1) * (cap + 1) <= S.max_cells) ++cap;
+  const float w0 = S.rlist / (float)S.nsub;  // +inf without cutoff
+  g.ncells = 1;
+  for (int d = 0; d < 3; ++d) {
+    const float lo = dec_float(b[d]), hi = dec_float(b[3 + d]);
+    const float ext = fmaxf(hi - lo, 0.0f);
+    float w = fmaxf(w0, ext / (float)cap * 1.0001f);
+    int n = isinf(w) ? 1 : min(cap, (int)(ext / w) + 1);
+    g.n[d] = n;
+    g.reach[d] = (n > 1) ? S.nsub : 0;
+    g.L[d] = 0.0f;
+    g.invL[d] = 0.0f;
+    g.origin[d] = lo;
+    g.inv_w[d] = isinf(w) ? 0.0f : 1.0f / w;
+    g.ncells *= n;
+    b[d] = enc_float(INFINITY);  // re-arm for the next build
+    b[3 + d] = enc_float(-INFINITY);
+  }
+  S.grid[r] = g;
+}
+
+// ---- rebuild: counting sort by cell ---------------------------------------------------
+__global__ void k_bin(DeviceState S, const float* __restrict__ pos, int parity) {
+  const int r = blockIdx.y;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.natoms) return;
+  const size_t a = (size_t)r * S.natoms + i;
+  const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
+  const int c = cell_of_point(S.grid[r], x, y, z);
+  S.cell_of[a] = c;
+  S.rank[a] = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
+  S.pos_ref[a] = make_float4(x, y, z, 0.0f);
+}
+
+__global__ void __launch_bounds__(1024) k_scan(DeviceState S, int parity) {
+  const int r = blockIdx.x;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  __shared__ int warp_tot[32];
+  const int n = S.grid[r].ncells;
+  const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
+  int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  const int chunk = (n + 1023) / 1024;
+  const int b = threadIdx.x * chunk, e = min(n, b + chunk);
+  int sum = 0;
+  for (int c = b; c < e; ++c) sum += cnt[c];
+  // block-wide exclusive scan of the per-thread sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_tot[lane];
+    int ti = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += v;
+    }
+    warp_tot[lane] = ti - t;  // exclusive offset of each warp
+  }
+  __syncthreads();
+  int run = warp_tot[wid] + incl - sum;
+  for (int c = b; c < e; ++c) {
+    start[c] = run;
+    run += cnt[c];
+  }
+  if (threadIdx.x == 1023) start[n] = run;  // inclusive prefix of the last thread = total
+}
+
+__global__ void k_place(DeviceState S, int parity) {
+  const int r = blockIdx.y;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.natoms) return;
+  const size_t a = (size_t)r * S.natoms + i;
+  const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  S.perm[(size_t)r * S.natoms + start[S.cell_of[a]] + S.rank[a]] = i;
+}
+
+// One warp per cell: sort the cell's atoms by original index, then emit the sorted
+// records.  Cells are small (a few to a few tens of atoms); rank-by-counting.
+__global__ void k_sort_pack(DeviceState S, int parity) {
+  const int r = blockIdx.y;
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+  const int ncells = S.grid[r].ncells;
+  const size_t base = (size_t)r * S.natoms;
+  int* perm = S.perm + base;
+  int* tmp = S.rank + base;  // free after k_place
+  int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
+  const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
+    const int b = start[c], n = start[c + 1] - b;
+    if (lane == 0) cnt[c] = 0;  // leave the counters clean for the next build
+    if (n <= 32) {
+      const int v = lane < n ? perm[b + lane] : 0x7fffffff;
+      int rk = 0;
+      for (int m = 0; m < n; ++m) rk += (__shfl_sync(0xffffffffu, v, m) < v);
+      __syncwarp();
+      if (lane < n) perm[b + rk] = v;
+    } else {
+      for (int e = lane; e < n; e += 32) {
+        const int v = perm[b + e];
+        int rk = 0;
+        for (int m = 0; m < n; ++m) rk += (perm[b + m] < v);
+        tmp[b + rk] = v;
+      }
+      __syncwarp();
+      __threadfence_block();
+      for (int e = lane; e < n; e += 32) perm[b + e] = tmp[b + e];
+    }
+    __syncwarp();
+    __threadfence_block();
+    for (int e = lane; e < n; e += 32) {
+      const int i = perm[b + e];
+      const float4 p = S.pos_ref[base + i];
+      S.inv[base + i] = b + e;
+      S.xq_s[base + b + e] = make_float4(p.x, p.y, p.z, S.q[i]);
+      S.type_s[base + b + e] = S.type[i];
+    }
+  }
+}
+
+// ---- rebuild: Verlet list ---------------------------------------------------------------
+// One warp per (sorted) atom.  Candidates come from the (2*reach+1)^3 surrounding
+// cells; cells adjacent in x are adjacent in memory, so each (dz,dy) row is one or two
+// contiguous runs of sorted atoms read with coalesced 16-byte loads.  The distance
+// test here is approximate and generous (rlist carries a safety margin); the exact
+// reference predicate is applied by the pair kernel.
+constexpr int BUILD_WARPS = 4;
+__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_list(DeviceState S, int parity) {
+  const int r = blockIdx.y;
+  int* fl = S.flags + r * F_COUNT;
+  if (!fl[F_REBUILD0 + parity]) return;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fl + F_NREBUILD, 1);
+  if (k >= S.natoms) return;
+  const Grid g = S.grid[r];
+  const size_t base = (size_t)r * S.natoms;
+  const float4* __restrict__ xq = S.xq_s + base;
+  const int* __restrict__ perm = S.perm + base;
+  const int* __restrict__ start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+
+  const int io = perm[k];
+  const int c = S.cell_of[base + io];
+  const int cx = c % g.n[0], cy = (c / g.n[0]) % g.n[1], cz = c / (g.n[0] * g.n[1]);
+  const float4 pi = xq[k];
+  const int e0 = S.excl_ptr ? S.excl_ptr[io] : 0;
+  const int ne = S.excl_ptr ? S.excl_ptr[io + 1] - e0 : 0;
+  const int my_excl = (lane < ne) ? S.excl_idx[e0 + lane] : -1;
+  const unsigned lt = (1u << lane) - 1u;
+  int count = 0;
+
+  for (int dz = -g.reach[2]; dz <= g.reach[2]; ++dz) {
+    int z2 = cz + dz;
+    if (g.periodic) z2 = (z2 + g.n[2]) % g.n[2];
+    else if (z2 < 0 || z2 >= g.n[2]) continue;
+    for (int dy = -g.reach[1]; dy <= g.reach[1]; ++dy) {
+      int y2 = cy + dy;
+      if (g.periodic) y2 = (y2 + g.n[1]) % g.n[1];
+      else if (y2 < 0 || y2 >= g.n[1]) continue;
+      const int rowbase = (z2 * g.n[1] + y2) * g.n[0];
+      int lo = cx - g.reach[0], hi = cx + g.reach[0];
+      int seg_lo[2], seg_hi[2], nseg = 1;
+      if (g.periodic) {
+        if (lo < 0) { seg_lo[0] = lo + g.n[0]; seg_hi[0] = g.n[0] - 1; seg_lo[1] = 0; seg_hi[1] = hi; nseg = 2; }
+        else if (hi >= g.n[0]) { seg_lo[0] = lo; seg_hi[0] = g.n[0] - 1; seg_lo[1] = 0; seg_hi[1] = hi - g.n[0]; nseg = 2; }
+        else { seg_lo[0] = lo; seg_hi[0] = hi; }
+      } else {
+        seg_lo[0] = max(lo, 0);
+        seg_hi[0] = min(hi, g.n[0] - 1);
+      }
+      for (int sgm = 0; sgm < nseg; ++sgm) {
+        const int a0 = start[rowbase + seg_lo[sgm]], a1 = start[rowbase + seg_hi[sgm] + 1];
+        for (int j0 = a0; j0 < a1; j0 += 32) {
+          const int j = j0 + lane;
+          bool ok = (j < a1) && (j != k);
+          if (ok) {
+            const float4 pj = xq[j];
+            float dx = pi.x - pj.x, dy2 = pi.y - pj.y, dz2 = pi.z - pj.z;
+            if (g.periodic) {
+              dx -= g.L[0] * rintf(dx * g.invL[0]);
+              dy2 -= g.L[1] * rintf(dy2 * g.invL[1]);
+              dz2 -= g.L[2] * rintf(dz2 * g.invL[2]);
+            }
+            ok = (dx * dx + dy2 * dy2 + dz2 * dz2) <= S.rlist2;
+          }
+          if (ne > 0) {  // warp-uniform
+            const int oj = ok ? perm[j] : -2;
+            const int nfast = min(ne, 32);
+            for (int e = 0; e < nfast; ++e)
+              if (__shfl_sync(0xffffffffu, my_excl, e) == oj) ok = false;
+            for (int e = 32; e < ne; ++e)
+              if (S.excl_idx[e0 + e] == oj) ok = false;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (ok) {
+            const int slot = count + __popc(m & lt);
+            if (slot < S.row_cap) row[slot] = j;
+          }
+          count += __popc(m);
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    S.nnbr[base + k] = min(count, S.row_cap);
+    if (count > S.row_cap) fl[F_OVERFLOW] = 1;
+    if (count > fl[F_MAXNBR]) atomicMax(fl + F_MAXNBR, count);
+  }
+}
+
+// ---- inspection: the reference's neighbour list ----------------------------------------
+// Applies the exact reference predicate to every listed pair and emits (i<j) in
+// original atom indices.  Used by the bit-exact index test.
+__global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long long capacity,
+                               unsigned long long* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= S.natoms) return;
+  const Grid g = S.grid[r];
+  const size_t base = (size_t)r * S.natoms;
+  const float4* xq = S.xq_s + base;
+  const int* perm = S.perm + base;
+  const int* row = S.nbr + (base + k) * (size_t)S.row_cap;
+  const int n = S.nnbr[base + k];
+  const float4 pi = xq[k];
+  const int oi = perm[k];
+  const unsigned lt = (1u << lane) - 1u;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    bool ok = false;
+    int oj = 0;
+    if (e < n) {
+      const int j = row[e];
+      const float4 pj = xq[j];
+      float dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
+      if (g.periodic) {
+        dx = min_image(dx, g.L[0], g.invL[0]);
+        dy = min_image(dy, g.L[1], g.invL[1]);
+        dz = min_image(dz, g.L[2], g.invL[2]);
+      }
+      oj = perm[j];
+      ok = (norm2_ref(dx, dy, dz) <= S.pp.s_max) && (oi < oj);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    unsigned long long b = 0;
+    if (lane == 0 && m) b = atomicAdd(count, (unsigned long long)__popc(m));
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (ok) {
+      const unsigned long long slot = b + __popc(m & lt);
+      if ((long long)slot < capacity) {
+        out[slot * 2 + 0] = oi;
+        out[slot * 2 + 1] = oj;
+      }
+    }
+  }
+}
+
+}  // namespace tmd

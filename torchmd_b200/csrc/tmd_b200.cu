@@ -1,0 +1,675 @@
+// tmd_b200.cu -- C ABI (include/tmd_b200.h) over the sm_100a kernels.
+// Host side only enqueues: no synchronisation and no allocation in the per-step
+// entry points once the context is finalised.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "bonded.cuh"
+#include "context.cuh"
+#include "integrate.cuh"
+#include "neighbor.cuh"
+#include "pair.cuh"
+
+using namespace tmd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define TMD_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(TMD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+#define TMD_LAUNCHED(ctx, name)                                                                 \
+  do {                                                                                          \
+    (ctx)->launches++;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(TMD_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n) {
+  if (*dst) {
+    cudaFree(*dst);
+    *dst = nullptr;
+  }
+  if (n == 0) return TMD_OK;
+  TMD_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+  TMD_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return TMD_OK;
+}
+
+template <typename T>
+int device_alloc(T** dst, size_t n) {
+  if (*dst) {
+    cudaFree(*dst);
+    *dst = nullptr;
+  }
+  if (n == 0) return TMD_OK;
+  TMD_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+  return TMD_OK;
+}
+
+inline int round_up32(long long v) { return (int)(((v + 31) / 32) * 32); }
+
+struct CtxPriv {
+  bool dirty = true;
+  size_t nbr_entries = 0;
+  std::vector<cudaEvent_t> ev;  // pair-kernel timing samples (begin,end interleaved)
+  int ev_used = 0;
+  bool profiling = false;
+};
+
+}  // namespace
+
+// private per-context bookkeeping kept out of the public struct layout
+struct tmd_ctx_full : tmd_ctx {
+  CtxPriv priv;
+};
+static inline CtxPriv& priv(tmd_ctx* c) { return static_cast<tmd_ctx_full*>(c)->priv; }
+
+extern "C" {
+
+const char* tmd_last_error(void) { return g_err.c_str(); }
+int tmd_version(void) { return 100; }
+
+int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
+  if (!out || natoms <= 0 || nreplicas <= 0) return fail(TMD_ERR_ARG, "tmd_create: bad arguments");
+  if (nreplicas > 65535) return fail(TMD_ERR_ARG, "tmd_create: at most 65535 replicas");
+  int ndev = 0;
+  TMD_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(TMD_ERR_ARG, "tmd_create: no such CUDA device");
+  DeviceGuard guard(device);
+  tmd_ctx_full* c = new tmd_ctx_full();
+  c->device = device;
+  c->natoms = natoms;
+  c->nrep = nreplicas;
+  DeviceState& d = c->d;
+  d.natoms = natoms;
+  d.nrep = nreplicas;
+  d.nsub = 2;
+  const size_t RN = (size_t)natoms * nreplicas;
+  int rc = TMD_OK;
+  if ((rc = device_alloc(&d.xq_s, RN))) return rc;
+  if ((rc = device_alloc(&d.type_s, RN))) return rc;
+  if ((rc = device_alloc(&d.perm, RN))) return rc;
+  if ((rc = device_alloc(&d.inv, RN))) return rc;
+  if ((rc = device_alloc(&d.pos_ref, RN))) return rc;
+  if ((rc = device_alloc(&d.cell_of, RN))) return rc;
+  if ((rc = device_alloc(&d.rank, RN))) return rc;
+  if ((rc = device_alloc(&d.nnbr, RN))) return rc;
+  if ((rc = device_alloc(&d.flags, (size_t)nreplicas * F_COUNT))) return rc;
+  if ((rc = device_alloc(&d.grid, (size_t)nreplicas))) return rc;
+  if ((rc = device_alloc(&d.bounds, (size_t)nreplicas * 6))) return rc;
+  if ((rc = device_alloc(&c->ke_scratch, (size_t)nreplicas))) return rc;
+  if ((rc = device_alloc(&c->e_scratch, (size_t)nreplicas * TMD_NUM_ENERGIES))) return rc;
+  TMD_CUDA(cudaMemset(d.xq_s, 0, RN * sizeof(float4)));
+  TMD_CUDA(cudaMemset(d.type_s, 0, RN * sizeof(int)));
+  TMD_CUDA(cudaMemset(d.nnbr, 0, RN * sizeof(int)));
+  *out = c;
+  return TMD_OK;
+}
+
+int tmd_destroy(tmd_ctx* ctx) {
+  if (!ctx) return TMD_OK;
+  DeviceGuard guard(ctx->device);
+  DeviceState& d = ctx->d;
+  void* bufs[] = {d.xq_s, d.type_s, d.perm, d.inv, d.pos_ref, d.cell_of, d.rank, d.nnbr, d.flags,
+                  d.grid, d.bounds, d.cell_count, d.cell_start, d.nbr, ctx->q, ctx->type,
+                  ctx->excl_ptr, ctx->excl_idx, ctx->AB, ctx->ke_scratch, ctx->e_scratch,
+                  ctx->bonds.idx, ctx->bonds.prm, ctx->angles.idx, ctx->angles.prm,
+                  ctx->torsions[0].idx, ctx->torsions[0].term_ptr, ctx->torsions[0].terms,
+                  ctx->torsions[1].idx, ctx->torsions[1].term_ptr, ctx->torsions[1].terms,
+                  ctx->pairs14.idx, ctx->pairs14.prm};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
+  delete static_cast<tmd_ctx_full*>(ctx);
+  return TMD_OK;
+}
+
+int tmd_set_atoms(tmd_ctx* ctx, const float* charges, const int32_t* types, int ntypes,
+                  const float* A, const float* B) {
+  if (!ctx || !charges || !types || ntypes <= 0) return fail(TMD_ERR_ARG, "tmd_set_atoms: bad arguments");
+  DeviceGuard guard(ctx->device);
+  for (int i = 0; i < ctx->natoms; ++i)
+    if (types[i] < 0 || types[i] >= ntypes) return fail(TMD_ERR_ARG, "tmd_set_atoms: atom type out of range");
+  ctx->charges_host.assign(charges, charges + ctx->natoms);
+  int rc;
+  if ((rc = upload(&ctx->type, types, (size_t)ctx->natoms))) return rc;
+  std::vector<float2> ab((size_t)ntypes * ntypes, make_float2(0.f, 0.f));
+  if (A && B)
+    for (size_t t = 0; t < ab.size(); ++t) ab[t] = make_float2(A[t], B[t]);
+  if ((rc = upload(&ctx->AB, ab.data(), ab.size()))) return rc;
+  ctx->d.ntypes = ntypes;
+  ctx->have_atoms = true;
+  priv(ctx).dirty = true;
+  return TMD_OK;
+}
+
+int tmd_set_exclusions(tmd_ctx* ctx, const int64_t* row_ptr, const int32_t* cols) {
+  if (!ctx || !row_ptr) return fail(TMD_ERR_ARG, "tmd_set_exclusions: bad arguments");
+  DeviceGuard guard(ctx->device);
+  const int n = ctx->natoms;
+  if (row_ptr[n] >= (1ll << 31)) return fail(TMD_ERR_ARG, "tmd_set_exclusions: too many entries");
+  std::vector<int> rp(n + 1);
+  for (int i = 0; i <= n; ++i) rp[i] = (int)row_ptr[i];
+  for (int64_t e = 0; e < row_ptr[n]; ++e)
+    if (cols[e] < 0 || cols[e] >= n) return fail(TMD_ERR_ARG, "tmd_set_exclusions: index out of range");
+  int rc;
+  if ((rc = upload(&ctx->excl_ptr, rp.data(), rp.size()))) return rc;
+  if ((rc = upload(&ctx->excl_idx, cols, (size_t)row_ptr[n]))) return rc;
+  ctx->have_excl = row_ptr[n] > 0;
+  priv(ctx).dirty = true;
+  return TMD_OK;
+}
+
+int tmd_set_nonbonded(tmd_ctx* ctx, uint32_t term_mask, double cutoff, double switch_dist, int rfa,
+                      double solvent_dielectric, double coulomb_constant, double skin) {
+  if (!ctx) return fail(TMD_ERR_ARG, "tmd_set_nonbonded: null context");
+  if (rfa && cutoff < 0) return fail(TMD_ERR_ARG, "tmd_set_nonbonded: reaction field needs a cutoff");
+  if (skin < 0) return fail(TMD_ERR_ARG, "tmd_set_nonbonded: negative skin");
+  if (switch_dist >= 0 && cutoff >= 0 && switch_dist >= cutoff)
+    return fail(TMD_ERR_ARG, "tmd_set_nonbonded: switch_dist must be below cutoff");
+  const uint32_t pair_bits = T_ELEC | T_LJ | T_REP | T_REPCG;
+  ctx->pair_mask = term_mask & pair_bits;
+  ctx->bonded_mask = term_mask & ~pair_bits;
+  ctx->cutoff = cutoff;
+  ctx->switch_dist = switch_dist;
+  ctx->rfa = rfa;
+  ctx->coulomb = coulomb_constant;
+  ctx->skin = cutoff >= 0 ? skin : 0.0;
+  PairParams& pp = ctx->d.pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.terms = ctx->pair_mask;
+  pp.has_cutoff = cutoff >= 0;
+  pp.cutoff = pp.has_cutoff ? (float)cutoff : INFINITY;
+  pp.s_max = pp.has_cutoff ? squared_threshold(pp.cutoff) : INFINITY;
+  // the reference switches only when both are given (forces.py:403)
+  pp.has_switch = (switch_dist >= 0 && cutoff >= 0);
+  pp.switch_dist = pp.has_switch ? (float)switch_dist : 0.f;
+  pp.inv_sw_width = pp.has_switch ? (float)(1.0 / (cutoff - switch_dist)) : 0.f;
+  pp.rfa = rfa ? 1 : 0;
+  if (rfa) {  // forces.py:466-468
+    const double denom = 2.0 * solvent_dielectric + 1.0;
+    const double krf = (1.0 / (cutoff * cutoff * cutoff)) * (solvent_dielectric - 1.0) / denom;
+    const double crf = (1.0 / cutoff) * (3.0 * solvent_dielectric) / denom;
+    pp.krf = (float)krf;
+    pp.crf = (float)crf;
+    pp.two_krf = (float)(2.0 * krf);
+  }
+  ctx->have_nonbonded = true;
+  priv(ctx).dirty = true;
+  return TMD_OK;
+}
+
+static int set_bonded(tmd_ctx* ctx, BondedSet& s, int n, int k, int p, const int32_t* idx, const float* prm) {
+  DeviceGuard guard(ctx->device);
+  if (n < 0 || (n > 0 && (!idx || !prm))) return fail(TMD_ERR_ARG, "bonded set: bad arguments");
+  for (long long e = 0; e < (long long)n * k; ++e)
+    if (idx[e] < 0 || idx[e] >= ctx->natoms) return fail(TMD_ERR_ARG, "bonded set: atom index out of range");
+  int rc;
+  if ((rc = upload(&s.idx, idx, (size_t)n * k))) return rc;
+  if ((rc = upload(&s.prm, prm, (size_t)n * p))) return rc;
+  s.n = n;
+  return TMD_OK;
+}
+
+int tmd_set_bonds(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
+  if (!ctx) return fail(TMD_ERR_ARG, "null context");
+  return set_bonded(ctx, ctx->bonds, n, 2, 2, idx, prm);
+}
+int tmd_set_angles(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
+  if (!ctx) return fail(TMD_ERR_ARG, "null context");
+  return set_bonded(ctx, ctx->angles, n, 3, 2, idx, prm);
+}
+int tmd_set_pairs14(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
+  if (!ctx) return fail(TMD_ERR_ARG, "null context");
+  return set_bonded(ctx, ctx->pairs14, n, 2, 4, idx, prm);
+}
+int tmd_set_torsions(tmd_ctx* ctx, int which, int n, const int32_t* idx, const int32_t* term_ptr,
+                     const float* terms, int amber_form) {
+  if (!ctx || which < 0 || which > 1) return fail(TMD_ERR_ARG, "tmd_set_torsions: bad arguments");
+  DeviceGuard guard(ctx->device);
+  BondedSet& s = ctx->torsions[which];
+  if (n < 0 || (n > 0 && (!idx || !term_ptr || !terms))) return fail(TMD_ERR_ARG, "tmd_set_torsions: bad arguments");
+  for (long long e = 0; e < (long long)n * 4; ++e)
+    if (idx[e] < 0 || idx[e] >= ctx->natoms) return fail(TMD_ERR_ARG, "tmd_set_torsions: atom index out of range");
+  int rc;
+  if ((rc = upload(&s.idx, idx, (size_t)n * 4))) return rc;
+  if ((rc = upload(&s.term_ptr, term_ptr, (size_t)(n ? n + 1 : 0)))) return rc;
+  if ((rc = upload(&s.terms, terms, (size_t)(n ? term_ptr[n] : 0) * 3))) return rc;
+  s.n = n;
+  s.amber = amber_form ? 1 : 0;
+  return TMD_OK;
+}
+
+int tmd_set_box(tmd_ctx* ctx, const float* box_diag) {
+  if (!ctx || !box_diag) return fail(TMD_ERR_ARG, "tmd_set_box: bad arguments");
+  int nzero = 0;
+  for (int e = 0; e < ctx->nrep * 3; ++e) {
+    if (!(box_diag[e] >= 0.f)) return fail(TMD_ERR_ARG, "tmd_set_box: negative or NaN box length");
+    nzero += (box_diag[e] == 0.f);
+  }
+  if (nzero != 0 && nzero != ctx->nrep * 3)
+    return fail(TMD_ERR_UNSUPPORTED, "tmd_set_box: box must be all zero (no wrapping) or all positive");
+  ctx->periodic = (nzero == 0);
+  ctx->box_host.assign(box_diag, box_diag + ctx->nrep * 3);
+  ctx->have_box = true;
+  priv(ctx).dirty = true;
+  return TMD_OK;
+}
+
+}  // extern "C"
+
+// ---- finalise: host-side sizing, allocation, uploads (first use / after changes) ----------
+static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
+  if (!ctx->have_atoms) return fail(TMD_ERR_STATE, "tmd_set_atoms has not been called");
+  if (!ctx->have_box) return fail(TMD_ERR_STATE, "tmd_set_box has not been called");
+  if (!ctx->have_nonbonded) return fail(TMD_ERR_STATE, "tmd_set_nonbonded has not been called");
+  TMD_CUDA(cudaStreamSynchronize(stream));
+  DeviceState& d = ctx->d;
+  const int N = ctx->natoms, R = ctx->nrep;
+  int rc;
+
+  // charges carry sqrt(coulomb constant) so q_i*q_j is the full prefactor
+  {
+    std::vector<float> qs(N);
+    const double sk = sqrt(ctx->coulomb > 0 ? ctx->coulomb : 0.0);
+    for (int i = 0; i < N; ++i) qs[i] = (float)((double)ctx->charges_host[i] * sk);
+    if ((rc = upload(&ctx->q, qs.data(), (size_t)N))) return rc;
+  }
+  d.q = ctx->q;
+  d.type = ctx->type;
+  d.AB = ctx->AB;
+  d.excl_ptr = ctx->have_excl ? ctx->excl_ptr : nullptr;
+  d.excl_idx = ctx->have_excl ? ctx->excl_idx : nullptr;
+
+  const bool has_cut = ctx->cutoff >= 0;
+  const double margin = 0.004;  // A: fp32 slack of the approximate build arithmetic and of binning
+  const double rl = has_cut ? ctx->cutoff + ctx->skin + margin : INFINITY;
+  d.rlist = (float)rl;
+  d.rlist2 = has_cut ? (float)(rl * rl) : INFINITY;
+  d.trigger2 = has_cut ? (float)(0.25 * ctx->skin * ctx->skin) : INFINITY;
+
+  // cell grid per replica
+  std::vector<Grid> grids(R);
+  long long max_cells = 1;
+  double max_density = 0.0;
+  for (int r = 0; r < R; ++r) {
+    Grid& g = grids[r];
+    memset(&g, 0, sizeof(g));
+    g.periodic = ctx->periodic ? 1 : 0;
+    g.ncells = 1;
+    double vol = 1.0;
+    for (int k = 0; k < 3; ++k) {
+      const float L = ctx->box_host[r * 3 + k];
+      g.L[k] = L;
+      g.invL[k] = ctx->periodic ? 1.0f / L : 0.f;
+      g.n[k] = 1;
+      g.reach[k] = 0;
+      g.origin[k] = 0.f;
+      g.inv_w[k] = 0.f;
+      if (ctx->periodic && has_cut) {
+        int n = (int)floor((double)L * d.nsub / rl);
+        n = std::min(n, 128);
+        if (n >= 2 * d.nsub + 1) {
+          g.n[k] = n;
+          g.reach[k] = d.nsub;
+          g.inv_w[k] = (float)(n / (double)L);
+        }
+      }
+      g.ncells *= g.n[k];
+      vol *= L;
+    }
+    max_cells = std::max<long long>(max_cells, g.ncells);
+    if (ctx->periodic) max_density = std::max(max_density, N / vol);
+  }
+  if (!ctx->periodic && has_cut) max_cells = 64 * 64 * 64;
+  d.max_cells = (int)max_cells;
+
+  // neighbour row capacity
+  long long cap;
+  if (!has_cut) cap = N;
+  else if (ctx->periodic) cap = (long long)(4.0 / 3.0 * M_PI * rl * rl * rl * max_density * 1.3) + 48;
+  else cap = 512;
+  cap = std::min<long long>(cap, N);
+  if (d.row_cap > cap) cap = d.row_cap;  // keep a capacity grown after an overflow
+  d.row_cap = round_up32(std::max<long long>(cap, 32));
+
+  if (ctx->pair_mask) {
+    const size_t need = (size_t)R * N * d.row_cap;
+    if (need * sizeof(int) > (size_t)96 << 30)
+      return fail(TMD_ERR_UNSUPPORTED, "neighbour list would exceed 96 GiB (no cutoff on a large system?)");
+    if (need != priv(ctx).nbr_entries) {
+      if ((rc = device_alloc(&d.nbr, need))) return rc;
+      priv(ctx).nbr_entries = need;
+    }
+    if ((rc = device_alloc(&d.cell_count, (size_t)R * (max_cells + 1)))) return rc;
+    if ((rc = device_alloc(&d.cell_start, (size_t)R * (max_cells + 1)))) return rc;
+    TMD_CUDA(cudaMemset(d.cell_count, 0, (size_t)R * (max_cells + 1) * sizeof(int)));
+    TMD_CUDA(cudaMemset(d.cell_start, 0, (size_t)R * (max_cells + 1) * sizeof(int)));
+  }
+  TMD_CUDA(cudaMemcpy(d.grid, grids.data(), (size_t)R * sizeof(Grid), cudaMemcpyHostToDevice));
+  TMD_CUDA(cudaMemset(d.pos_ref, 0xFF, (size_t)R * N * sizeof(float4)));  // NaN: forces a build
+  TMD_CUDA(cudaMemset(d.flags, 0, (size_t)R * F_COUNT * sizeof(int)));
+  {
+    std::vector<int> ident((size_t)R * N);
+    for (int r = 0; r < R; ++r)
+      for (int i = 0; i < N; ++i) ident[(size_t)r * N + i] = i;
+    TMD_CUDA(cudaMemcpy(d.inv, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TMD_CUDA(cudaMemcpy(d.perm, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> b((size_t)R * 6);
+    const float pinf = INFINITY, ninf = -INFINITY;
+    int ep, en;
+    memcpy(&ep, &pinf, 4);  // enc(+inf) = bits of +inf
+    memcpy(&en, &ninf, 4);
+    en ^= 0x7fffffff;       // enc of a negative float
+    for (int r = 0; r < R; ++r)
+      for (int k = 0; k < 3; ++k) {
+        b[r * 6 + k] = ep;
+        b[r * 6 + 3 + k] = en;
+      }
+    TMD_CUDA(cudaMemcpy(d.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  ctx->call_index = 0;
+  priv(ctx).dirty = false;
+  return TMD_OK;
+}
+
+static inline dim3 atoms_grid(const tmd_ctx* ctx, int threads) {
+  return dim3((unsigned)((ctx->natoms + threads - 1) / threads), (unsigned)ctx->nrep);
+}
+
+static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, cudaStream_t st) {
+  DeviceState& d = ctx->d;
+  const int N = ctx->natoms, R = ctx->nrep;
+  const int parity = (int)(ctx->call_index & 1);
+  ctx->call_index++;
+  ctx->force_calls++;
+  if (energies) TMD_CUDA(cudaMemsetAsync(energies, 0, (size_t)R * TMD_NUM_ENERGIES * sizeof(double), st));
+
+  if (ctx->pair_mask) {
+    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
+    TMD_LAUNCHED(ctx, "k_prepare");
+    if (!ctx->periodic && ctx->cutoff >= 0) {
+      k_bounds<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
+      TMD_LAUNCHED(ctx, "k_bounds");
+      k_grid<<<(R + 63) / 64, 64, 0, st>>>(d, parity);
+      TMD_LAUNCHED(ctx, "k_grid");
+    }
+    k_bin<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
+    TMD_LAUNCHED(ctx, "k_bin");
+    k_scan<<<R, 1024, 0, st>>>(d, parity);
+    TMD_LAUNCHED(ctx, "k_scan");
+    k_place<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, parity);
+    TMD_LAUNCHED(ctx, "k_place");
+    {
+      const int blocks = std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8));
+      k_sort_pack<<<dim3(blocks, R), 256, 0, st>>>(d, parity);
+      TMD_LAUNCHED(ctx, "k_sort_pack");
+    }
+    k_build_list<<<dim3((N + BUILD_WARPS - 1) / BUILD_WARPS, R), BUILD_WARPS * 32, 0, st>>>(d, parity);
+    TMD_LAUNCHED(ctx, "k_build_list");
+
+    const dim3 pg((N + PAIR_WARPS - 1) / PAIR_WARPS, R);
+    CtxPriv& pv = priv(ctx);
+    const bool sample = pv.profiling && (size_t)(pv.ev_used + 2) <= pv.ev.size();
+    if (sample) TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used], st));
+    if (energies) {
+      if (ctx->periodic) k_pair<true, true><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
+      else k_pair<true, false><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
+    } else {
+      if (ctx->periodic) k_pair<false, true><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
+      else k_pair<false, false><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
+    }
+    TMD_LAUNCHED(ctx, "k_pair");
+    if (sample) {
+      TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used + 1], st));
+      pv.ev_used += 2;
+    }
+  } else {
+    TMD_CUDA(cudaMemsetAsync(forces, 0, (size_t)R * N * 3 * sizeof(float), st));
+  }
+
+  const uint32_t bm = ctx->bonded_mask;
+  auto blocks_for = [&](int n) { return dim3((n + BONDED_THREADS - 1) / BONDED_THREADS, R); };
+  if ((bm & TMD_TERM(TMD_E_BONDS)) && ctx->bonds.n) {
+    k_bonds<<<blocks_for(ctx->bonds.n), BONDED_THREADS, 0, st>>>(d, ctx->bonds, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_bonds");
+  }
+  if ((bm & TMD_TERM(TMD_E_ANGLES)) && ctx->angles.n) {
+    k_angles<<<blocks_for(ctx->angles.n), BONDED_THREADS, 0, st>>>(d, ctx->angles, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_angles");
+  }
+  if ((bm & TMD_TERM(TMD_E_DIHEDRALS)) && ctx->torsions[0].n) {
+    k_torsions<<<blocks_for(ctx->torsions[0].n), BONDED_THREADS, 0, st>>>(d, ctx->torsions[0], TMD_E_DIHEDRALS, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_torsions");
+  }
+  if ((bm & TMD_TERM(TMD_E_14)) && ctx->pairs14.n) {
+    k_pairs14<<<blocks_for(ctx->pairs14.n), BONDED_THREADS, 0, st>>>(d, ctx->pairs14, ctx->q, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_pairs14");
+  }
+  if ((bm & TMD_TERM(TMD_E_IMPROPERS)) && ctx->torsions[1].n) {
+    k_torsions<<<blocks_for(ctx->torsions[1].n), BONDED_THREADS, 0, st>>>(d, ctx->torsions[1], TMD_E_IMPROPERS, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_torsions(impropers)");
+  }
+  return TMD_OK;
+}
+
+static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses,
+                            double dt, cudaStream_t st) {
+  k_vv_first<<<atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, pos, vel, forces, masses,
+                                                                      (float)dt, (float)(0.5 * dt));
+  TMD_LAUNCHED(ctx, "k_vv_first");
+  return TMD_OK;
+}
+
+static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, const float* masses, double dt,
+                             double gamma, const float* vcoeff, const float* noise, uint64_t seed,
+                             uint64_t step, double* ke, cudaStream_t st) {
+  const bool thermo = (gamma >= 0.0) && vcoeff != nullptr;
+  const dim3 g = atoms_grid(ctx, INTEG_THREADS);
+  const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-gamma);
+  if (ke) TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
+  if (thermo) {
+    if (ke) k_vv_second<true, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else k_vv_second<true, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+  } else {
+    if (ke) k_vv_second<false, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else k_vv_second<false, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+  }
+  TMD_LAUNCHED(ctx, "k_vv_second");
+  return TMD_OK;
+}
+
+extern "C" {
+
+int tmd_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, tmd_stream stream) {
+  if (!ctx || !pos || !forces) return fail(TMD_ERR_ARG, "tmd_forces: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (priv(ctx).dirty && (rc = finalize(ctx, st))) return rc;
+  return enqueue_forces(ctx, pos, forces, energies, st);
+}
+
+int tmd_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses, double dt,
+                 tmd_stream stream) {
+  if (!ctx || !pos || !vel || !forces || !masses) return fail(TMD_ERR_ARG, "tmd_vv_first: null pointer");
+  DeviceGuard guard(ctx->device);
+  return enqueue_vv_first(ctx, pos, vel, forces, masses, dt, (cudaStream_t)stream);
+}
+
+int tmd_vv_second(tmd_ctx* ctx, float* vel, const float* forces, const float* masses, double dt, double gamma,
+                  const float* vcoeff, const float* noise, uint64_t seed, uint64_t step_index, double* ke,
+                  tmd_stream stream) {
+  if (!ctx || !vel || !forces || !masses) return fail(TMD_ERR_ARG, "tmd_vv_second: null pointer");
+  DeviceGuard guard(ctx->device);
+  return enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, noise, seed, step_index, ke,
+                           (cudaStream_t)stream);
+}
+
+int tmd_kinetic_energy(tmd_ctx* ctx, const float* vel, const float* masses, double* ke, tmd_stream stream) {
+  if (!ctx || !vel || !masses || !ke) return fail(TMD_ERR_ARG, "tmd_kinetic_energy: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
+  k_kinetic<<<atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, vel, masses, ke);
+  TMD_LAUNCHED(ctx, "k_kinetic");
+  return TMD_OK;
+}
+
+int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces, const float* masses,
+                 double dt, double gamma, const float* vcoeff, const float* noise, uint64_t seed,
+                 uint64_t first_step, double* energies, double* ke, tmd_stream stream) {
+  if (!ctx || !pos || !vel || !forces || !masses || niter < 0) return fail(TMD_ERR_ARG, "tmd_md_steps: bad arguments");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (priv(ctx).dirty && (rc = finalize(ctx, st))) return rc;
+  const size_t per_step = (size_t)ctx->nrep * ctx->natoms * 3;
+  for (int it = 0; it < niter; ++it) {
+    const bool last = (it == niter - 1);
+    if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st))) return rc;
+    if ((rc = enqueue_forces(ctx, pos, forces, last ? energies : nullptr, st))) return rc;
+    if ((rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, noise ? noise + it * per_step : nullptr,
+                                seed, first_step + it, last ? ke : nullptr, st)))
+      return rc;
+  }
+  return TMD_OK;
+}
+
+int tmd_md_steps_host(tmd_ctx* ctx, int niter, float* pos_host, float* vel_host, float* forces_dev,
+                      const float* masses_dev, float* pos_dev, float* vel_dev, double dt, double gamma,
+                      const float* vcoeff_dev, uint64_t seed, uint64_t first_step, double* energies_host,
+                      double* ke_host, tmd_stream stream) {
+  if (!ctx || !pos_host || !vel_host || !pos_dev || !vel_dev) return fail(TMD_ERR_ARG, "tmd_md_steps_host: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)ctx->nrep * ctx->natoms * 3 * sizeof(float);
+  TMD_CUDA(cudaMemcpyAsync(pos_dev, pos_host, bytes, cudaMemcpyHostToDevice, st));
+  TMD_CUDA(cudaMemcpyAsync(vel_dev, vel_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = tmd_md_steps(ctx, niter, pos_dev, vel_dev, forces_dev, masses_dev, dt, gamma, vcoeff_dev, nullptr, seed,
+                        first_step, energies_host ? ctx->e_scratch : nullptr, ke_host ? ctx->ke_scratch : nullptr, stream);
+  if (rc) return rc;
+  TMD_CUDA(cudaMemcpyAsync(pos_host, pos_dev, bytes, cudaMemcpyDeviceToHost, st));
+  TMD_CUDA(cudaMemcpyAsync(vel_host, vel_dev, bytes, cudaMemcpyDeviceToHost, st));
+  if (energies_host)
+    TMD_CUDA(cudaMemcpyAsync(energies_host, ctx->e_scratch, (size_t)ctx->nrep * TMD_NUM_ENERGIES * sizeof(double),
+                             cudaMemcpyDeviceToHost, st));
+  if (ke_host)
+    TMD_CUDA(cudaMemcpyAsync(ke_host, ctx->ke_scratch, (size_t)ctx->nrep * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TMD_CUDA(cudaStreamSynchronize(st));
+  return TMD_OK;
+}
+
+int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs, int64_t capacity,
+                     int64_t* count, tmd_stream stream) {
+  if (!ctx || !pairs || !count || replica < 0 || replica >= ctx->nrep)
+    return fail(TMD_ERR_ARG, "tmd_export_pairs: bad arguments");
+  if (!ctx->pair_mask) return fail(TMD_ERR_STATE, "tmd_export_pairs: no pair term enabled");
+  if (priv(ctx).dirty || ctx->force_calls == 0)
+    return fail(TMD_ERR_STATE, "tmd_export_pairs: call tmd_forces on these positions first");
+  (void)pos;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  TMD_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st));
+  k_export_pairs<<<(ctx->natoms + 3) / 4, 128, 0, st>>>(ctx->d, replica, pairs, (long long)capacity,
+                                                       reinterpret_cast<unsigned long long*>(count));
+  TMD_LAUNCHED(ctx, "k_export_pairs");
+  return TMD_OK;
+}
+
+int tmd_profile_begin(tmd_ctx* ctx, int max_samples) {
+  if (!ctx || max_samples <= 0) return fail(TMD_ERR_ARG, "tmd_profile_begin: bad arguments");
+  DeviceGuard guard(ctx->device);
+  CtxPriv& pv = priv(ctx);
+  while ((int)pv.ev.size() < 2 * max_samples) {
+    cudaEvent_t e;
+    TMD_CUDA(cudaEventCreate(&e));
+    pv.ev.push_back(e);
+  }
+  pv.ev_used = 0;
+  pv.profiling = true;
+  return TMD_OK;
+}
+
+int tmd_profile_end(tmd_ctx* ctx, double* total_ms, int* nsamples, tmd_stream stream) {
+  if (!ctx || !total_ms || !nsamples) return fail(TMD_ERR_ARG, "tmd_profile_end: bad arguments");
+  DeviceGuard guard(ctx->device);
+  CtxPriv& pv = priv(ctx);
+  pv.profiling = false;
+  TMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  double tot = 0.0;
+  for (int k = 0; k + 1 < pv.ev_used; k += 2) {
+    float ms = 0.f;
+    TMD_CUDA(cudaEventElapsedTime(&ms, pv.ev[k], pv.ev[k + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *nsamples = pv.ev_used / 2;
+  pv.ev_used = 0;
+  return TMD_OK;
+}
+
+int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
+  if (!ctx || !out) return fail(TMD_ERR_ARG, "tmd_get_stats: null pointer");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  TMD_CUDA(cudaStreamSynchronize(st));
+  memset(out, 0, sizeof(*out));
+  out->force_calls = ctx->force_calls;
+  out->kernel_launches = ctx->launches;
+  out->row_capacity = ctx->d.row_cap;
+  if (priv(ctx).dirty || !ctx->d.flags) return TMD_OK;
+  std::vector<int> fl((size_t)ctx->nrep * F_COUNT);
+  TMD_CUDA(cudaMemcpy(fl.data(), ctx->d.flags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  Grid g0;
+  TMD_CUDA(cudaMemcpy(&g0, ctx->d.grid, sizeof(Grid), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 3; ++k) out->ncells[k] = g0.n[k];
+  bool overflow = false;
+  for (int r = 0; r < ctx->nrep; ++r) {
+    out->rebuilds += fl[r * F_COUNT + F_NREBUILD];
+    out->max_neighbours = std::max(out->max_neighbours, fl[r * F_COUNT + F_MAXNBR]);
+    overflow |= fl[r * F_COUNT + F_OVERFLOW] != 0;
+  }
+  out->overflow = overflow;
+  if (overflow) {
+    // grow the rows, invalidate the list; the caller recomputes (standalone force call)
+    // or reports the run as invalid (fused multi-step call)
+    ctx->d.row_cap = round_up32((long long)(out->max_neighbours * 1.25) + 32);
+    priv(ctx).dirty = true;
+    return fail(TMD_ERR_OVERFLOW, "neighbour row capacity exceeded; capacity grown, recompute required");
+  }
+  return TMD_OK;
+}
+
+}  // extern "C"
