@@ -234,7 +234,13 @@ class OracleForces:
         solventDielectric=78.5,
         switch_dist=None,
         exclusions=("bonds", "angles", "1-4"),
+        decision_dtype=None,
     ):
+        """``decision_dtype``: evaluate the ``dist <= cutoff`` masks in this dtype (e.g. the
+        reference's fp32 decisions) while the energies/forces use the dtype of ``pos`` --
+        the yardstick for an fp32 kernel: same pair set, exact values.  ``None`` = the
+        reference's behaviour (decisions in the dtype of ``pos``)."""
+        self.decision_dtype = decision_dtype
         self.par = par
         self.terms = [t.lower() for t in terms]
         for t in self.terms:
@@ -265,6 +271,14 @@ class OracleForces:
             return self.pairs
         return self.pairs[dist <= self.cutoff]  # forces.py:77
 
+    def _inside(self, xyz, idx, bd, dist):
+        """dist <= cutoff, decided in ``decision_dtype`` when one is set (forces.py:77)."""
+        dd = self.decision_dtype
+        if dd is None or dd == xyz.dtype:
+            return dist <= self.cutoff
+        d, _, _ = pair_geometry(xyz.to(dd), idx, bd.to(dd))
+        return d <= self.cutoff
+
     def compute(self, pos, box, forces):
         """Fill ``forces`` (R,N,3) in place, return list of {term: float}."""
         par, terms = self.par, self.terms
@@ -291,7 +305,7 @@ class OracleForces:
                 prm = par.bond_params["params"][par.bond_params["map"][:, 1]]
                 dist, unit, _ = pair_geometry(xyz, idx, bd)
                 if self.cutoff is not None:  # bonds are cutoff-filtered too
-                    keep = dist <= self.cutoff
+                    keep = self._inside(xyz, idx, bd, dist)
                     dist, unit, idx, prm = dist[keep], unit[keep], idx[keep], prm[keep]
                 ene, dedr = harmonic_bond(dist, prm)
                 e["bonds"] = e["bonds"] + ene.sum()
@@ -338,7 +352,7 @@ class OracleForces:
                 dist, unit, _ = pair_geometry(xyz, self.pairs, bd)
                 pairs = self.pairs
                 if self.cutoff is not None:
-                    keep = dist <= self.cutoff
+                    keep = self._inside(xyz, pairs, bd, dist)
                     dist, unit, pairs = dist[keep], unit[keep], pairs[keep]
                 ti = par.mapped_atom_types[pairs] if par.mapped_atom_types is not None else None
                 for t in terms:

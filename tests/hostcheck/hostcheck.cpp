@@ -41,13 +41,13 @@ void hc_pair_terms(int n, const float* s, const float* qq, const float* A, const
   pp.two_krf = 2.0f * krf;
   for (int k = 0; k < n; ++k) {
     float a = 0, b = 0, c = 0, d = 0, rinv;
-    dedr[k] = pair_terms(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv);
+    dedr[k] = (terms == (T_LJ | T_ELEC) && has_switch && rfa) ? pair_terms<1>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv) : pair_terms<0>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv);
     e_el[k] = a; e_lj[k] = b; e_rep[k] = c; e_cg[k] = d;
   }
 }
 
 void hc_bond(int n, const float* r, const float* k0, const float* r0, float* e, float* dedr) {
-  for (int k = 0; k < n; ++k) bond_term(r[k], k0[k], r0[k], e[k], dedr[k]);
+  for (int k = 0; k < n; ++k) bond_term<float>(r[k], k0[k], r0[k], e[k], dedr[k]);
 }
 
 void hc_angle(int n, const float* r21, const float* r23, const float* k0, const float* th0, float* e, float* f) {
@@ -65,7 +65,7 @@ void hc_torsion(int n, const float* r12, const float* r23, const float* r34, con
   for (int k = 0; k < n; ++k) {
     Vec3 a = {r12[3 * k], r12[3 * k + 1], r12[3 * k + 2]}, b = {r23[3 * k], r23[3 * k + 1], r23[3 * k + 2]},
          c = {r34[3 * k], r34[3 * k + 1], r34[3 * k + 2]};
-    TorsionGeom g = torsion_geom(a, b, c);
+    TorsionGeom<float> g = torsion_geom(a, b, c);
     float ee = 0, coef = 0;
     for (int m = term_ptr[k]; m < term_ptr[k + 1]; ++m)
       torsion_term(g.phi, terms[3 * m], terms[3 * m + 1], terms[3 * m + 2], amber, ee, coef);

@@ -1,10 +1,16 @@
 // bonded.cuh -- bonded terms (K4): bonds, angles, proper/improper torsions, 1-4.
 //
 // Replaces forces.py:122-258 (+ evaluate_bonds/angles/torsion, forces.py:494-605).
-// One thread per term instance, original atom order, forces accumulated with
-// fp32 atomics AFTER the pair kernel has written the non-bonded force (so the
-// pair kernel's plain store doubles as the zeroing of Forces.compute,
-// forces.py:113-114).  These are O(N) and a few percent of the pair work.
+//
+// Atom-centric and deterministic: one thread per ATOM walks the list of bonded term
+// instances the atom takes part in (CSR built once on the host from the topology),
+// re-evaluates each term, keeps the force on its own atom, and adds the sum to the
+// force array with a plain read-modify-write -- no atomics, fixed summation order,
+// bitwise reproducible.  Every term is evaluated once per participating atom (2-4x
+// redundant arithmetic on an O(N) workload that is a few percent of the pair kernel);
+// its energy is booked by the atom in slot 0 only.  Runs AFTER the pair kernel, whose
+// plain store of the non-bonded force doubles as the zeroing of Forces.compute
+// (forces.py:113-114).
 #pragma once
 #include "context.cuh"
 #include "pair.cuh"
@@ -12,6 +18,15 @@
 namespace tmd {
 
 constexpr int BONDED_THREADS = 128;
+
+// kinds of term instance an atom entry can point at
+enum { BK_BOND = 0, BK_ANGLE = 1, BK_DIHEDRAL = 2, BK_IMPROPER = 3, BK_PAIR14 = 4 };
+
+struct BondedTables {
+  const int* atom_ptr;   // (natoms+1) CSR over atoms
+  const int* entries;    // packed: kind (3 bits) | slot in the term (2 bits) | term index (27 bits)
+  BondedSet bonds, angles, torsions[2], pairs14;
+};
 
 struct BoxView {
   int periodic;
@@ -28,135 +43,101 @@ __device__ __forceinline__ BoxView box_of(const DeviceState& S, int r) {
 __device__ __forceinline__ Vec3 load3(const float* p, size_t atom) {
   return {p[atom * 3 + 0], p[atom * 3 + 1], p[atom * 3 + 2]};
 }
-__device__ __forceinline__ void add3(float* f, size_t atom, Vec3 v) {
-  atomicAdd(f + atom * 3 + 0, v.x);
-  atomicAdd(f + atom * 3 + 1, v.y);
-  atomicAdd(f + atom * 3 + 2, v.z);
-}
 
-// bonds: E = k (r-r0)^2; bonds longer than the cutoff are skipped like the
-// reference does (forces.py:128-136).
 __global__ void __launch_bounds__(BONDED_THREADS)
-k_bonds(DeviceState S, BondedSet B, const float* __restrict__ pos, float* __restrict__ forces,
-        double* __restrict__ energies) {
+k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, const float* __restrict__ pos,
+         float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t base = (size_t)r * S.natoms;
-  float e = 0.f;
-  if (t < B.n) {
+  double e_bond = 0., e_angle = 0., e_dih = 0., e_imp = 0., e_lj = 0., e_el = 0.;
+  if (a < S.natoms) {
     const BoxView bx = box_of(S, r);
-    const int i = B.idx[2 * t], j = B.idx[2 * t + 1];
-    const Vec3 d = delta_ref(load3(pos, base + i), load3(pos, base + j), bx.periodic, bx.L, bx.invL);
-    const float dist = sqrt_rn(norm2_ref(d.x, d.y, d.z));
-    if (!S.pp.has_cutoff || dist <= S.pp.cutoff) {
-      float dedr;
-      bond_term(dist, B.prm[2 * t], B.prm[2 * t + 1], e, dedr);
-      const Vec3 fv = (dedr / dist) * d;
-      add3(forces, base + i, -1.0f * fv);
-      add3(forces, base + j, fv);
+    Vec3d f = {0., 0., 0.};
+    for (int p = T.atom_ptr[a]; p < T.atom_ptr[a + 1]; ++p) {
+      const unsigned ent = (unsigned)T.entries[p];
+      const int kind = ent >> 29, slot = (ent >> 27) & 3, t = ent & 0x7ffffff;
+      if (kind == BK_BOND) {
+        // E = k (r-r0)^2; bonds longer than the cutoff are skipped like the reference (forces.py:128-136)
+        const int i = T.bonds.idx[2 * t], j = T.bonds.idx[2 * t + 1];
+        const Vec3 pi = load3(pos, base + i), pj = load3(pos, base + j);
+        const Vec3 dref = delta_ref(pi, pj, bx.periodic, bx.L, bx.invL);
+        if (!S.pp.has_cutoff || sqrt_rn(norm2_ref(dref.x, dref.y, dref.z)) <= S.pp.cutoff) {  // reference decision
+          const Vec3d d = delta_f64(pi, pj, bx.periodic, bx.L);
+          const double dist = norm(d);
+          double e, dedr;
+          bond_term<double>(dist, T.bonds.prm[2 * t], T.bonds.prm[2 * t + 1], e, dedr);
+          const Vec3d fv = (dedr / dist) * d;  // force on j; i gets the opposite
+          f = slot == 0 ? f - fv : f + fv;
+          if (slot == 0) e_bond += e;
+        }
+      } else if (kind == BK_ANGLE) {
+        const int a0 = T.angles.idx[3 * t], a1 = T.angles.idx[3 * t + 1], a2 = T.angles.idx[3 * t + 2];
+        const Vec3 p1 = load3(pos, base + a1);
+        const Vec3d r21 = delta_f64(load3(pos, base + a0), p1, bx.periodic, bx.L);
+        const Vec3d r23 = delta_f64(load3(pos, base + a2), p1, bx.periodic, bx.L);
+        Vec3d f0, f1, f2;
+        const double e = angle_term<double>(r21, r23, T.angles.prm[2 * t], T.angles.prm[2 * t + 1], f0, f1, f2);
+        f = f + (slot == 0 ? f0 : (slot == 1 ? f1 : f2));
+        if (slot == 0) e_angle += e;
+      } else if (kind == BK_DIHEDRAL || kind == BK_IMPROPER) {
+        const BondedSet& B = T.torsions[kind == BK_IMPROPER];
+        const Vec3 p0 = load3(pos, base + B.idx[4 * t]), p1 = load3(pos, base + B.idx[4 * t + 1]);
+        const Vec3 p2 = load3(pos, base + B.idx[4 * t + 2]), p3 = load3(pos, base + B.idx[4 * t + 3]);
+        const Vec3d r12 = delta_f64(p0, p1, bx.periodic, bx.L);
+        const Vec3d r23 = delta_f64(p1, p2, bx.periodic, bx.L);
+        const Vec3d r34 = delta_f64(p2, p3, bx.periodic, bx.L);
+        const TorsionGeom<double> g = torsion_geom(r12, r23, r34);
+        double e = 0., coef = 0.;
+        for (int m = B.term_ptr[t]; m < B.term_ptr[t + 1]; ++m)
+          torsion_term<double>(g.phi, B.terms[3 * m], B.terms[3 * m + 1], B.terms[3 * m + 2], B.amber, e, coef);
+        Vec3d f0, f1, f2, f3;
+        torsion_forces(g, coef, f0, f1, f2, f3);
+        f = f + (slot == 0 ? f0 : (slot == 1 ? f1 : (slot == 2 ? f2 : f3)));
+        if (slot == 0) {
+          if (kind == BK_IMPROPER) e_imp += e;
+          else e_dih += e;
+        }
+      } else {  // BK_PAIR14 (forces.py:185-236): LJ/scnb with no cutoff or switch, Coulomb/scee, never RF
+        const int i = T.pairs14.idx[2 * t], j = T.pairs14.idx[2 * t + 1];
+        const Vec3d d = delta_f64(load3(pos, base + i), load3(pos, base + j), bx.periodic, bx.L);
+        const double dist = norm(d);
+        const double rinv = 1.0 / dist;
+        const float* prm = T.pairs14.prm + 4 * t;  // A, B, scnb, scee
+        double dedr = 0.;
+        if (S.pp.terms & T_LJ) {
+          const double r6 = rinv * rinv * rinv * rinv * rinv * rinv;
+          const double a12 = prm[0] * r6 * r6, b6 = prm[1] * r6;
+          if (slot == 0) e_lj += (a12 - b6) / prm[2];
+          dedr += (6.0 * b6 - 12.0 * a12) * rinv / prm[2];
+        }
+        if (S.pp.terms & T_ELEC) {
+          const double e = (double)q_scaled[i] * (double)q_scaled[j] * rinv / prm[3];
+          if (slot == 0) e_el += e;
+          dedr -= e * rinv;
+        }
+        const Vec3d fv = (dedr * rinv) * d;
+        f = slot == 0 ? f - fv : f + fv;
+      }
     }
-  }
-  if (energies) {
-    __shared__ double red[BONDED_THREADS / 32];
-    block_accumulate<BONDED_THREADS / 32>((double)e, energies + (size_t)r * TMD_NUM_ENERGIES + TMD_E_BONDS, red);
-  }
-}
-
-__global__ void __launch_bounds__(BONDED_THREADS)
-k_angles(DeviceState S, BondedSet B, const float* __restrict__ pos, float* __restrict__ forces,
-         double* __restrict__ energies) {
-  const int r = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t base = (size_t)r * S.natoms;
-  float e = 0.f;
-  if (t < B.n) {
-    const BoxView bx = box_of(S, r);
-    const int a0 = B.idx[3 * t], a1 = B.idx[3 * t + 1], a2 = B.idx[3 * t + 2];
-    const Vec3 p1 = load3(pos, base + a1);
-    const Vec3 r21 = delta_ref(load3(pos, base + a0), p1, bx.periodic, bx.L, bx.invL);
-    const Vec3 r23 = delta_ref(load3(pos, base + a2), p1, bx.periodic, bx.L, bx.invL);
-    Vec3 f0, f1, f2;
-    e = angle_term(r21, r23, B.prm[2 * t], B.prm[2 * t + 1], f0, f1, f2);
-    add3(forces, base + a0, f0);
-    add3(forces, base + a1, f1);
-    add3(forces, base + a2, f2);
-  }
-  if (energies) {
-    __shared__ double red[BONDED_THREADS / 32];
-    block_accumulate<BONDED_THREADS / 32>((double)e, energies + (size_t)r * TMD_NUM_ENERGIES + TMD_E_ANGLES, red);
-  }
-}
-
-// proper dihedrals (slot TMD_E_DIHEDRALS) and impropers (slot TMD_E_IMPROPERS)
-__global__ void __launch_bounds__(BONDED_THREADS)
-k_torsions(DeviceState S, BondedSet B, int slot, const float* __restrict__ pos,
-           float* __restrict__ forces, double* __restrict__ energies) {
-  const int r = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t base = (size_t)r * S.natoms;
-  float e = 0.f;
-  if (t < B.n) {
-    const BoxView bx = box_of(S, r);
-    const int a0 = B.idx[4 * t], a1 = B.idx[4 * t + 1], a2 = B.idx[4 * t + 2], a3 = B.idx[4 * t + 3];
-    const Vec3 p0 = load3(pos, base + a0), p1 = load3(pos, base + a1);
-    const Vec3 p2 = load3(pos, base + a2), p3 = load3(pos, base + a3);
-    const Vec3 r12 = delta_ref(p0, p1, bx.periodic, bx.L, bx.invL);
-    const Vec3 r23 = delta_ref(p1, p2, bx.periodic, bx.L, bx.invL);
-    const Vec3 r34 = delta_ref(p2, p3, bx.periodic, bx.L, bx.invL);
-    const TorsionGeom g = torsion_geom(r12, r23, r34);
-    float coef = 0.f;
-    for (int m = B.term_ptr[t]; m < B.term_ptr[t + 1]; ++m)
-      torsion_term(g.phi, B.terms[3 * m], B.terms[3 * m + 1], B.terms[3 * m + 2], B.amber, e, coef);
-    Vec3 f0, f1, f2, f3;
-    torsion_forces(g, coef, f0, f1, f2, f3);
-    add3(forces, base + a0, f0);
-    add3(forces, base + a1, f1);
-    add3(forces, base + a2, f2);
-    add3(forces, base + a3, f3);
-  }
-  if (energies) {
-    __shared__ double red[BONDED_THREADS / 32];
-    block_accumulate<BONDED_THREADS / 32>((double)e, energies + (size_t)r * TMD_NUM_ENERGIES + slot, red);
-  }
-}
-
-// 1-4 pairs (forces.py:185-236): LJ scaled by 1/scnb with no cutoff and no switch,
-// Coulomb scaled by 1/scee and never reaction-field; energies are booked under the
-// lj / electrostatics slots, the "1-4" slot stays zero.
-__global__ void __launch_bounds__(BONDED_THREADS)
-k_pairs14(DeviceState S, BondedSet B, const float* __restrict__ q_scaled,
-          const float* __restrict__ pos, float* __restrict__ forces, double* __restrict__ energies) {
-  const int r = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t base = (size_t)r * S.natoms;
-  float e_lj = 0.f, e_el = 0.f;
-  if (t < B.n) {
-    const BoxView bx = box_of(S, r);
-    const int i = B.idx[2 * t], j = B.idx[2 * t + 1];
-    const Vec3 d = delta_ref(load3(pos, base + i), load3(pos, base + j), bx.periodic, bx.L, bx.invL);
-    const float dist = sqrt_rn(norm2_ref(d.x, d.y, d.z));
-    const float rinv = 1.0f / dist;
-    const float A = B.prm[4 * t], Bc = B.prm[4 * t + 1], scnb = B.prm[4 * t + 2], scee = B.prm[4 * t + 3];
-    float dedr = 0.f;
-    if (S.pp.terms & T_LJ) {
-      const float r6 = rinv * rinv * rinv * rinv * rinv * rinv;
-      const float a12 = A * r6 * r6, b6 = Bc * r6;
-      e_lj = (a12 - b6) / scnb;
-      dedr += (6.0f * b6 - 12.0f * a12) * rinv / scnb;
+    if (T.atom_ptr[a + 1] > T.atom_ptr[a]) {
+      float* out = forces + (base + a) * 3;
+      out[0] = (float)((double)out[0] + f.x);
+      out[1] = (float)((double)out[1] + f.y);
+      out[2] = (float)((double)out[2] + f.z);
     }
-    if (S.pp.terms & T_ELEC) {
-      e_el = q_scaled[i] * q_scaled[j] * rinv / scee;
-      dedr -= e_el * rinv;
-    }
-    const Vec3 fv = (dedr * rinv) * d;
-    add3(forces, base + i, -1.0f * fv);
-    add3(forces, base + j, fv);
   }
   if (energies) {
     __shared__ double red[BONDED_THREADS / 32];
     double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
-    if (S.pp.terms & T_LJ) block_accumulate<BONDED_THREADS / 32>((double)e_lj, E + TMD_E_LJ, red);
-    if (S.pp.terms & T_ELEC) block_accumulate<BONDED_THREADS / 32>((double)e_el, E + TMD_E_ELECTROSTATICS, red);
+    if (T.bonds.n) block_accumulate<BONDED_THREADS / 32>(e_bond, E + TMD_E_BONDS, red);
+    if (T.angles.n) block_accumulate<BONDED_THREADS / 32>(e_angle, E + TMD_E_ANGLES, red);
+    if (T.torsions[0].n) block_accumulate<BONDED_THREADS / 32>(e_dih, E + TMD_E_DIHEDRALS, red);
+    if (T.torsions[1].n) block_accumulate<BONDED_THREADS / 32>(e_imp, E + TMD_E_IMPROPERS, red);
+    if (T.pairs14.n) {
+      if (S.pp.terms & T_LJ) block_accumulate<BONDED_THREADS / 32>(e_lj, E + TMD_E_LJ, red);
+      if (S.pp.terms & T_ELEC) block_accumulate<BONDED_THREADS / 32>(e_el, E + TMD_E_ELECTROSTATICS, red);
+    }
   }
 }
 

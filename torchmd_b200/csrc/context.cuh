@@ -31,7 +31,7 @@ enum {
   F_OVERFLOW = 2,
   F_NREBUILD = 3,
   F_MAXNBR = 4,
-  F_BADCELL = 5,
+  F_FARPOS = 5,    // a position was further than 2000 box lengths from the origin
   F_COUNT = 8
 };
 
@@ -41,6 +41,7 @@ struct DeviceState {
   int row_cap;      // neighbour entries reserved per atom
   int max_cells;    // capacity of the cell arrays per replica
   int nsub;         // cells per list radius
+  int check_far;    // flag positions beyond 2000 box lengths (guard-free minimum image in use)
   // per-atom static data (original order)
   const float* q;        // charge * sqrt(coulomb constant)
   const int* type;       // atom type id
@@ -52,6 +53,7 @@ struct DeviceState {
   // per replica dynamic data (index [rep*natoms + k])
   float4* xq_s;          // sorted: raw x,y,z + scaled charge
   int* type_s;           // sorted atom type
+  float4* xw_s;          // sorted: coordinates folded into the box at the last build (list build only)
   int* perm;             // sorted slot -> original atom
   int* inv;              // original atom -> sorted slot
   float4* pos_ref;       // positions at the last rebuild (original order)
@@ -93,12 +95,18 @@ struct tmd_ctx {
   int* excl_idx = nullptr;
   float2* AB = nullptr;
   tmd::BondedSet bonds, angles, torsions[2], pairs14;
+  std::vector<int32_t> bonds_idx_h, angles_idx_h, torsions_idx_h[2], pairs14_idx_h;  // host copies for the atom CSR
+  int* bonded_atom_ptr = nullptr;    // device CSR: atom -> bonded term entries (see bonded.cuh)
+  int* bonded_entries = nullptr;
+  int bonded_nentries = 0;
   uint32_t bonded_mask = 0;   // which bonded energy terms are enabled
   uint32_t pair_mask = 0;
   double coulomb = 0.0, cutoff = -1.0, switch_dist = -1.0, skin = 0.0;
   int rfa = 0;
   bool have_atoms = false, have_nonbonded = false, have_box = false, have_excl = false;
   bool periodic = false;
+  bool safe_image = false;           // guard-free minimum image valid (see min_image_fast)
+  int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
   std::vector<float> box_host;       // (nrep,3)
   std::vector<float> charges_host;   // unscaled charges
   uint64_t call_index = 0;           // parity selects the rebuild flag

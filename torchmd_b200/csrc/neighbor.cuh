@@ -66,6 +66,11 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int pari
   if (!(d2 <= S.trigger2)) {  // also true for NaN (= no list yet)
     if (fl[F_REBUILD0 + parity] == 0) fl[F_REBUILD0 + parity] = 1;
   }
+  if (S.check_far) {
+    const Grid* g = S.grid + r;
+    if (!(fabsf(x) < 2000.f * g->L[0]) || !(fabsf(y) < 2000.f * g->L[1]) || !(fabsf(z) < 2000.f * g->L[2]))
+      fl[F_FARPOS] = 1;
+  }
   const int k = S.inv[a];
   S.xq_s[(size_t)r * S.natoms + k] = make_float4(x, y, z, S.q[i]);
 }
@@ -197,6 +202,9 @@ __global__ void k_sort_pack(DeviceState S, int parity) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
   const int ncells = S.grid[r].ncells;
+  const int gper = S.grid[r].periodic;
+  const float gL0 = S.grid[r].L[0], gL1 = S.grid[r].L[1], gL2 = S.grid[r].L[2];
+  const float giL0 = S.grid[r].invL[0], giL1 = S.grid[r].invL[1], giL2 = S.grid[r].invL[2];
   const size_t base = (size_t)r * S.natoms;
   int* perm = S.perm + base;
   int* tmp = S.rank + base;  // free after k_place
@@ -230,98 +238,207 @@ __global__ void k_sort_pack(DeviceState S, int parity) {
       S.inv[base + i] = b + e;
       S.xq_s[base + b + e] = make_float4(p.x, p.y, p.z, S.q[i]);
       S.type_s[base + b + e] = S.type[i];
+      float wx = p.x, wy = p.y, wz = p.z;  // coordinates folded into [0, L] for the list build
+      if (gper) {
+        wx -= gL0 * floorf(wx * giL0);
+        wy -= gL1 * floorf(wy * giL1);
+        wz -= gL2 * floorf(wz * giL2);
+      }
+      S.xw_s[base + b + e] = make_float4(wx, wy, wz, 0.f);
     }
   }
 }
 
 // ---- rebuild: Verlet list ---------------------------------------------------------------
-// One warp per (sorted) atom.  Candidates come from the (2*reach+1)^3 surrounding
-// cells; cells adjacent in x are adjacent in memory, so each (dz,dy) row is one or two
-// contiguous runs of sorted atoms read with coalesced 16-byte loads.  The distance
-// test here is approximate and generous (rlist carries a safety margin); the exact
-// reference predicate is applied by the pair kernel.
-constexpr int BUILD_WARPS = 4;
-__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_list(DeviceState S, int parity) {
+// One CTA per cell.  The atoms of the (2*reach+1)^3 surrounding cells are staged in
+// shared memory once per cell, already shifted by the periodic image of their cell, so
+// the inner loop is a bare distance test on shared-memory operands: no per-pair minimum
+// image, no per-atom cell arithmetic, no global gathers.  Cells adjacent in x are
+// adjacent in memory, so every (dz,dy) row is one or two contiguous runs copied with
+// coalesced 16-byte loads.  Each warp then takes atoms of the cell in turn and appends
+// the accepted partners (sorted indices) to the atom's 128-byte-aligned row.  The test
+// is generous (rlist carries a safety margin); the exact reference predicate is applied
+// by the pair kernel.  Row order is fixed by the run order: deterministic.
+constexpr int BT_WARPS = 8;
+constexpr int BT_TILE = 2048;   // candidates staged per pass (32 KB)
+constexpr int BT_MAXRUN = 64;   // (2*2+1)^2 rows x 2 segments = 50
+constexpr int BT_MAXI = 256;    // atoms of the cell handled per pass
+
+struct Run {
+  int a0, len;
+  float sx, sy, sz;
+};
+
+template <bool WRAP>
+__device__ __forceinline__ void build_process_tile(const DeviceState& S, const Grid& g, size_t base,
+                                                   const float4* tile, int fill, int b0, int nib, int* counts,
+                                                   bool w0, bool w1, bool w2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const float rl2 = S.rlist2;
+  for (int ii = warp; ii < nib; ii += BT_WARPS) {
+    const int k = b0 + ii;
+    const float4 pi = S.xw_s[base + k];
+    // exclusions of this atom as sorted indices, one per lane; [exlo, exhi] bounds them so
+    // that the (rare) chunks which can contain one are the only ones paying for the test
+    int ne = 0, my_excl = -1, exlo = 0x7fffffff, exhi = -1;
+    if (S.excl_ptr) {
+      const int io = S.perm[base + k];
+      const int e0 = S.excl_ptr[io];
+      ne = S.excl_ptr[io + 1] - e0;
+      for (int eb = 0; eb < ne; eb += 32) {  // more than 32 exclusions: bounds over all, lanes keep the first 32
+        const int v = (eb + lane < ne) ? S.inv[base + S.excl_idx[e0 + eb + lane]] : -1;
+        if (eb == 0) my_excl = v;
+        if (v >= 0) { exlo = min(exlo, v); exhi = max(exhi, v); }
+      }
+      for (int o = 16; o; o >>= 1) {
+        exlo = min(exlo, __shfl_xor_sync(0xffffffffu, exlo, o));
+        exhi = max(exhi, __shfl_xor_sync(0xffffffffu, exhi, o));
+      }
+    }
+    int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+    int count = counts[ii];
+#pragma unroll 1
+    for (int c0 = 0; c0 < fill; c0 += 32) {
+      const int c = c0 + lane;
+      bool ok = false;
+      int j = -2;
+      if (c < fill) {
+        const float4 pj = tile[c];
+        j = __float_as_int(pj.w);
+        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (WRAP) {  // a dimension too short for cells: one cell spans it, fold per pair
+          if (w0) dx -= g.L[0] * rintf(dx * g.invL[0]);
+          if (w1) dy -= g.L[1] * rintf(dy * g.invL[1]);
+          if (w2) dz -= g.L[2] * rintf(dz * g.invL[2]);
+        }
+        ok = (dx * dx + dy * dy + dz * dz <= rl2) && (j != k);
+      }
+      if (__any_sync(0xffffffffu, ok && j >= exlo && j <= exhi)) {
+        const int nfast = min(ne, 32);
+#pragma unroll 1
+        for (int e = 0; e < nfast; ++e)
+          if (__shfl_sync(0xffffffffu, my_excl, e) == j) ok = false;
+        if (ne > 32) {
+          const int e0 = S.excl_ptr[S.perm[base + k]];
+#pragma unroll 1
+          for (int e = 32; e < ne; ++e)
+            if (S.inv[base + S.excl_idx[e0 + e]] == j) ok = false;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int slot = count + __popc(m & lt);
+        if (slot < S.row_cap) row[slot] = j;
+      }
+      count += __popc(m);
+    }
+    if (lane == 0) counts[ii] = count;
+  }
+}
+
+__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int parity) {
   const int r = blockIdx.y;
   int* fl = S.flags + r * F_COUNT;
   if (!fl[F_REBUILD0 + parity]) return;
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fl + F_NREBUILD, 1);
-  if (k >= S.natoms) return;
+  __shared__ float4 tile[BT_TILE];
+  __shared__ Run runs[BT_MAXRUN];
+  __shared__ int roff[BT_MAXRUN + 1];  // exclusive prefix of the run lengths
+  __shared__ int counts[BT_MAXI];
   const Grid g = S.grid[r];
   const size_t base = (size_t)r * S.natoms;
-  const float4* __restrict__ xq = S.xq_s + base;
-  const int* __restrict__ perm = S.perm + base;
+  const float4* __restrict__ xw = S.xw_s + base;
   const int* __restrict__ start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+  const bool w0 = g.periodic && g.n[0] == 1, w1 = g.periodic && g.n[1] == 1, w2 = g.periodic && g.n[2] == 1;
+  const int tid = threadIdx.x, nthr = BT_WARPS * 32;
+  const int ny = 2 * g.reach[1] + 1, nz = 2 * g.reach[2] + 1;
+  const int nrows = ny * nz;  // <= 25, two run slots each
 
-  const int io = perm[k];
-  const int c = S.cell_of[base + io];
-  const int cx = c % g.n[0], cy = (c / g.n[0]) % g.n[1], cz = c / (g.n[0] * g.n[1]);
-  const float4 pi = xq[k];
-  const int e0 = S.excl_ptr ? S.excl_ptr[io] : 0;
-  const int ne = S.excl_ptr ? S.excl_ptr[io + 1] - e0 : 0;
-  const int my_excl = (lane < ne) ? S.excl_idx[e0 + lane] : -1;
-  const unsigned lt = (1u << lane) - 1u;
-  int count = 0;
-
-  for (int dz = -g.reach[2]; dz <= g.reach[2]; ++dz) {
-    int z2 = cz + dz;
-    if (g.periodic) z2 = (z2 + g.n[2]) % g.n[2];
-    else if (z2 < 0 || z2 >= g.n[2]) continue;
-    for (int dy = -g.reach[1]; dy <= g.reach[1]; ++dy) {
-      int y2 = cy + dy;
-      if (g.periodic) y2 = (y2 + g.n[1]) % g.n[1];
-      else if (y2 < 0 || y2 >= g.n[1]) continue;
-      const int rowbase = (z2 * g.n[1] + y2) * g.n[0];
-      int lo = cx - g.reach[0], hi = cx + g.reach[0];
-      int seg_lo[2], seg_hi[2], nseg = 1;
-      if (g.periodic) {
-        if (lo < 0) { seg_lo[0] = lo + g.n[0]; seg_hi[0] = g.n[0] - 1; seg_lo[1] = 0; seg_hi[1] = hi; nseg = 2; }
-        else if (hi >= g.n[0]) { seg_lo[0] = lo; seg_hi[0] = g.n[0] - 1; seg_lo[1] = 0; seg_hi[1] = hi - g.n[0]; nseg = 2; }
-        else { seg_lo[0] = lo; seg_hi[0] = hi; }
-      } else {
-        seg_lo[0] = max(lo, 0);
-        seg_hi[0] = min(hi, g.n[0] - 1);
-      }
-      for (int sgm = 0; sgm < nseg; ++sgm) {
-        const int a0 = start[rowbase + seg_lo[sgm]], a1 = start[rowbase + seg_hi[sgm] + 1];
-        for (int j0 = a0; j0 < a1; j0 += 32) {
-          const int j = j0 + lane;
-          bool ok = (j < a1) && (j != k);
-          if (ok) {
-            const float4 pj = xq[j];
-            float dx = pi.x - pj.x, dy2 = pi.y - pj.y, dz2 = pi.z - pj.z;
-            if (g.periodic) {
-              dx -= g.L[0] * rintf(dx * g.invL[0]);
-              dy2 -= g.L[1] * rintf(dy2 * g.invL[1]);
-              dz2 -= g.L[2] * rintf(dz2 * g.invL[2]);
-            }
-            ok = (dx * dx + dy2 * dy2 + dz2 * dz2) <= S.rlist2;
+  for (int c = blockIdx.x; c < g.ncells; c += gridDim.x) {
+    const int b0c = start[c], ni = start[c + 1] - b0c;
+    if (ni == 0) continue;  // block-uniform
+    __syncthreads();        // previous cell's shared state no longer in use
+    // ---- run table: one thread per (dz,dy) row of neighbour cells, all loads in flight together
+    if (tid < BT_MAXRUN / 2) {
+      Run ra = {0, 0, 0.f, 0.f, 0.f}, rb = {0, 0, 0.f, 0.f, 0.f};
+      if (tid < nrows) {
+        const int cx = c % g.n[0], cy = (c / g.n[0]) % g.n[1], cz = c / (g.n[0] * g.n[1]);
+        int z2 = cz + tid / ny - g.reach[2], y2 = cy + tid % ny - g.reach[1];
+        float sz = 0.f, sy = 0.f;
+        bool valid = true;
+        if (g.periodic) {
+          if (z2 < 0) { z2 += g.n[2]; sz = -g.L[2]; } else if (z2 >= g.n[2]) { z2 -= g.n[2]; sz = g.L[2]; }
+          if (y2 < 0) { y2 += g.n[1]; sy = -g.L[1]; } else if (y2 >= g.n[1]) { y2 -= g.n[1]; sy = g.L[1]; }
+        } else {
+          valid = z2 >= 0 && z2 < g.n[2] && y2 >= 0 && y2 < g.n[1];
+        }
+        if (valid) {
+          const int rowbase = (z2 * g.n[1] + y2) * g.n[0];
+          const int lo = cx - g.reach[0], hi = cx + g.reach[0];
+          int alo = lo, ahi = hi, blo = 0, bhi = -1;
+          float asx = 0.f, bsx = 0.f;
+          if (g.periodic) {
+            if (lo < 0) { alo = lo + g.n[0]; ahi = g.n[0] - 1; asx = -g.L[0]; blo = 0; bhi = hi; }
+            else if (hi >= g.n[0]) { alo = lo; ahi = g.n[0] - 1; blo = 0; bhi = hi - g.n[0]; bsx = g.L[0]; }
+          } else {
+            alo = max(lo, 0);
+            ahi = min(hi, g.n[0] - 1);
           }
-          if (ne > 0) {  // warp-uniform
-            const int oj = ok ? perm[j] : -2;
-            const int nfast = min(ne, 32);
-            for (int e = 0; e < nfast; ++e)
-              if (__shfl_sync(0xffffffffu, my_excl, e) == oj) ok = false;
-            for (int e = 32; e < ne; ++e)
-              if (S.excl_idx[e0 + e] == oj) ok = false;
+          const int a0 = start[rowbase + alo], a1 = start[rowbase + ahi + 1];
+          ra = {a0, a1 - a0, asx, sy, sz};
+          if (bhi >= blo) {
+            const int c0 = start[rowbase + blo], c1 = start[rowbase + bhi + 1];
+            rb = {c0, c1 - c0, bsx, sy, sz};
           }
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (ok) {
-            const int slot = count + __popc(m & lt);
-            if (slot < S.row_cap) row[slot] = j;
-          }
-          count += __popc(m);
         }
       }
+      runs[2 * tid] = ra;
+      runs[2 * tid + 1] = rb;
+      // exclusive scan of the 64 lengths by the first warp (two per lane)
+      const int l0 = ra.len, l1 = rb.len;
+      int incl = l0 + l1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      roff[2 * tid] = incl - l0 - l1;
+      roff[2 * tid + 1] = incl - l1;
+      if (tid == 31) roff[BT_MAXRUN] = incl;
     }
-  }
-  if (lane == 0) {
-    S.nnbr[base + k] = min(count, S.row_cap);
-    if (count > S.row_cap) fl[F_OVERFLOW] = 1;
-    if (count > fl[F_MAXNBR]) atomicMax(fl + F_MAXNBR, count);
+    __syncthreads();
+    const int M = roff[BT_MAXRUN];
+    for (int i0 = 0; i0 < ni; i0 += BT_MAXI) {
+      const int nib = min(BT_MAXI, ni - i0);
+      const int b0 = b0c + i0;
+      for (int t = tid; t < nib; t += nthr) counts[t] = 0;
+      for (int t0 = 0; t0 < M; t0 += BT_TILE) {
+        const int fill = min(BT_TILE, M - t0);
+        __syncthreads();  // tile free, counts initialised
+        for (int u = tid; u < fill; u += nthr) {
+          const int slot = t0 + u;
+          int q = 0;  // binary search: last run with roff[q] <= slot
+#pragma unroll
+          for (int step = BT_MAXRUN / 2; step; step >>= 1)
+            if (roff[q + step] <= slot) q += step;
+          const Run rn = runs[q];
+          const int j = rn.a0 + (slot - roff[q]);
+          const float4 p = xw[j];
+          tile[u] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j));
+        }
+        __syncthreads();
+        if (w0 || w1 || w2) build_process_tile<true>(S, g, base, tile, fill, b0, nib, counts, w0, w1, w2);
+        else build_process_tile<false>(S, g, base, tile, fill, b0, nib, counts, w0, w1, w2);
+      }
+      __syncthreads();
+      for (int t = tid; t < nib; t += nthr) {
+        const int cnt = counts[t];
+        S.nnbr[base + b0 + t] = min(cnt, S.row_cap);
+        if (cnt > S.row_cap) fl[F_OVERFLOW] = 1;
+        if (cnt > fl[F_MAXNBR]) atomicMax(fl + F_MAXNBR, cnt);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -350,7 +467,7 @@ __global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long
       const int j = row[e];
       const float4 pj = xq[j];
       float dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
-      if (g.periodic) {
+      if (g.periodic) {  // always the guarded (exact) form here
         dx = min_image(dx, g.L[0], g.invL[0]);
         dy = min_image(dy, g.L[1], g.invL[1]);
         dz = min_image(dz, g.L[2], g.invL[2]);

@@ -44,7 +44,10 @@ __device__ __forceinline__ void block_accumulate(double v, double* dst, double* 
   }
 }
 
-template <bool ENERGY, bool PERIODIC>
+// ENERGY   also accumulate the per-term energies (only the last step of a fused run needs them)
+// PERIODIC minimum image on; SAFE: guard-free minimum image (see min_image_fast)
+// MODE     0 = pair terms selected at run time, 1 = LJ+switch + reaction-field Coulomb
+template <bool ENERGY, bool PERIODIC, bool SAFE, int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
@@ -62,7 +65,7 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
     const int n = S.nnbr[base + k];
     const float4 pi = xq[k];
     const int ti = types[k] * S.ntypes;
-    const bool need_ab = (pp.terms & (T_LJ | T_REP | T_REPCG)) != 0;
+    const bool need_ab = MODE == 1 ? true : (pp.terms & (T_LJ | T_REP | T_REPCG)) != 0;
     float Lx = 0.f, Ly = 0.f, Lz = 0.f, iLx = 0.f, iLy = 0.f, iLz = 0.f;
     if (PERIODIC) {
       const Grid* g = S.grid + r;
@@ -70,27 +73,58 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
       iLx = g->invL[0]; iLy = g->invL[1]; iLz = g->invL[2];
     }
     float fx = 0.f, fy = 0.f, fz = 0.f;
-#pragma unroll 2
-    for (int e = lane; e < n; e += 32) {
-      const int j = __ldcs(row + e);  // streamed once per step: do not keep in L1
+
+    // One interaction of atom i with listed partner j (j < 0: padding lane).
+    auto interact = [&](int j) {
+      if (j < 0) return;
       const float4 pj = xq[j];
-      float dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
+      const float dx0 = sub_rn(pi.x, pj.x), dy0 = sub_rn(pi.y, pj.y), dz0 = sub_rn(pi.z, pj.z);
+      float wx = dx0, wy = dy0, wz = dz0;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
       if (PERIODIC) {
-        dx = min_image(dx, Lx, iLx);
-        dy = min_image(dy, Ly, iLy);
-        dz = min_image(dz, Lz, iLz);
+        if (SAFE) {
+          wx = min_image_fast(dx0, Lx, iLx, rx);
+          wy = min_image_fast(dy0, Ly, iLy, ry);
+          wz = min_image_fast(dz0, Lz, iLz, rz);
+        } else {
+          wx = min_image_exact(dx0, Lx, iLx, rx);
+          wy = min_image_exact(dy0, Ly, iLy, ry);
+          wz = min_image_exact(dz0, Lz, iLz, rz);
+        }
       }
-      const float s = norm2_ref(dx, dy, dz);
+      float s = norm2_ref(wx, wy, wz);  // the reference's own rounding: decides in/out
       if (s <= pp.s_max) {
+        if (PERIODIC && (rx != 0.f || ry != 0.f || rz != 0.f)) {
+          // straddles the box: give the VALUES the bits fl(pi-pj) dropped (sub_err)
+          wx += sub_err(pi.x, pj.x, dx0);
+          wy += sub_err(pi.y, pj.y, dy0);
+          wz += sub_err(pi.z, pj.z, dz0);
+          s = wx * wx + wy * wy + wz * wz;
+        }
         float2 ab = make_float2(0.f, 0.f);
         if (need_ab) ab = __ldg(S.AB + ti + types[j]);
         float rinv;
-        const float dedr = pair_terms(pp, s, pi.w * pj.w, ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
+        const float dedr = pair_terms<MODE>(pp, s, pi.w * pj.w, ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
         const float c = dedr * rinv;  // force on i is -unit*dE/dr = -(w/r) dE/dr
-        fx -= dx * c;
-        fy -= dy * c;
-        fz -= dz * c;
+        fx -= wx * c;
+        fy -= wy * c;
+        fz -= wz * c;
       }
+    };
+
+    // The row streams from HBM exactly once per step: load it two iterations ahead of
+    // its use (evict-first), so DRAM latency overlaps the arithmetic of earlier pairs.
+    int e = lane;
+    int j0 = (e < n) ? __ldcs(row + e) : -1;
+    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    while (e < n) {
+      const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+      const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+      interact(j0);
+      interact(j1);
+      j0 = jn0;
+      j1 = jn1;
+      e += 64;
     }
     fx = warp_sum(fx);
     fy = warp_sum(fy);
@@ -105,11 +139,12 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
   if (ENERGY) {
     __shared__ double red[PAIR_WARPS];
     double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
+    const uint32_t terms = MODE == 1 ? (T_LJ | T_ELEC) : pp.terms;
     // every pair is visited from both of its atoms
-    if (pp.terms & T_ELEC) block_accumulate<PAIR_WARPS>(0.5 * (double)e_el, E + TMD_E_ELECTROSTATICS, red);
-    if (pp.terms & T_LJ) block_accumulate<PAIR_WARPS>(0.5 * (double)e_lj, E + TMD_E_LJ, red);
-    if (pp.terms & T_REP) block_accumulate<PAIR_WARPS>(0.5 * (double)e_rep, E + TMD_E_REPULSION, red);
-    if (pp.terms & T_REPCG) block_accumulate<PAIR_WARPS>(0.5 * (double)e_cg, E + TMD_E_REPULSIONCG, red);
+    if (terms & T_ELEC) block_accumulate<PAIR_WARPS>(0.5 * (double)e_el, E + TMD_E_ELECTROSTATICS, red);
+    if (terms & T_LJ) block_accumulate<PAIR_WARPS>(0.5 * (double)e_lj, E + TMD_E_LJ, red);
+    if (terms & T_REP) block_accumulate<PAIR_WARPS>(0.5 * (double)e_rep, E + TMD_E_REPULSION, red);
+    if (terms & T_REPCG) block_accumulate<PAIR_WARPS>(0.5 * (double)e_cg, E + TMD_E_REPULSIONCG, red);
   }
 }
 

@@ -104,13 +104,47 @@ TMD_HD float rsqrt_refined(float a) {
 // from a rounding boundary (and small enough for the trick) it provably equals
 // rint(div_rn(d, L)), because |d*fl(1/L) - div_rn(d,L)| < 2^-22 |q| < 1e-3 for
 // |q| < 4096.  Otherwise the true IEEE division is taken.  L*r and the final
-// subtraction are single rounded ops like torch's.
-TMD_HD float min_image(float d, float L, float invL) {
+// subtraction are single rounded ops like torch's.  `r` returns the image count.
+TMD_HD float min_image_exact(float d, float L, float invL, float& r) {
   const float magic = 12582912.0f;  // 1.5 * 2^23
   float q = d * invL;
-  float r = sub_rn(add_rn(q, magic), magic);
+  r = sub_rn(add_rn(q, magic), magic);
   if (!(fabsf(q - r) < 0.45f) || !(fabsf(q) < 4096.0f)) r = rintf(div_rn(d, L));
   return sub_rn(d, mul_rn(L, r));
+}
+// Same result without the guard, valid when the caller guarantees |w| < 0.45 L and
+// |d| < 4096 L for every pair it sees: the host checks  cutoff + 2*skin < 0.45 * min(L)
+// (listed pairs cannot be further apart) and k_prepare flags positions beyond 2000 L.
+TMD_HD float min_image_fast(float d, float L, float invL, float& r) {
+  const float magic = 12582912.0f;
+  r = sub_rn(add_rn(d * invL, magic), magic);
+  return sub_rn(d, mul_rn(L, r));
+}
+TMD_HD float min_image(float d, float L, float invL) {
+  float r;
+  return min_image_exact(d, L, invL, r);
+}
+
+// Exact rounding error of d = fl(a - b)  (Knuth TwoSum on a + (-b)): a - b == d + err.
+// Across the periodic boundary a - b is ~L and loses up to ulp(L)/2 (4e-6 A for
+// L ~ 100 A); with a force gradient of ~40 kcal/mol/A^2 on a hydrogen bond that alone
+// is 1.5e-4 kcal/mol/A -- the dominant error of the reference's own fp32 path.  The
+// cutoff DECISION keeps the reference's rounded value; the force VALUES add err back.
+TMD_HD float sub_err(float a, float b, float d) {
+  float a1 = add_rn(d, b);
+  float c1 = sub_rn(d, a1);
+  float da = sub_rn(a, a1);
+  return sub_rn(da, add_rn(b, c1));
+}
+
+TMD_HD float rcp_refined(float a) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+  return fmaf(y, fmaf(-a, y, 1.0f), y);  // one Newton step: ~0.5 ulp, no slow path
+#else
+  return 1.0f / a;
+#endif
 }
 
 // Largest fp32 s with sqrt_rn(s) <= rc: turns the reference's `dist <= cutoff` into a
@@ -159,21 +193,30 @@ enum : uint32_t {
 // Returns dE/dr summed over the enabled terms; energies are ADDED to e_lj / e_el /
 // e_rep / e_repcg.  Follows forces.py:381-491 including the reference's switched
 // LJ force  s*dE/dr + E*s'/r  (the extra 1/r is the reference's, forces.py:410-412).
+// MODE 0: terms chosen at run time from pp;  MODE 1: LJ with switch + reaction-field
+// electrostatics (the production water/protein set-up) resolved at compile time.
+template <int MODE>
 TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float B,
                         float& e_el, float& e_lj, float& e_rep, float& e_repcg,
                         float& rinv_out) {
+  const bool do_lj = MODE == 1 ? true : (pp.terms & T_LJ) != 0;
+  const bool do_el = MODE == 1 ? true : (pp.terms & T_ELEC) != 0;
+  const bool do_rep = MODE == 1 ? false : (pp.terms & T_REP) != 0;
+  const bool do_cg = MODE == 1 ? false : (pp.terms & T_REPCG) != 0;
+  const bool sw_on = MODE == 1 ? true : pp.has_switch != 0;
+  const bool rf_on = MODE == 1 ? true : pp.rfa != 0;
   float rinv = rsqrt_refined(s);
   float r = s * rinv;
-  float rinv2 = rcp_rn(s);  // correctly rounded: the high powers below inherit 3x, not 6x, its error
+  float rinv2 = rcp_refined(s);  // ~0.5 ulp: the high powers below inherit 3x, not 6x, its error
   float rinv6 = rinv2 * rinv2 * rinv2;
   float dedr = 0.0f;
   rinv_out = rinv;
-  if (pp.terms & T_LJ) {
+  if (do_lj) {
     float a12 = A * rinv6 * rinv6;
     float b6 = B * rinv6;
     float e = a12 - b6;
     float f = (6.0f * b6 - 12.0f * a12) * rinv;
-    if (pp.has_switch) {
+    if (sw_on) {
       // branch-free: t = 0 below the switch distance gives sw = 1, dsw = 0
       float t = fmaxf((r - pp.switch_dist) * pp.inv_sw_width, 0.0f);
       float sw = 1.0f + t * t * t * (-10.0f + t * (15.0f - t * 6.0f));
@@ -184,8 +227,8 @@ TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float 
     e_lj += e;
     dedr += f;
   }
-  if (pp.terms & T_ELEC) {
-    if (pp.rfa) {
+  if (do_el) {
+    if (rf_on) {
       e_el += qq * (rinv + pp.krf * s - pp.crf);
       dedr += qq * (pp.two_krf * r - rinv2);
     } else {
@@ -194,12 +237,12 @@ TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float 
       dedr -= e * rinv;
     }
   }
-  if (pp.terms & T_REP) {
+  if (do_rep) {
     float a12 = A * rinv6 * rinv6;
     e_rep += a12;
     dedr -= 12.0f * a12 * rinv;
   }
-  if (pp.terms & T_REPCG) {
+  if (do_cg) {
     float b6 = B * rinv6;
     e_repcg += b6;
     dedr -= 6.0f * b6 * rinv;
@@ -208,19 +251,26 @@ TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float 
 }
 
 // ---- bonded terms --------------------------------------------------------------------
-struct Vec3 {
-  float x, y, z;
+// Templated on the real type: the bonded kernel evaluates them in fp64 (they are O(N),
+// a few percent of the pair work, and a stiff bond turns the 6e-8 A rounding of an fp32
+// bond length into a 5e-5 kcal/mol/A force error: 2k = 900 kcal/mol/A^2 for O-H),
+// the host unit tests also in fp32.
+template <typename T>
+struct Vec3T {
+  T x, y, z;
 };
-TMD_HD Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-TMD_HD Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-TMD_HD Vec3 operator*(float s, Vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
-TMD_HD float dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-TMD_HD Vec3 cross(Vec3 a, Vec3 b) {
+using Vec3 = Vec3T<float>;
+using Vec3d = Vec3T<double>;
+template <typename T> TMD_HD Vec3T<T> operator+(Vec3T<T> a, Vec3T<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> TMD_HD Vec3T<T> operator-(Vec3T<T> a, Vec3T<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> TMD_HD Vec3T<T> operator*(T s, Vec3T<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T> TMD_HD T dot(Vec3T<T> a, Vec3T<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> TMD_HD Vec3T<T> cross(Vec3T<T> a, Vec3T<T> b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-TMD_HD float norm(Vec3 a) { return sqrtf(dot(a, a)); }
+template <typename T> TMD_HD T norm(Vec3T<T> a) { return sqrt(dot(a, a)); }
 
-// Minimum-image difference of two positions, reference rounding.
+// Minimum-image difference of two positions, reference rounding (decisions).
 TMD_HD Vec3 delta_ref(Vec3 a, Vec3 b, int periodic, Vec3 L, Vec3 invL) {
   Vec3 d = {sub_rn(a.x, b.x), sub_rn(a.y, b.y), sub_rn(a.z, b.z)};
   if (periodic) {
@@ -231,79 +281,97 @@ TMD_HD Vec3 delta_ref(Vec3 a, Vec3 b, int periodic, Vec3 L, Vec3 invL) {
   return d;
 }
 
+// The same difference for VALUE arithmetic in fp64: exact subtraction of the fp32
+// inputs, minimum image with the fp32 box length.
+TMD_HD Vec3d delta_f64(Vec3 a, Vec3 b, int periodic, Vec3 L) {
+  Vec3d d = {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+  if (periodic) {
+    d.x -= (double)L.x * rint(d.x / (double)L.x);
+    d.y -= (double)L.y * rint(d.y / (double)L.y);
+    d.z -= (double)L.z * rint(d.z / (double)L.z);
+  }
+  return d;
+}
+
 // Harmonic bond (forces.py:494-503): E = k (r-r0)^2, dE/dr = 2k (r-r0).
-TMD_HD void bond_term(float r, float k, float r0, float& e, float& dedr) {
-  float x = r - r0;
+template <typename T>
+TMD_HD void bond_term(T r, T k, T r0, T& e, T& dedr) {
+  T x = r - r0;
   e = k * x * x;
-  dedr = 2.0f * k * x;
+  dedr = T(2) * k * x;
 }
 
 // Harmonic angle (forces.py:506-539).  r21 = p0-p1, r23 = p2-p1.
-TMD_HD float angle_term(Vec3 r21, Vec3 r23, float k, float theta0, Vec3& f0, Vec3& f1, Vec3& f2) {
-  float inv21 = 1.0f / norm(r21);
-  float inv23 = 1.0f / norm(r23);
-  float c = dot(r23, r21) * inv21 * inv23;
-  c = fminf(fmaxf(c, -1.0f), 1.0f);
-  float dth = acosf(c) - theta0;
-  float sn = sqrtf(1.0f - c * c);
-  float coef = (sn != 0.0f) ? (-2.0f * k * dth / sn) : 0.0f;  // zero force at sin==0
+template <typename T>
+TMD_HD T angle_term(Vec3T<T> r21, Vec3T<T> r23, T k, T theta0, Vec3T<T>& f0, Vec3T<T>& f1, Vec3T<T>& f2) {
+  T inv21 = T(1) / norm(r21);
+  T inv23 = T(1) / norm(r23);
+  T c = dot(r23, r21) * inv21 * inv23;
+  c = c < T(-1) ? T(-1) : (c > T(1) ? T(1) : c);
+  T dth = acos(c) - theta0;
+  T sn = sqrt(T(1) - c * c);
+  T coef = (sn != T(0)) ? (T(-2) * k * dth / sn) : T(0);  // zero force at sin==0
   f0 = (coef * inv21) * ((c * inv21) * r21 - inv23 * r23);
   f2 = (coef * inv23) * ((c * inv23) * r23 - inv21 * r21);
-  f1 = -1.0f * (f0 + f2);
+  f1 = T(-1) * (f0 + f2);
   return k * dth * dth;
 }
 
 // Torsion angle phi = -atan2(sin, cos) (forces.py:544-553) and the geometric
 // factors the force projection needs.
+template <typename T>
 struct TorsionGeom {
-  Vec3 cA, cB;
-  float nA2, nB2, n23, g1, g2, phi;
+  Vec3T<T> cA, cB;
+  T nA2, nB2, n23, g1, g2, phi;
 };
-TMD_HD TorsionGeom torsion_geom(Vec3 r12, Vec3 r23, Vec3 r34) {
-  TorsionGeom g;
+template <typename T>
+TMD_HD TorsionGeom<T> torsion_geom(Vec3T<T> r12, Vec3T<T> r23, Vec3T<T> r34) {
+  TorsionGeom<T> g;
   g.cA = cross(r12, r23);
   g.cB = cross(r23, r34);
-  Vec3 cC = cross(r23, g.cA);
-  float nA = norm(g.cA), nB = norm(g.cB), nC = norm(cC);
-  Vec3 uB = (1.0f / nB) * g.cB;
-  float cosphi = dot(g.cA, uB) / nA;
-  float sinphi = dot(cC, uB) / nC;
-  g.phi = -atan2f(sinphi, cosphi);
+  Vec3T<T> cC = cross(r23, g.cA);
+  T nA = norm(g.cA), nB = norm(g.cB), nC = norm(cC);
+  Vec3T<T> uB = (T(1) / nB) * g.cB;
+  T cosphi = dot(g.cA, uB) / nA;
+  T sinphi = dot(cC, uB) / nC;
+  g.phi = -atan2(sinphi, cosphi);
   g.nA2 = nA * nA;
   g.nB2 = nB * nB;
-  float n23sq = dot(r23, r23);
-  g.n23 = sqrtf(n23sq);
+  T n23sq = dot(r23, r23);
+  g.n23 = sqrt(n23sq);
   g.g1 = dot(r12, r23) / n23sq;
   g.g2 = dot(r34, r23) / n23sq;
   return g;
 }
 // One torsion term: energy and dE/dphi-like coefficient (forces.py:566-579).
-TMD_HD void torsion_term(float phi, float k, float phi0, float per, int amber_form, float& e,
-                         float& coef) {
+template <typename T>
+TMD_HD void torsion_term(T phi, T k, T phi0, T per, int amber_form, T& e, T& coef) {
   if (amber_form) {
-    float a = per * phi - phi0;
-    e += k * (1.0f + cosf(a));
-    coef += -per * k * sinf(a);
+    T a = per * phi - phi0;
+    e += k * (T(1) + cos(a));
+    coef += -per * k * sin(a);
   } else {
-    const float pi = 3.14159265358979323846f;
-    float a = phi - phi0;
-    if (a < -pi) a += 2.0f * pi;
-    else if (a > pi) a -= 2.0f * pi;
+    const T pi = T(3.14159265358979323846);
+    T a = phi - phi0;
+    if (a < -pi) a += T(2) * pi;
+    else if (a > pi) a -= T(2) * pi;
     e += k * a * a;
-    coef += 2.0f * k * a;
+    coef += T(2) * k * a;
   }
 }
 // Force projection (forces.py:584-603).
-TMD_HD void torsion_forces(const TorsionGeom& g, float coef, Vec3& f0, Vec3& f1, Vec3& f2, Vec3& f3) {
-  float ff0 = (-coef * g.n23) / g.nA2;
-  float ff3 = (coef * g.n23) / g.nB2;
-  Vec3 v0 = ff0 * g.cA;
-  Vec3 v3 = ff3 * g.cB;
-  Vec3 s = g.g1 * v0 - g.g2 * v3;
-  f0 = -1.0f * v0;
+template <typename T>
+TMD_HD void torsion_forces(const TorsionGeom<T>& g, T coef, Vec3T<T>& f0, Vec3T<T>& f1, Vec3T<T>& f2,
+                           Vec3T<T>& f3) {
+  T ff0 = (-coef * g.n23) / g.nA2;
+  T ff3 = (coef * g.n23) / g.nB2;
+  Vec3T<T> v0 = ff0 * g.cA;
+  Vec3T<T> v3 = ff3 * g.cB;
+  Vec3T<T> s = g.g1 * v0 - g.g2 * v3;
+  f0 = T(-1) * v0;
   f1 = v0 + s;
   f2 = v3 - s;
-  f3 = -1.0f * v3;
+  f3 = T(-1) * v3;
 }
 
 }  // namespace tmd

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -119,6 +120,7 @@ int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   int rc = TMD_OK;
   if ((rc = device_alloc(&d.xq_s, RN))) return rc;
   if ((rc = device_alloc(&d.type_s, RN))) return rc;
+  if ((rc = device_alloc(&d.xw_s, RN))) return rc;
   if ((rc = device_alloc(&d.perm, RN))) return rc;
   if ((rc = device_alloc(&d.inv, RN))) return rc;
   if ((rc = device_alloc(&d.pos_ref, RN))) return rc;
@@ -141,13 +143,13 @@ int tmd_destroy(tmd_ctx* ctx) {
   if (!ctx) return TMD_OK;
   DeviceGuard guard(ctx->device);
   DeviceState& d = ctx->d;
-  void* bufs[] = {d.xq_s, d.type_s, d.perm, d.inv, d.pos_ref, d.cell_of, d.rank, d.nnbr, d.flags,
+  void* bufs[] = {d.xq_s, d.xw_s, d.type_s, d.perm, d.inv, d.pos_ref, d.cell_of, d.rank, d.nnbr, d.flags,
                   d.grid, d.bounds, d.cell_count, d.cell_start, d.nbr, ctx->q, ctx->type,
                   ctx->excl_ptr, ctx->excl_idx, ctx->AB, ctx->ke_scratch, ctx->e_scratch,
                   ctx->bonds.idx, ctx->bonds.prm, ctx->angles.idx, ctx->angles.prm,
                   ctx->torsions[0].idx, ctx->torsions[0].term_ptr, ctx->torsions[0].terms,
                   ctx->torsions[1].idx, ctx->torsions[1].term_ptr, ctx->torsions[1].terms,
-                  ctx->pairs14.idx, ctx->pairs14.prm};
+                  ctx->pairs14.idx, ctx->pairs14.prm, ctx->bonded_atom_ptr, ctx->bonded_entries};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
@@ -230,7 +232,8 @@ int tmd_set_nonbonded(tmd_ctx* ctx, uint32_t term_mask, double cutoff, double sw
   return TMD_OK;
 }
 
-static int set_bonded(tmd_ctx* ctx, BondedSet& s, int n, int k, int p, const int32_t* idx, const float* prm) {
+static int set_bonded(tmd_ctx* ctx, BondedSet& s, std::vector<int32_t>& idx_h, int n, int k, int p,
+                      const int32_t* idx, const float* prm) {
   DeviceGuard guard(ctx->device);
   if (n < 0 || (n > 0 && (!idx || !prm))) return fail(TMD_ERR_ARG, "bonded set: bad arguments");
   for (long long e = 0; e < (long long)n * k; ++e)
@@ -239,20 +242,22 @@ static int set_bonded(tmd_ctx* ctx, BondedSet& s, int n, int k, int p, const int
   if ((rc = upload(&s.idx, idx, (size_t)n * k))) return rc;
   if ((rc = upload(&s.prm, prm, (size_t)n * p))) return rc;
   s.n = n;
+  idx_h.assign(idx, idx + (size_t)n * k);
+  priv(ctx).dirty = true;
   return TMD_OK;
 }
 
 int tmd_set_bonds(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
   if (!ctx) return fail(TMD_ERR_ARG, "null context");
-  return set_bonded(ctx, ctx->bonds, n, 2, 2, idx, prm);
+  return set_bonded(ctx, ctx->bonds, ctx->bonds_idx_h, n, 2, 2, idx, prm);
 }
 int tmd_set_angles(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
   if (!ctx) return fail(TMD_ERR_ARG, "null context");
-  return set_bonded(ctx, ctx->angles, n, 3, 2, idx, prm);
+  return set_bonded(ctx, ctx->angles, ctx->angles_idx_h, n, 3, 2, idx, prm);
 }
 int tmd_set_pairs14(tmd_ctx* ctx, int n, const int32_t* idx, const float* prm) {
   if (!ctx) return fail(TMD_ERR_ARG, "null context");
-  return set_bonded(ctx, ctx->pairs14, n, 2, 4, idx, prm);
+  return set_bonded(ctx, ctx->pairs14, ctx->pairs14_idx_h, n, 2, 4, idx, prm);
 }
 int tmd_set_torsions(tmd_ctx* ctx, int which, int n, const int32_t* idx, const int32_t* term_ptr,
                      const float* terms, int amber_form) {
@@ -268,6 +273,8 @@ int tmd_set_torsions(tmd_ctx* ctx, int which, int n, const int32_t* idx, const i
   if ((rc = upload(&s.terms, terms, (size_t)(n ? term_ptr[n] : 0) * 3))) return rc;
   s.n = n;
   s.amber = amber_form ? 1 : 0;
+  ctx->torsions_idx_h[which].assign(idx, idx + (size_t)n * 4);
+  priv(ctx).dirty = true;
   return TMD_OK;
 }
 
@@ -355,6 +362,16 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   if (!ctx->periodic && has_cut) max_cells = 64 * 64 * 64;
   d.max_cells = (int)max_cells;
 
+  // guard-free minimum image is valid iff no listed pair can be further than 0.45 L apart
+  ctx->safe_image = false;
+  if (ctx->periodic && has_cut) {
+    float lmin = INFINITY;
+    for (int e = 0; e < R * 3; ++e) lmin = std::min(lmin, ctx->box_host[e]);
+    ctx->safe_image = (ctx->cutoff + 2.0 * ctx->skin + 2.0 * margin) < 0.45 * (double)lmin;
+  }
+  d.check_far = ctx->safe_image ? 1 : 0;
+  ctx->pair_mode = (ctx->pair_mask == (T_LJ | T_ELEC) && d.pp.has_switch && d.pp.rfa) ? 1 : 0;
+
   // neighbour row capacity
   long long cap;
   if (!has_cut) cap = N;
@@ -399,9 +416,56 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       }
     TMD_CUDA(cudaMemcpy(d.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  // atom -> bonded term entries (kind | slot | term), fixed order: deterministic bonded forces
+  {
+    const uint32_t bm = ctx->bonded_mask;
+    struct Src { int kind, k; const std::vector<int32_t>* idx; bool on; };
+    const Src src[5] = {
+        {BK_BOND, 2, &ctx->bonds_idx_h, (bm & TMD_TERM(TMD_E_BONDS)) != 0},
+        {BK_ANGLE, 3, &ctx->angles_idx_h, (bm & TMD_TERM(TMD_E_ANGLES)) != 0},
+        {BK_DIHEDRAL, 4, &ctx->torsions_idx_h[0], (bm & TMD_TERM(TMD_E_DIHEDRALS)) != 0},
+        {BK_PAIR14, 2, &ctx->pairs14_idx_h, (bm & TMD_TERM(TMD_E_14)) != 0},
+        {BK_IMPROPER, 4, &ctx->torsions_idx_h[1], (bm & TMD_TERM(TMD_E_IMPROPERS)) != 0}};
+    std::vector<int> ptr(N + 1, 0);
+    for (const Src& sc : src)
+      if (sc.on)
+        for (int32_t a : *sc.idx) ptr[a + 1]++;
+    for (int i = 0; i < N; ++i) ptr[i + 1] += ptr[i];
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1), ent(ptr[N]);
+    for (const Src& sc : src) {
+      if (!sc.on) continue;
+      const size_t nt = sc.idx->size() / sc.k;
+      if (nt >= (1u << 27)) return fail(TMD_ERR_UNSUPPORTED, "more than 2^27 bonded terms of one kind");
+      for (size_t t = 0; t < nt; ++t)
+        for (int sl = 0; sl < sc.k; ++sl)
+          ent[fill[(*sc.idx)[t * sc.k + sl]]++] = (int)(((unsigned)sc.kind << 29) | ((unsigned)sl << 27) | (unsigned)t);
+    }
+    ctx->bonded_nentries = ptr[N];
+    if ((rc = upload(&ctx->bonded_atom_ptr, ptr.data(), ptr.size()))) return rc;
+    if ((rc = upload(&ctx->bonded_entries, ent.data(), ent.size()))) return rc;
+  }
   ctx->call_index = 0;
   priv(ctx).dirty = false;
   return TMD_OK;
+}
+
+template <bool E, bool P, bool SAFE>
+static void launch_pair_mode(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
+  if (ctx->pair_mode == 1) k_pair<E, P, SAFE, 1><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
+  else k_pair<E, P, SAFE, 0><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
+}
+static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
+  const bool e = energies != nullptr;
+  if (!ctx->periodic) {
+    if (e) launch_pair_mode<true, false, false>(ctx, pg, st, forces, energies);
+    else launch_pair_mode<false, false, false>(ctx, pg, st, forces, energies);
+  } else if (ctx->safe_image) {
+    if (e) launch_pair_mode<true, true, true>(ctx, pg, st, forces, energies);
+    else launch_pair_mode<false, true, true>(ctx, pg, st, forces, energies);
+  } else {
+    if (e) launch_pair_mode<true, true, false>(ctx, pg, st, forces, energies);
+    else launch_pair_mode<false, true, false>(ctx, pg, st, forces, energies);
+  }
 }
 
 static inline dim3 atoms_grid(const tmd_ctx* ctx, int threads) {
@@ -436,20 +500,14 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       k_sort_pack<<<dim3(blocks, R), 256, 0, st>>>(d, parity);
       TMD_LAUNCHED(ctx, "k_sort_pack");
     }
-    k_build_list<<<dim3((N + BUILD_WARPS - 1) / BUILD_WARPS, R), BUILD_WARPS * 32, 0, st>>>(d, parity);
+    k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, st>>>(d, parity);
     TMD_LAUNCHED(ctx, "k_build_list");
 
     const dim3 pg((N + PAIR_WARPS - 1) / PAIR_WARPS, R);
     CtxPriv& pv = priv(ctx);
     const bool sample = pv.profiling && (size_t)(pv.ev_used + 2) <= pv.ev.size();
     if (sample) TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used], st));
-    if (energies) {
-      if (ctx->periodic) k_pair<true, true><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
-      else k_pair<true, false><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
-    } else {
-      if (ctx->periodic) k_pair<false, true><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
-      else k_pair<false, false><<<pg, PAIR_WARPS * 32, 0, st>>>(d, forces, energies);
-    }
+    launch_pair(ctx, pg, st, forces, energies);
     TMD_LAUNCHED(ctx, "k_pair");
     if (sample) {
       TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used + 1], st));
@@ -459,27 +517,23 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     TMD_CUDA(cudaMemsetAsync(forces, 0, (size_t)R * N * 3 * sizeof(float), st));
   }
 
-  const uint32_t bm = ctx->bonded_mask;
-  auto blocks_for = [&](int n) { return dim3((n + BONDED_THREADS - 1) / BONDED_THREADS, R); };
-  if ((bm & TMD_TERM(TMD_E_BONDS)) && ctx->bonds.n) {
-    k_bonds<<<blocks_for(ctx->bonds.n), BONDED_THREADS, 0, st>>>(d, ctx->bonds, pos, forces, energies);
-    TMD_LAUNCHED(ctx, "k_bonds");
-  }
-  if ((bm & TMD_TERM(TMD_E_ANGLES)) && ctx->angles.n) {
-    k_angles<<<blocks_for(ctx->angles.n), BONDED_THREADS, 0, st>>>(d, ctx->angles, pos, forces, energies);
-    TMD_LAUNCHED(ctx, "k_angles");
-  }
-  if ((bm & TMD_TERM(TMD_E_DIHEDRALS)) && ctx->torsions[0].n) {
-    k_torsions<<<blocks_for(ctx->torsions[0].n), BONDED_THREADS, 0, st>>>(d, ctx->torsions[0], TMD_E_DIHEDRALS, pos, forces, energies);
-    TMD_LAUNCHED(ctx, "k_torsions");
-  }
-  if ((bm & TMD_TERM(TMD_E_14)) && ctx->pairs14.n) {
-    k_pairs14<<<blocks_for(ctx->pairs14.n), BONDED_THREADS, 0, st>>>(d, ctx->pairs14, ctx->q, pos, forces, energies);
-    TMD_LAUNCHED(ctx, "k_pairs14");
-  }
-  if ((bm & TMD_TERM(TMD_E_IMPROPERS)) && ctx->torsions[1].n) {
-    k_torsions<<<blocks_for(ctx->torsions[1].n), BONDED_THREADS, 0, st>>>(d, ctx->torsions[1], TMD_E_IMPROPERS, pos, forces, energies);
-    TMD_LAUNCHED(ctx, "k_torsions(impropers)");
+  if (ctx->bonded_nentries > 0) {
+    const uint32_t bm = ctx->bonded_mask;
+    BondedTables T;
+    T.atom_ptr = ctx->bonded_atom_ptr;
+    T.entries = ctx->bonded_entries;
+    T.bonds = ctx->bonds;
+    T.angles = ctx->angles;
+    T.torsions[0] = ctx->torsions[0];
+    T.torsions[1] = ctx->torsions[1];
+    T.pairs14 = ctx->pairs14;
+    if (!(bm & TMD_TERM(TMD_E_BONDS))) T.bonds.n = 0;
+    if (!(bm & TMD_TERM(TMD_E_ANGLES))) T.angles.n = 0;
+    if (!(bm & TMD_TERM(TMD_E_DIHEDRALS))) T.torsions[0].n = 0;
+    if (!(bm & TMD_TERM(TMD_E_IMPROPERS))) T.torsions[1].n = 0;
+    if (!(bm & TMD_TERM(TMD_E_14))) T.pairs14.n = 0;
+    k_bonded<<<atoms_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies);
+    TMD_LAUNCHED(ctx, "k_bonded");
   }
   return TMD_OK;
 }
@@ -662,6 +716,11 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
     overflow |= fl[r * F_COUNT + F_OVERFLOW] != 0;
   }
   out->overflow = overflow;
+  for (int r = 0; r < ctx->nrep; ++r)
+    if (fl[r * F_COUNT + F_FARPOS])
+      return fail(TMD_ERR_UNSUPPORTED,
+                  "a position is more than 2000 box lengths from the origin: wrap the coordinates "
+                  "(torchmd Wrapper) -- results since the last check are not reliable");
   if (overflow) {
     // grow the rows, invalidate the list; the caller recomputes (standalone force call)
     // or reports the run as invalid (fused multi-step call)
