@@ -118,7 +118,9 @@ int tmd_vv_first(tmd_ctx* ctx, float* pos_dev, float* vel_dev, const float* forc
 
 /* langevin (integrator.py:72-74) followed by _second_VV (integrator.py:67-69).
  * gamma < 0 or vcoeff_dev == NULL: no thermostat.  noise_dev (R,N,3) N(0,1)
- * draws, or NULL to draw in-kernel from Philox4x32-10(seed, step_index).
+ * draws, or NULL to draw in-kernel from Philox4x32-10(seed, step_index + number of
+ * tmd_vv_first calls on this context so far -- the count lives on the device so a
+ * captured CUDA graph of one step can be replayed).
  * ke_dev != NULL: also write the kinetic energy per replica (R doubles)
  * (kinetic_energy, integrator.py:8-30). */
 int tmd_vv_second(tmd_ctx* ctx, float* vel_dev, const float* forces_dev, const float* masses_dev,
@@ -145,6 +147,17 @@ int tmd_md_steps_host(tmd_ctx* ctx, int niter, float* pos_host, float* vel_host,
                       double dt, double gamma, const float* vcoeff_dev, uint64_t seed,
                       uint64_t first_step_index, double* energies_host, double* ke_host,
                       tmd_stream stream);
+
+/* ---- decomposed runs (one context per rank, every rank holds all positions) --------- */
+
+/* Restrict the FORCE and INTEGRATION work of this context to the atoms
+ * [first_atom, first_atom+count) (original indices): tmd_forces fills forces only for
+ * them (their complete force: every partner is visible locally), tmd_vv_first /
+ * tmd_vv_second / tmd_kinetic_energy update only them, energies are this rank's share
+ * (sum over ranks = total).  The caller exchanges positions between tmd_vv_first and
+ * tmd_forces (one all-gather per step).  Default: all atoms.  No reference counterpart
+ * (the reference is single-device). */
+int tmd_set_owned_atoms(tmd_ctx* ctx, int first_atom, int count);
 
 /* ---- inspection ------------------------------------------------------------ */
 

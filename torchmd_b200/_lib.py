@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtmd_b200.so")
+LIB_PATH = os.environ.get("TMD_B200_LIB", os.path.join(_HERE, "libtmd_b200.so"))  # override: tuning builds only
 
 OK = 0
 ERR_OVERFLOW = -4
@@ -69,6 +69,7 @@ _SIGNATURES = {
     "tmd_md_steps_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "tmd_export_pairs": (C.c_int, [_P, _P, C.c_int, _P, C.c_int64, _P, _P]),
     "tmd_get_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
+    "tmd_set_owned_atoms": (C.c_int, [_P, C.c_int, C.c_int]),
     "tmd_profile_begin": (C.c_int, [_P, C.c_int]),
     "tmd_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), _P]),
 }

@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(BONDED_THREADS)
 k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, const float* __restrict__ pos,
          float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = S.own_lo + blockIdx.x * blockDim.x + threadIdx.x;  // owned atoms only
   const size_t base = (size_t)r * S.natoms;
   double e_bond = 0., e_angle = 0., e_dih = 0., e_imp = 0., e_lj = 0., e_el = 0.;
-  if (a < S.natoms) {
+  if (a < S.own_lo + S.own_n) {
     const BoxView bx = box_of(S, r);
     Vec3d f = {0., 0., 0.};
     for (int p = T.atom_ptr[a]; p < T.atom_ptr[a + 1]; ++p) {

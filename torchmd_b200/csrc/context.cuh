@@ -41,6 +41,8 @@ struct DeviceState {
   int row_cap;      // neighbour entries reserved per atom
   int max_cells;    // capacity of the cell arrays per replica
   int nsub;         // cells per list radius
+  int own_lo, own_n, own_all;  // atoms (original indices) whose forces this context computes; all by default
+  unsigned long long* counters;  // [0] force calls (parity of the rebuild flag), [1] vv_first calls (Philox position)
   int check_far;    // flag positions beyond 2000 box lengths (guard-free minimum image in use)
   // per-atom static data (original order)
   const float* q;        // charge * sqrt(coulomb constant)

@@ -15,11 +15,13 @@ constexpr int INTEG_THREADS = 256;
 
 // pos += vel*dt + ((0.5*a)*dt)*dt ;  vel += (0.5*dt)*a ;  a = F/m     (integrator.py:61-64)
 __global__ void __launch_bounds__(INTEG_THREADS)
-k_vv_first(int natoms, float* __restrict__ pos, float* __restrict__ vel,
-           const float* __restrict__ forces, const float* __restrict__ masses, float dt, float hdt) {
+k_vv_first(int natoms, int lo, int cnt, unsigned long long* counters, float* __restrict__ pos,
+           float* __restrict__ vel, const float* __restrict__ forces, const float* __restrict__ masses,
+           float dt, float hdt) {
   const int r = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= natoms) return;
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;  // atoms [lo, lo+cnt) only
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) counters[1] += 1;  // Philox position of this step
+  if (i >= lo + cnt) return;
   const float m = masses[i];
   const size_t a = ((size_t)r * natoms + i) * 3;
 #pragma unroll
@@ -65,14 +67,16 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t step, uint64_t s
 // (integrator.py:72-74 then 67-69), optionally followed by the kinetic energy.
 template <bool THERMOSTAT, bool KINETIC>
 __global__ void __launch_bounds__(INTEG_THREADS)
-k_vv_second(int natoms, float* __restrict__ vel, const float* __restrict__ forces,
+k_vv_second(int natoms, int lo, int cnt, const unsigned long long* __restrict__ counters,
+            float* __restrict__ vel, const float* __restrict__ forces,
             const float* __restrict__ masses, float dt, float hdt, float neg_gamma,
             const float* __restrict__ vcoeff, const float* __restrict__ noise, uint64_t seed,
-            uint64_t step, double* __restrict__ ke) {
+            uint64_t step_offset, double* __restrict__ ke) {
   const int r = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t step = step_offset + counters[1];  // device-resident step count: graph replayable
   double ek = 0.0;
-  if (i < natoms) {
+  if (i < lo + cnt) {
     const float m = masses[i];
     const size_t slot = (size_t)r * natoms + i;
     const size_t a = slot * 3;
@@ -104,12 +108,12 @@ k_vv_second(int natoms, float* __restrict__ vel, const float* __restrict__ force
 }
 
 __global__ void __launch_bounds__(INTEG_THREADS)
-k_kinetic(int natoms, const float* __restrict__ vel, const float* __restrict__ masses,
+k_kinetic(int natoms, int lo, int cnt, const float* __restrict__ vel, const float* __restrict__ masses,
           double* __restrict__ ke) {
   const int r = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   double ek = 0.0;
-  if (i < natoms) {
+  if (i < lo + cnt) {
     const size_t a = ((size_t)r * natoms + i) * 3;
     const float vx = vel[a], vy = vel[a + 1], vz = vel[a + 2];
     ek = 0.5 * (double)masses[i] * (double)(vx * vx + vy * vy + vz * vz);

@@ -52,7 +52,8 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, fl
 }
 
 // ---- every call ---------------------------------------------------------------
-__global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int parity) {
+__global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int* fl = S.flags + r * F_COUNT;
@@ -76,7 +77,8 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int pari
 }
 
 // ---- rebuild: non-periodic bounding box -------------------------------------------
-__global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int parity) {
+__global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,7 +105,8 @@ __global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int parit
   }
 }
 
-__global__ void k_grid(DeviceState S, int parity) {
+__global__ void k_grid(DeviceState S, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S.nrep) return;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
@@ -133,7 +136,8 @@ __global__ void k_grid(DeviceState S, int parity) {
 }
 
 // ---- rebuild: counting sort by cell ---------------------------------------------------
-__global__ void k_bin(DeviceState S, const float* __restrict__ pos, int parity) {
+__global__ void k_bin(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,7 +150,8 @@ __global__ void k_bin(DeviceState S, const float* __restrict__ pos, int parity) 
   S.pos_ref[a] = make_float4(x, y, z, 0.0f);
 }
 
-__global__ void __launch_bounds__(1024) k_scan(DeviceState S, int parity) {
+__global__ void __launch_bounds__(1024) k_scan(DeviceState S, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.x;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   __shared__ int warp_tot[32];
@@ -184,7 +189,8 @@ __global__ void __launch_bounds__(1024) k_scan(DeviceState S, int parity) {
   if (threadIdx.x == 1023) start[n] = run;  // inclusive prefix of the last thread = total
 }
 
-__global__ void k_place(DeviceState S, int parity) {
+__global__ void k_place(DeviceState S, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,7 +202,8 @@ __global__ void k_place(DeviceState S, int parity) {
 
 // One warp per cell: sort the cell's atoms by original index, then emit the sorted
 // records.  Cells are small (a few to a few tens of atoms); rank-by-counting.
-__global__ void k_sort_pack(DeviceState S, int parity) {
+__global__ void k_sort_pack(DeviceState S, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   const int lane = threadIdx.x & 31;
@@ -278,6 +285,10 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
   const float rl2 = S.rlist2;
   for (int ii = warp; ii < nib; ii += BT_WARPS) {
     const int k = b0 + ii;
+    if (!S.own_all) {  // decomposed run: rows only for the atoms this rank owns
+      const int io = S.perm[base + k];
+      if (io < S.own_lo || io >= S.own_lo + S.own_n) continue;
+    }
     const float4 pi = S.xw_s[base + k];
     // exclusions of this atom as sorted indices, one per lane; [exlo, exhi] bounds them so
     // that the (rare) chunks which can contain one are the only ones paying for the test
@@ -302,10 +313,11 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     for (int c0 = 0; c0 < fill; c0 += 32) {
       const int c = c0 + lane;
       bool ok = false;
-      int j = -2;
+      int j = -2, entry = -1;
       if (c < fill) {
         const float4 pj = tile[c];
-        j = __float_as_int(pj.w);
+        entry = __float_as_int(pj.w);
+        j = entry & 0xffffff;
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         if (WRAP) {  // a dimension too short for cells: one cell spans it, fold per pair
           if (w0) dx -= g.L[0] * rintf(dx * g.invL[0]);
@@ -329,7 +341,7 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         const int slot = count + __popc(m & lt);
-        if (slot < S.row_cap) row[slot] = j;
+        if (slot < S.row_cap) row[slot] = entry;
       }
       count += __popc(m);
     }
@@ -337,7 +349,8 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
   }
 }
 
-__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int parity) {
+__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int /*unused*/) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   int* fl = S.flags + r * F_COUNT;
   if (!fl[F_REBUILD0 + parity]) return;
@@ -358,6 +371,14 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int
   for (int c = blockIdx.x; c < g.ncells; c += gridDim.x) {
     const int b0c = start[c], ni = start[c + 1] - b0c;
     if (ni == 0) continue;  // block-uniform
+    if (!S.own_all) {       // decomposed run: skip cells without an owned atom
+      int mine = 0;
+      for (int t = tid; t < ni; t += nthr) {
+        const int io = S.perm[base + b0c + t];
+        mine |= (io >= S.own_lo && io < S.own_lo + S.own_n);
+      }
+      if (!__syncthreads_or(mine)) continue;
+    }
     __syncthreads();        // previous cell's shared state no longer in use
     // ---- run table: one thread per (dz,dy) row of neighbour cells, all loads in flight together
     if (tid < BT_MAXRUN / 2) {
@@ -424,7 +445,8 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int
           const Run rn = runs[q];
           const int j = rn.a0 + (slot - roff[q]);
           const float4 p = xw[j];
-          tile[u] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j));
+          // the list entry: sorted index (24 bits) + atom type (8 bits), see pair.cuh
+          tile[u] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j | (S.type_s[base + j] << 24)));
         }
         __syncthreads();
         if (w0 || w1 || w2) build_process_tile<true>(S, g, base, tile, fill, b0, nib, counts, w0, w1, w2);
@@ -458,13 +480,14 @@ __global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long
   const int n = S.nnbr[base + k];
   const float4 pi = xq[k];
   const int oi = perm[k];
+  if (!S.own_all && (oi < S.own_lo || oi >= S.own_lo + S.own_n)) return;  // rows of other ranks are not built here
   const unsigned lt = (1u << lane) - 1u;
   for (int e0 = 0; e0 < n; e0 += 32) {
     const int e = e0 + lane;
     bool ok = false;
     int oj = 0;
     if (e < n) {
-      const int j = row[e];
+      const int j = row[e] & 0xffffff;
       const float4 pj = xq[j];
       float dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
       if (g.periodic) {  // always the guarded (exact) form here
@@ -473,7 +496,8 @@ __global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long
         dz = min_image(dz, g.L[2], g.invL[2]);
       }
       oj = perm[j];
-      ok = (norm2_ref(dx, dy, dz) <= S.pp.s_max) && (oi < oj);
+      ok = (norm2_ref(dx, dy, dz) <= S.pp.s_max) &&
+           (oi < oj || (!S.own_all && (oj < S.own_lo || oj >= S.own_lo + S.own_n)));  // each pair once per owner set
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     unsigned long long b = 0;

@@ -16,6 +16,9 @@
 namespace tmd {
 
 constexpr int PAIR_WARPS = 8;
+#ifndef PAIR_MINBLOCKS
+#define PAIR_MINBLOCKS 4  // CTAs per SM the register allocation must allow (tuned on B200, see profiles/)
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -48,23 +51,25 @@ __device__ __forceinline__ void block_accumulate(double v, double* dst, double* 
 // PERIODIC minimum image on; SAFE: guard-free minimum image (see min_image_fast)
 // MODE     0 = pair terms selected at run time, 1 = LJ+switch + reaction-field Coulomb
 template <bool ENERGY, bool PERIODIC, bool SAFE, int MODE>
-__global__ void __launch_bounds__(PAIR_WARPS * 32)
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_MINBLOCKS)
 k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  const int kk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const int N = S.natoms;
   const size_t base = (size_t)r * N;
   const PairParams pp = S.pp;
   float e_el = 0.f, e_lj = 0.f, e_rep = 0.f, e_cg = 0.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
 
-  if (k < N) {
+  if (kk < S.own_n) {
+    // whole system: rows in sorted order; decomposed run: the rows of the owned atoms
+    const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
     const float4* __restrict__ xq = S.xq_s + base;
-    const int* __restrict__ types = S.type_s + base;
     const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
     const int n = S.nnbr[base + k];
     const float4 pi = xq[k];
-    const int ti = types[k] * S.ntypes;
+    const int ti = S.type_s[base + k] * S.ntypes;
     const bool need_ab = MODE == 1 ? true : (pp.terms & (T_LJ | T_REP | T_REPCG)) != 0;
     float Lx = 0.f, Ly = 0.f, Lz = 0.f, iLx = 0.f, iLy = 0.f, iLz = 0.f;
     if (PERIODIC) {
@@ -74,10 +79,12 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
     }
     float fx = 0.f, fy = 0.f, fz = 0.f;
 
-    // One interaction of atom i with listed partner j (j < 0: padding lane).
-    auto interact = [&](int j) {
-      if (j < 0) return;
-      const float4 pj = xq[j];
+    // One interaction of atom i with a listed partner.  A list entry carries the partner's
+    // sorted index in its low 24 bits and its atom type in the high 8 (packed at build
+    // time), so the LJ table row is known without a second gather; `pj` is the partner's
+    // position/charge record, fetched one iteration ahead.
+    auto interact = [&](int entry, const float4 pj) {
+      if (entry < 0) return;
       const float dx0 = sub_rn(pi.x, pj.x), dy0 = sub_rn(pi.y, pj.y), dz0 = sub_rn(pi.z, pj.z);
       float wx = dx0, wy = dy0, wz = dz0;
       float rx = 0.f, ry = 0.f, rz = 0.f;
@@ -102,7 +109,7 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
           s = wx * wx + wy * wy + wz * wz;
         }
         float2 ab = make_float2(0.f, 0.f);
-        if (need_ab) ab = __ldg(S.AB + ti + types[j]);
+        if (need_ab) ab = __ldg(S.AB + ti + (entry >> 24));
         float rinv;
         const float dedr = pair_terms<MODE>(pp, s, pi.w * pj.w, ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
         const float c = dedr * rinv;  // force on i is -unit*dE/dr = -(w/r) dE/dr
@@ -111,19 +118,25 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
         fz -= wz * c;
       }
     };
+    auto fetch = [&](int entry) { return entry >= 0 ? xq[entry & 0xffffff] : make_float4(0.f, 0.f, 0.f, 0.f); };
 
-    // The row streams from HBM exactly once per step: load it two iterations ahead of
-    // its use (evict-first), so DRAM latency overlaps the arithmetic of earlier pairs.
+    // Three-stage software pipeline per lane: list entries are loaded two iterations
+    // ahead of their use (they stream from HBM once per step, evict-first), partner
+    // records one iteration ahead (L1/L2 gathers), arithmetic on the current pair.
     int e = lane;
     int j0 = (e < n) ? __ldcs(row + e) : -1;
     int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+    int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    float4 p0 = fetch(j0), p1 = fetch(j1);
     while (e < n) {
-      const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-      const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
-      interact(j0);
-      interact(j1);
-      j0 = jn0;
-      j1 = jn1;
+      const int jnn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
+      const int jnn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
+      const float4 pn0 = fetch(jn0), pn1 = fetch(jn1);
+      interact(j0, p0);
+      interact(j1, p1);
+      j0 = jn0; j1 = jn1; p0 = pn0; p1 = pn1;
+      jn0 = jnn0; jn1 = jnn1;
       e += 64;
     }
     fx = warp_sum(fx);

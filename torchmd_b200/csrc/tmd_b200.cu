@@ -130,6 +130,11 @@ int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   if ((rc = device_alloc(&d.flags, (size_t)nreplicas * F_COUNT))) return rc;
   if ((rc = device_alloc(&d.grid, (size_t)nreplicas))) return rc;
   if ((rc = device_alloc(&d.bounds, (size_t)nreplicas * 6))) return rc;
+  if ((rc = device_alloc(&d.counters, (size_t)2))) return rc;
+  TMD_CUDA(cudaMemset(d.counters, 0, 2 * sizeof(unsigned long long)));
+  d.own_lo = 0;
+  d.own_n = natoms;
+  d.own_all = 1;
   if ((rc = device_alloc(&c->ke_scratch, (size_t)nreplicas))) return rc;
   if ((rc = device_alloc(&c->e_scratch, (size_t)nreplicas * TMD_NUM_ENERGIES))) return rc;
   TMD_CUDA(cudaMemset(d.xq_s, 0, RN * sizeof(float4)));
@@ -144,7 +149,7 @@ int tmd_destroy(tmd_ctx* ctx) {
   DeviceGuard guard(ctx->device);
   DeviceState& d = ctx->d;
   void* bufs[] = {d.xq_s, d.xw_s, d.type_s, d.perm, d.inv, d.pos_ref, d.cell_of, d.rank, d.nnbr, d.flags,
-                  d.grid, d.bounds, d.cell_count, d.cell_start, d.nbr, ctx->q, ctx->type,
+                  d.grid, d.bounds, d.counters, d.cell_count, d.cell_start, d.nbr, ctx->q, ctx->type,
                   ctx->excl_ptr, ctx->excl_idx, ctx->AB, ctx->ke_scratch, ctx->e_scratch,
                   ctx->bonds.idx, ctx->bonds.prm, ctx->angles.idx, ctx->angles.prm,
                   ctx->torsions[0].idx, ctx->torsions[0].term_ptr, ctx->torsions[0].terms,
@@ -382,6 +387,9 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   d.row_cap = round_up32(std::max<long long>(cap, 32));
 
   if (ctx->pair_mask) {
+    if (N > (1 << 24) || d.ntypes > 128)
+      return fail(TMD_ERR_UNSUPPORTED, "neighbour entries pack a 24-bit atom index and a 7-bit atom type: "
+                                       "at most 16,777,216 atoms per replica and 128 atom types");
     const size_t need = (size_t)R * N * d.row_cap;
     if (need * sizeof(int) > (size_t)96 << 30)
       return fail(TMD_ERR_UNSUPPORTED, "neighbour list would exceed 96 GiB (no cutoff on a large system?)");
@@ -397,6 +405,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   TMD_CUDA(cudaMemcpy(d.grid, grids.data(), (size_t)R * sizeof(Grid), cudaMemcpyHostToDevice));
   TMD_CUDA(cudaMemset(d.pos_ref, 0xFF, (size_t)R * N * sizeof(float4)));  // NaN: forces a build
   TMD_CUDA(cudaMemset(d.flags, 0, (size_t)R * F_COUNT * sizeof(int)));
+  TMD_CUDA(cudaMemset(d.counters, 0, sizeof(unsigned long long)));  // flag parity restarts with the flags
   {
     std::vector<int> ident((size_t)R * N);
     for (int r = 0; r < R; ++r)
@@ -471,6 +480,9 @@ static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, d
 static inline dim3 atoms_grid(const tmd_ctx* ctx, int threads) {
   return dim3((unsigned)((ctx->natoms + threads - 1) / threads), (unsigned)ctx->nrep);
 }
+static inline dim3 owned_grid(const tmd_ctx* ctx, int threads) {
+  return dim3((unsigned)((std::max(ctx->d.own_n, 1) + threads - 1) / threads), (unsigned)ctx->nrep);
+}
 
 static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, cudaStream_t st) {
   DeviceState& d = ctx->d;
@@ -503,7 +515,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, st>>>(d, parity);
     TMD_LAUNCHED(ctx, "k_build_list");
 
-    const dim3 pg((N + PAIR_WARPS - 1) / PAIR_WARPS, R);
+    const dim3 pg((std::max(d.own_n, 1) + PAIR_WARPS - 1) / PAIR_WARPS, R);
     CtxPriv& pv = priv(ctx);
     const bool sample = pv.profiling && (size_t)(pv.ev_used + 2) <= pv.ev.size();
     if (sample) TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used], st));
@@ -532,7 +544,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     if (!(bm & TMD_TERM(TMD_E_DIHEDRALS))) T.torsions[0].n = 0;
     if (!(bm & TMD_TERM(TMD_E_IMPROPERS))) T.torsions[1].n = 0;
     if (!(bm & TMD_TERM(TMD_E_14))) T.pairs14.n = 0;
-    k_bonded<<<atoms_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies);
+    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies);
     TMD_LAUNCHED(ctx, "k_bonded");
   }
   return TMD_OK;
@@ -540,8 +552,8 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
 
 static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses,
                             double dt, cudaStream_t st) {
-  k_vv_first<<<atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, pos, vel, forces, masses,
-                                                                      (float)dt, (float)(0.5 * dt));
+  k_vv_first<<<owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(
+      ctx->natoms, ctx->d.own_lo, ctx->d.own_n, ctx->d.counters, pos, vel, forces, masses, (float)dt, (float)(0.5 * dt));
   TMD_LAUNCHED(ctx, "k_vv_first");
   return TMD_OK;
 }
@@ -550,15 +562,17 @@ static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, cons
                              double gamma, const float* vcoeff, const float* noise, uint64_t seed,
                              uint64_t step, double* ke, cudaStream_t st) {
   const bool thermo = (gamma >= 0.0) && vcoeff != nullptr;
-  const dim3 g = atoms_grid(ctx, INTEG_THREADS);
+  const dim3 g = owned_grid(ctx, INTEG_THREADS);
+  const int lo = ctx->d.own_lo, cnt = ctx->d.own_n;
+  const unsigned long long* ctr = ctx->d.counters;
   const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-gamma);
   if (ke) TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
   if (thermo) {
-    if (ke) k_vv_second<true, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
-    else k_vv_second<true, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    if (ke) k_vv_second<true, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else k_vv_second<true, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
   } else {
-    if (ke) k_vv_second<false, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
-    else k_vv_second<false, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    if (ke) k_vv_second<false, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else k_vv_second<false, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
   }
   TMD_LAUNCHED(ctx, "k_vv_second");
   return TMD_OK;
@@ -596,7 +610,7 @@ int tmd_kinetic_energy(tmd_ctx* ctx, const float* vel, const float* masses, doub
   DeviceGuard guard(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
-  k_kinetic<<<atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, vel, masses, ke);
+  k_kinetic<<<owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, ctx->d.own_lo, ctx->d.own_n, vel, masses, ke);
   TMD_LAUNCHED(ctx, "k_kinetic");
   return TMD_OK;
 }
@@ -615,7 +629,7 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
     if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st))) return rc;
     if ((rc = enqueue_forces(ctx, pos, forces, last ? energies : nullptr, st))) return rc;
     if ((rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, noise ? noise + it * per_step : nullptr,
-                                seed, first_step + it, last ? ke : nullptr, st)))
+                                seed, first_step, last ? ke : nullptr, st)))
       return rc;
   }
   return TMD_OK;
@@ -659,6 +673,15 @@ int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs
   k_export_pairs<<<(ctx->natoms + 3) / 4, 128, 0, st>>>(ctx->d, replica, pairs, (long long)capacity,
                                                        reinterpret_cast<unsigned long long*>(count));
   TMD_LAUNCHED(ctx, "k_export_pairs");
+  return TMD_OK;
+}
+
+int tmd_set_owned_atoms(tmd_ctx* ctx, int first_atom, int count) {
+  if (!ctx || first_atom < 0 || count < 0 || first_atom + count > ctx->natoms)
+    return fail(TMD_ERR_ARG, "tmd_set_owned_atoms: range outside the system");
+  ctx->d.own_lo = first_atom;
+  ctx->d.own_n = count;
+  ctx->d.own_all = (first_atom == 0 && count == ctx->natoms) ? 1 : 0;
   return TMD_OK;
 }
 

@@ -1,0 +1,295 @@
+"""Decomposed (multi-GPU) MD step: one process per GPU, NCCL over NVLink.
+
+The reference is single-device; this is the B200 box's 8-GPU mode for ONE large
+system (BASELINE.json config 4).  Decomposition:
+
+* every rank holds all positions (16 B/atom: 1.6 MB at 100k atoms -- the halo of a
+  50 A brick with a 10 A list radius would already be 1.5x its own volume, SURVEY.md
+  section 8e) and the same cell list / sorted order;
+* rank r OWNS a contiguous range of atoms -- a slab of the box for the generator's
+  lattice ordering -- and computes the complete force on exactly those atoms (their
+  neighbour rows, their bonded terms), integrates exactly those atoms, and
+* ONE collective per step: an all-gather of the new positions between the first
+  half-kick and the force evaluation.  No force reduction (full neighbour rows), no
+  velocity exchange (ownership is static).  Energies / kinetic energy are summed
+  across ranks only when ``step()`` returns.
+
+Because each atom's neighbour row is built from the same sorted order by whichever
+rank owns it, forces -- and with the counter-based Langevin noise keyed on the global
+atom index, whole trajectories -- are bitwise identical to the single-GPU run.
+
+One MD step (kernels + the all-gather) is captured once as a CUDA graph and replayed:
+every per-step quantity that changes (rebuild flag parity, Philox step) lives on the
+device, so the graph is replayable and the host issues one launch per step.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .integrator import Integrator, kinetic_to_temp
+
+
+class SlabDecomposition:
+    """Static ownership of atom ranges and the padded gather layout (pure host logic)."""
+
+    def __init__(self, natoms, world, rank):
+        self.natoms, self.world, self.rank = natoms, world, rank
+        self.chunk = -(-natoms // world)  # atoms per rank, last rank may own fewer
+        self.padded = self.chunk * world
+        self.lo = min(natoms, rank * self.chunk)
+        self.hi = min(natoms, self.lo + self.chunk)
+
+    @property
+    def count(self):
+        return self.hi - self.lo
+
+    def ranges(self):
+        return [(min(self.natoms, r * self.chunk), min(self.natoms, (r + 1) * self.chunk)) for r in range(self.world)]
+
+    def rehome(self, pos):
+        """Move a (1,N,3) position tensor into a buffer padded to world*chunk atoms and
+        return (buffer, view): the view has the original shape and aliases the buffer, so an
+        all-gather into the buffer updates the positions in place."""
+        buf = torch.zeros(self.padded * 3, dtype=pos.dtype, device=pos.device)
+        buf[: self.natoms * 3] = pos.reshape(-1)
+        return buf, buf[: self.natoms * 3].view(1, self.natoms, 3)
+
+    def gather(self, buf, send, group=None):
+        """All-gather every rank's owned slice of ``buf`` (flattened xyz) into ``buf``."""
+        c3 = self.chunk * 3
+        send.copy_(buf[self.rank * c3 : (self.rank + 1) * c3])
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(buf, send, group=group)
+        else:  # gloo (CPU tests)
+            parts = [torch.empty_like(send) for _ in range(self.world)]
+            dist.all_gather(parts, send, group=group)
+            for r, p in enumerate(parts):
+                buf[r * c3 : (r + 1) * c3] = p
+
+
+class DecomposedIntegrator:
+    """``Integrator.step`` semantics for one system spread over the ranks of ``group``.
+
+    ``system`` must hold identical data on every rank (same generator, same seed); after
+    construction ``system.pos`` aliases a padded gather buffer.  Single replica only.
+    """
+
+    def __init__(self, system, forces, timestep, device, gamma=None, T=None, group=None, use_graph=True):
+        if system.pos.shape[0] != 1:
+            raise NotImplementedError("decomposed runs take one replica; shard replicas across ranks instead")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.system, self.forces = system, forces
+        n = system.pos.shape[1]
+        self.dec = SlabDecomposition(n, self.world, self.rank)
+        self.buf, system.pos = self.dec.rehome(system.pos)
+        self.send = torch.empty(self.dec.chunk * 3, dtype=system.pos.dtype, device=system.pos.device)
+        self.integ = Integrator(system, forces, timestep, device, gamma=gamma, T=T)
+        seed = torch.tensor([self.integ.seed], dtype=torch.int64, device=system.pos.device)
+        dist.broadcast(seed, 0, group=group)  # one noise stream, independent of the rank count
+        self.integ.seed = int(seed.item())
+        self.integ._require_cuda()
+        self.ctx = forces._ensure_ctx(system.pos)
+        forces._ensure_box(system.box)
+        _lib.check(_lib.lib().tmd_set_owned_atoms(self.ctx, self.dec.lo, self.dec.count))
+        nrep = 1
+        self.ene = torch.zeros((nrep, _lib.NUM_ENERGIES), dtype=torch.float64, device=system.pos.device)
+        self.ke = torch.zeros(nrep, dtype=torch.float64, device=system.pos.device)
+        self.use_graph = use_graph
+        self._graphs = {}
+
+    # one MD step on the current stream; with_energy: also this rank's energy / KE share
+    def _enqueue_step(self, with_energy):
+        s, ig, L = self.system, self.integ, _lib.lib()
+        stream = torch.cuda.current_stream(s.pos.device).cuda_stream
+        thermostat = bool(ig.T)
+        gamma = float(ig.gamma) if thermostat else -1.0
+        vcoeff = ig.vcoeff.data_ptr() if thermostat else None
+        _lib.check(L.tmd_vv_first(self.ctx, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
+        self.dec.gather(self.buf, self.send, self.group)  # the exchange step: new positions to everyone
+        _lib.check(L.tmd_forces(self.ctx, s.pos.data_ptr(), s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
+        _lib.check(
+            L.tmd_vv_second(self.ctx, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, gamma, vcoeff,
+                            None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
+        )
+
+    def _graph(self, with_energy):
+        """Capture one step (kernels + all-gather) once; None if capture is not possible."""
+        if with_energy in self._graphs:
+            return self._graphs[with_energy]
+        g = None
+        if self.use_graph:
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step(with_energy)
+                # the capture only records; state was not advanced
+            except Exception as err:  # pragma: no cover - depends on the NCCL build
+                if self.rank == 0:
+                    print(f"[domain] CUDA graph capture unavailable ({type(err).__name__}: {err}); stepping eagerly")
+                g = None
+                self.use_graph = False
+                torch.cuda.synchronize()
+        self._graphs[with_energy] = g
+        return g
+
+    def step(self, niter=1):
+        """niter MD steps; returns (Ekin, pot, T) of the whole system like Integrator.step."""
+        for it in range(niter):
+            last = it == niter - 1
+            g = self._graph(last)
+            if g is not None:
+                g.replay()
+            else:
+                self._enqueue_step(last)
+        tot = torch.cat([self.ene.sum(dim=1), self.ke])  # this rank's shares
+        dist.all_reduce(tot, group=self.group)
+        self.forces.stats()  # raises on neighbour-row overflow / far positions
+        host = tot.cpu().numpy()
+        n = self.system.pos.shape[1]
+        ekin = host[1:].astype("float32")
+        return ekin, [float(host[0])], kinetic_to_temp(ekin, n)
+
+
+def bench_decomposed(args, world, rank, local, config):
+    """bench.py body for N > 1 (same workload as the single-GPU arm, strong scaling)."""
+    import ctypes as C
+    import json
+    import os
+
+    from . import Forces, System, maxwell_boltzmann, testsystems
+    import bench as B
+
+    dev = f"cuda:{local}"
+    sysd = testsystems.water_box(B.N_WATERS, seed=0)
+    n = len(sysd["coords"])
+    par = testsystems.water_parameters(sysd, device=dev)
+    system = System(n, 1, torch.float32, dev)
+    system.set_positions(sysd["coords"])
+    system.set_box(sysd["box"])
+    torch.manual_seed(1)
+    system.set_velocities(maxwell_boltzmann(par.masses, B.TEMPERATURE, 1))
+    forces = Forces(par, terms=B.TERMS, **B.CFG)
+
+    eq = DecomposedIntegrator(system, forces, B.TIMESTEP_FS, dev, gamma=10.0, T=B.TEMPERATURE, use_graph=False)
+    forces.compute(system.pos, system.box, system.forces)  # sizes the neighbour rows (owned atoms)
+    eq.step(niter=args.equil)
+    integ = DecomposedIntegrator.__new__(DecomposedIntegrator)
+    integ.__dict__.update(eq.__dict__)  # same buffers, production thermostat
+    integ.integ = Integrator(system, forces, B.TIMESTEP_FS, dev, gamma=B.GAMMA_PS, T=B.TEMPERATURE)
+    integ.integ.seed = eq.integ.seed
+    integ.integ._require_cuda()
+    integ.use_graph, integ._graphs = True, {}
+    ekin, pot, T = integ.step(niter=max(3, args.warmup))
+
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    st0 = forces.stats()
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    _lib.check(L.tmd_profile_begin(forces._ctx, args.steps))
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    ekin, pot, T = integ.step(niter=args.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    pair_ms, pair_n = C.c_double(), C.c_int()
+    _lib.check(L.tmd_profile_end(forces._ctx, C.byref(pair_ms), C.byref(pair_n), stream))
+    clocks = sampler.stop() if sampler else None
+    st1 = forces.stats()
+    t = torch.tensor([ev0.elapsed_time(ev1), pair_ms.value / max(1, pair_n.value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank
+    ms_total, pair_avg_ms = float(t[0]), float(t[1])
+    launches = torch.tensor([st1["kernel_launches"] - st0["kernel_launches"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(launches)
+
+    # in-cutoff pairs: every rank counts the pairs of its owned atoms (i<j, or j foreign)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    dummy = torch.zeros(2, dtype=torch.int32, device=dev)
+    _lib.check(L.tmd_export_pairs(forces._ctx, system.pos.data_ptr(), 0, dummy.data_ptr(), 0, count.data_ptr(), stream))
+    dist.all_reduce(count)
+
+    # end to end: host-resident positions in and out every step
+    e2e_steps = min(args.steps, args.e2e_steps)
+    hpos = torch.empty(system.pos.shape, dtype=torch.float32, pin_memory=True)
+    hpos.copy_(system.pos)
+    for k in range(3 + e2e_steps):
+        if k == 3:
+            dist.barrier()
+            torch.cuda.synchronize()
+            import time
+
+            t0 = time.perf_counter()
+        system.pos.copy_(hpos, non_blocking=True)
+        integ.step(niter=1)
+        hpos.copy_(system.pos, non_blocking=True)
+        torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", B.FALLBACK_HBM_GBS))
+    ms_per_step = ms_total / args.steps
+    # cross-rank pairs are seen from both owners: halve them out of the per-rank byte model by
+    # using the single-GPU definition on the whole system, divided over the ranks
+    p_rc_total = None
+    alg_bytes_rank = None
+    achieved = None
+    line = {
+        "metric": "MD steps/sec (100k-atom water, fp32)",
+        "value": 1e3 / ms_per_step,
+        "unit": "steps/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": config,
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_steps / float(t_e2e[0]),
+            "unit": "steps/s",
+            "h2d_bytes_per_step": system.pos.numel() * 4,
+            "d2h_bytes_per_step": system.pos.numel() * 4 + 16,
+            "steps": e2e_steps,
+            "api": "DecomposedIntegrator.step(1) with pinned host positions copied in and out every step",
+        },
+        "gpu_launches": int(launches.item()),
+        "roofline": {
+            "kernel": "k_pair (non-bonded pair kernel), slowest rank",
+            "bound": "hbm",
+            "achieved": (32.0 * n / world + 4.0 * int(count.item()) / world) / (pair_avg_ms * 1e-3) / 1e9 if pair_avg_ms > 0 else 0.0,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": ((32.0 * n / world + 4.0 * int(count.item()) / world) / (pair_avg_ms * 1e-3) / 1e9 / peak) if pair_avg_ms > 0 else 0.0,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes": 32.0 * n / world + 4.0 * int(count.item()) / world,
+            "pair_entries_counted": int(count.item()),
+            "avg_kernel_ms": pair_avg_ms,
+            "share_of_step": pair_avg_ms / ms_per_step,
+            "traffic": None,
+        },
+        "cpu_baseline": None,
+        "state": {
+            "temperature_K": float(T[0]),
+            "epot": float(pot[0]),
+            "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
+            "cuda_graph": bool(integ.use_graph),
+            "collective": "one all-gather of positions per step (NCCL)",
+        },
+    }
+    print(json.dumps(line), flush=True)

@@ -137,7 +137,7 @@ class Integrator:
             _lib.check(
                 L.tmd_md_steps(
                     ctx, niter, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), self.masses.data_ptr(),
-                    self.dt, gamma, vcoeff, _lib.ptr(noise), self.seed, self._step_index,
+                    self.dt, gamma, vcoeff, _lib.ptr(noise), self.seed, 0,
                     ene.data_ptr(), ke.data_ptr(), stream,
                 )
             )
@@ -163,7 +163,7 @@ class Integrator:
                 _lib.check(
                     L.tmd_vv_second(
                         ctx, s.vel.data_ptr(), s.forces.data_ptr(), self.masses.data_ptr(), self.dt, gamma, vcoeff,
-                        noise[it].data_ptr() if noise is not None else None, self.seed, self._step_index,
+                        noise[it].data_ptr() if noise is not None else None, self.seed, 0,
                         ke.data_ptr() if last else None, stream,
                     )
                 )
