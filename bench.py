@@ -204,13 +204,17 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
         from torchmd_b200 import domain  # spatial decomposition driver
 
-        return domain.bench_decomposed(args, world, rank, local, workload_config(world))
+        try:
+            return domain.bench_decomposed(args, world, rank, local, workload_config(world))
+        finally:
+            dist.destroy_process_group()
 
     sysd = testsystems.water_box(N_WATERS, seed=0)
     n = len(sysd["coords"])
@@ -228,6 +232,7 @@ def gpu_arm(args):
     for _ in range(args.equil // 100):
         eq.step(niter=100)
     integ = Integrator(system, forces, TIMESTEP_FS, dev, gamma=GAMMA_PS, T=TEMPERATURE)
+    sampler = ClockSampler(local)  # runs through the warm-up too (same load), so short runs still get samples
     for _ in range(max(3, args.warmup) // 50 + 1):
         ekin, pot, T = integ.step(niter=50)
 
@@ -235,7 +240,6 @@ def gpu_arm(args):
     stream = torch.cuda.current_stream().cuda_stream
     st0 = forces.stats()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     _lib.check(L.tmd_profile_begin(forces._ctx, args.steps))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -363,7 +367,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--equil", type=int, default=600, help="relaxation steps before warm-up (lattice start)")

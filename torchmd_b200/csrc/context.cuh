@@ -108,6 +108,7 @@ struct tmd_ctx {
   bool have_atoms = false, have_nonbonded = false, have_box = false, have_excl = false;
   bool periodic = false;
   bool safe_image = false;           // guard-free minimum image valid (see min_image_fast)
+  int coop_blocks = 0;               // CTAs per replica of the cooperative rebuild kernel (0: separate kernels)
   int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
   std::vector<float> box_host;       // (nrep,3)
   std::vector<float> charges_host;   // unscaled charges

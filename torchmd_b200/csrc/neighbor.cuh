@@ -21,6 +21,8 @@
 // Every rebuild kernel returns immediately unless the replica's rebuild flag is
 // set, so the host can enqueue them unconditionally (no host round trip).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "context.cuh"
 
 namespace tmd {
@@ -52,7 +54,7 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, fl
 }
 
 // ---- every call ---------------------------------------------------------------
-__global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
+__global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
   const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
   const int r = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,20 +75,25 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos, int /*un
       fl[F_FARPOS] = 1;
   }
   const int k = S.inv[a];
-  S.xq_s[(size_t)r * S.natoms + k] = make_float4(x, y, z, S.q[i]);
+  S.xq_s[(size_t)r * (S.natoms + 1) + k] = make_float4(x, y, z, S.q[i]);
 }
 
-// ---- rebuild: non-periodic bounding box -------------------------------------------
-__global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- rebuild phases -----------------------------------------------------------------
+// Each phase is a device function over a (bx of nbx blocks) slice of the grid with
+// grid-stride loops, so the same code runs as separate gated kernels or as the phases of
+// the single cooperative kernel k_rebuild (one launch per step instead of five).
+
+// non-periodic bounding box
+__device__ __forceinline__ void phase_bounds(const DeviceState& S, int r, int bx, int nbx,
+                                             const float* __restrict__ pos) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (i < S.natoms) {
+  for (int i = bx * blockDim.x + threadIdx.x; i < S.natoms; i += nbx * blockDim.x) {
     const size_t a = ((size_t)r * S.natoms + i) * 3;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) lo[d] = hi[d] = pos[a + d];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], pos[a + d]);
+      hi[d] = fmaxf(hi[d], pos[a + d]);
+    }
   }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -105,11 +112,8 @@ __global__ void k_bounds(DeviceState S, const float* __restrict__ pos, int /*unu
   }
 }
 
-__global__ void k_grid(DeviceState S, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= S.nrep) return;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+// cell grid from the bounding box (one thread per replica)
+__device__ __forceinline__ void phase_grid(const DeviceState& S, int r) {
   int* b = reinterpret_cast<int*>(S.bounds) + r * 6;
   Grid g;
   g.periodic = 0;
@@ -135,35 +139,36 @@ __global__ void k_grid(DeviceState S, int /*unused*/) {
   S.grid[r] = g;
 }
 
-// ---- rebuild: counting sort by cell ---------------------------------------------------
-__global__ void k_bin(DeviceState S, const float* __restrict__ pos, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.natoms) return;
-  const size_t a = (size_t)r * S.natoms + i;
-  const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
-  const int c = cell_of_point(S.grid[r], x, y, z);
-  S.cell_of[a] = c;
-  S.rank[a] = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
-  S.pos_ref[a] = make_float4(x, y, z, 0.0f);
+// counting sort by cell, pass 1: cell index per atom + slot in the cell
+__device__ __forceinline__ void phase_bin(const DeviceState& S, int r, int bx, int nbx,
+                                          const float* __restrict__ pos) {
+  const int ncells = S.grid[r].ncells;
+  for (int i = bx * blockDim.x + threadIdx.x; i < S.natoms; i += nbx * blockDim.x) {
+    const size_t a = (size_t)r * S.natoms + i;
+    const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
+    int c = cell_of_point(S.grid[r], x, y, z);
+    if (!isfinite(x + y + z)) {  // blown-up coordinates: report, and spread them so no cell degenerates
+      S.flags[r * F_COUNT + F_FARPOS] = 1;
+      c = i % ncells;
+    }
+    S.cell_of[a] = c;
+    const int slot = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
+    S.rank[a] = ncells == 1 ? i : slot;  // one cell (small box / no cutoff): already in index order
+    S.pos_ref[a] = make_float4(x, y, z, 0.0f);
+  }
 }
 
-__global__ void __launch_bounds__(1024) k_scan(DeviceState S, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.x;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  __shared__ int warp_tot[32];
+// exclusive scan of the cell counts by ONE block (any multiple of 32 threads up to 1024)
+__device__ __forceinline__ void phase_scan(const DeviceState& S, int r, int* warp_tot /*32 ints shared*/) {
   const int n = S.grid[r].ncells;
+  const int nt = blockDim.x;
   const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  const int chunk = (n + 1023) / 1024;
+  const int chunk = (n + nt - 1) / nt;
   const int b = threadIdx.x * chunk, e = min(n, b + chunk);
   int sum = 0;
   for (int c = b; c < e; ++c) sum += cnt[c];
-  // block-wide exclusive scan of the per-thread sums
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = nt >> 5;
   int incl = sum;
   for (int o = 1; o < 32; o <<= 1) {
     int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(1024) k_scan(DeviceState S, int /*unused*/) {
   if (lane == 31) warp_tot[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int t = warp_tot[lane];
+    int t = lane < nw ? warp_tot[lane] : 0;
     int ti = t;
     for (int o = 1; o < 32; o <<= 1) {
       int v = __shfl_up_sync(0xffffffffu, ti, o);
@@ -186,41 +191,39 @@ __global__ void __launch_bounds__(1024) k_scan(DeviceState S, int /*unused*/) {
     start[c] = run;
     run += cnt[c];
   }
-  if (threadIdx.x == 1023) start[n] = run;  // inclusive prefix of the last thread = total
+  if (threadIdx.x == nt - 1) start[n] = run;  // inclusive prefix of the last thread = total
+  __syncthreads();
 }
 
-__global__ void k_place(DeviceState S, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.natoms) return;
-  const size_t a = (size_t)r * S.natoms + i;
+// counting sort, pass 2: scatter
+__device__ __forceinline__ void phase_place(const DeviceState& S, int r, int bx, int nbx) {
   const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  S.perm[(size_t)r * S.natoms + start[S.cell_of[a]] + S.rank[a]] = i;
+  for (int i = bx * blockDim.x + threadIdx.x; i < S.natoms; i += nbx * blockDim.x) {
+    const size_t a = (size_t)r * S.natoms + i;
+    S.perm[(size_t)r * S.natoms + start[S.cell_of[a]] + S.rank[a]] = i;
+  }
 }
 
 // One warp per cell: sort the cell's atoms by original index, then emit the sorted
 // records.  Cells are small (a few to a few tens of atoms); rank-by-counting.
-__global__ void k_sort_pack(DeviceState S, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+__device__ __forceinline__ void phase_sort_pack(const DeviceState& S, int r, int bx, int nbx) {
   const int lane = threadIdx.x & 31;
-  const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+  const int warps_per_grid = nbx * (blockDim.x >> 5);
   const int ncells = S.grid[r].ncells;
   const int gper = S.grid[r].periodic;
   const float gL0 = S.grid[r].L[0], gL1 = S.grid[r].L[1], gL2 = S.grid[r].L[2];
   const float giL0 = S.grid[r].invL[0], giL1 = S.grid[r].invL[1], giL2 = S.grid[r].invL[2];
   const size_t base = (size_t)r * S.natoms;
   int* perm = S.perm + base;
-  int* tmp = S.rank + base;  // free after k_place
+  int* tmp = S.rank + base;  // free after the scatter
   int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
+  for (int c = bx * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
     const int b = start[c], n = start[c + 1] - b;
     if (lane == 0) cnt[c] = 0;  // leave the counters clean for the next build
-    if (n <= 32) {
+    if (ncells == 1) {
+      // single cell: phase_bin placed the atoms in index order already
+    } else if (n <= 32) {
       const int v = lane < n ? perm[b + lane] : 0x7fffffff;
       int rk = 0;
       for (int m = 0; m < n; ++m) rk += (__shfl_sync(0xffffffffu, v, m) < v);
@@ -243,7 +246,7 @@ __global__ void k_sort_pack(DeviceState S, int /*unused*/) {
       const int i = perm[b + e];
       const float4 p = S.pos_ref[base + i];
       S.inv[base + i] = b + e;
-      S.xq_s[base + b + e] = make_float4(p.x, p.y, p.z, S.q[i]);
+      S.xq_s[(size_t)r * (S.natoms + 1) + b + e] = make_float4(p.x, p.y, p.z, S.q[i]);
       S.type_s[base + b + e] = S.type[i];
       float wx = p.x, wy = p.y, wz = p.z;  // coordinates folded into [0, L] for the list build
       if (gper) {
@@ -254,6 +257,38 @@ __global__ void k_sort_pack(DeviceState S, int /*unused*/) {
       S.xw_s[base + b + e] = make_float4(wx, wy, wz, 0.f);
     }
   }
+}
+
+// separate gated kernels (fallback path / non-cooperative devices)
+#define TMD_GATE                                                                    \
+  const int parity = (int)(S.counters[0] & 1ull); /* device-resident: replayable */ \
+  if (!S.flags[blockIdx.y * F_COUNT + F_REBUILD0 + parity]) return;
+__global__ void k_bounds(DeviceState S, const float* __restrict__ pos) {
+  TMD_GATE
+  phase_bounds(S, blockIdx.y, blockIdx.x, gridDim.x, pos);
+}
+__global__ void k_grid(DeviceState S) {
+  const int parity = (int)(S.counters[0] & 1ull);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < S.nrep && S.flags[r * F_COUNT + F_REBUILD0 + parity]) phase_grid(S, r);
+}
+__global__ void k_bin(DeviceState S, const float* __restrict__ pos) {
+  TMD_GATE
+  phase_bin(S, blockIdx.y, blockIdx.x, gridDim.x, pos);
+}
+__global__ void __launch_bounds__(1024) k_scan(DeviceState S) {
+  const int parity = (int)(S.counters[0] & 1ull);
+  if (!S.flags[blockIdx.x * F_COUNT + F_REBUILD0 + parity]) return;
+  __shared__ int warp_tot[32];
+  phase_scan(S, blockIdx.x, warp_tot);
+}
+__global__ void k_place(DeviceState S) {
+  TMD_GATE
+  phase_place(S, blockIdx.y, blockIdx.x, gridDim.x);
+}
+__global__ void k_sort_pack(DeviceState S) {
+  TMD_GATE
+  phase_sort_pack(S, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // ---- rebuild: Verlet list ---------------------------------------------------------------
@@ -276,13 +311,21 @@ struct Run {
   float sx, sy, sz;
 };
 
+struct BuildShared {
+  float4 tile[BT_TILE];
+  Run runs[BT_MAXRUN];
+  int roff[BT_MAXRUN + 1];  // exclusive prefix of the run lengths
+  int counts[BT_MAXI];
+};
+
 template <bool WRAP>
 __device__ __forceinline__ void build_process_tile(const DeviceState& S, const Grid& g, size_t base,
-                                                   const float4* tile, int fill, int b0, int nib, int* counts,
-                                                   bool w0, bool w1, bool w2) {
+                                                   BuildShared& sh, int fill, int b0, int nib, bool w0,
+                                                   bool w1, bool w2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const float rl2 = S.rlist2;
+  const int cap = S.row_cap;
   for (int ii = warp; ii < nib; ii += BT_WARPS) {
     const int k = b0 + ii;
     if (!S.own_all) {  // decomposed run: rows only for the atoms this rank owns
@@ -292,10 +335,10 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     const float4 pi = S.xw_s[base + k];
     // exclusions of this atom as sorted indices, one per lane; [exlo, exhi] bounds them so
     // that the (rare) chunks which can contain one are the only ones paying for the test
-    int ne = 0, my_excl = -1, exlo = 0x7fffffff, exhi = -1;
+    int ne = 0, my_excl = -1, exlo = 0x7fffffff, exhi = -1, e0 = 0;
     if (S.excl_ptr) {
       const int io = S.perm[base + k];
-      const int e0 = S.excl_ptr[io];
+      e0 = S.excl_ptr[io];
       ne = S.excl_ptr[io + 1] - e0;
       for (int eb = 0; eb < ne; eb += 32) {  // more than 32 exclusions: bounds over all, lanes keep the first 32
         const int v = (eb + lane < ne) ? S.inv[base + S.excl_idx[e0 + eb + lane]] : -1;
@@ -307,58 +350,54 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
         exhi = max(exhi, __shfl_xor_sync(0xffffffffu, exhi, o));
       }
     }
-    int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
-    int count = counts[ii];
+    int* __restrict__ row = S.nbr + (base + k) * (size_t)cap;
+    int count = sh.counts[ii];
+    const float4* __restrict__ tp = sh.tile + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < fill; c0 += 32) {
-      const int c = c0 + lane;
-      bool ok = false;
-      int j = -2, entry = -1;
-      if (c < fill) {
-        const float4 pj = tile[c];
-        entry = __float_as_int(pj.w);
-        j = entry & 0xffffff;
-        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        if (WRAP) {  // a dimension too short for cells: one cell spans it, fold per pair
-          if (w0) dx -= g.L[0] * rintf(dx * g.invL[0]);
-          if (w1) dy -= g.L[1] * rintf(dy * g.invL[1]);
-          if (w2) dz -= g.L[2] * rintf(dz * g.invL[2]);
-        }
-        ok = (dx * dx + dy * dy + dz * dz <= rl2) && (j != k);
+    for (int c0 = 0; c0 < fill; c0 += 32, tp += 32) {
+      // candidates beyond `fill` in the last chunk: the tile is padded with far-away records
+      const float4 pj = *tp;
+      const int entry = __float_as_int(pj.w);
+      const int j = entry & 0xffffff;
+      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      if (WRAP) {  // a dimension too short for cells: one cell spans it, fold per pair
+        if (w0) dx -= g.L[0] * rintf(dx * g.invL[0]);
+        if (w1) dy -= g.L[1] * rintf(dy * g.invL[1]);
+        if (w2) dz -= g.L[2] * rintf(dz * g.invL[2]);
       }
-      if (__any_sync(0xffffffffu, ok && j >= exlo && j <= exhi)) {
+      const bool near = (dx * dx + dy * dy + dz * dz <= rl2) && (j != k);
+      unsigned m = __ballot_sync(0xffffffffu, near);
+      if (__any_sync(0xffffffffu, near && j >= exlo && j <= exhi)) {  // rare: an exclusion may be in this chunk
+        bool excl = false;
         const int nfast = min(ne, 32);
 #pragma unroll 1
-        for (int e = 0; e < nfast; ++e)
-          if (__shfl_sync(0xffffffffu, my_excl, e) == j) ok = false;
-        if (ne > 32) {
-          const int e0 = S.excl_ptr[S.perm[base + k]];
+        for (int e = 0; e < nfast; ++e) excl |= (__shfl_sync(0xffffffffu, my_excl, e) == j);
 #pragma unroll 1
-          for (int e = 32; e < ne; ++e)
-            if (S.inv[base + S.excl_idx[e0 + e]] == j) ok = false;
-        }
+        for (int e = 32; e < ne; ++e) excl |= (S.inv[base + S.excl_idx[e0 + e]] == j);
+        m &= ~__ballot_sync(0xffffffffu, excl);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) {
-        const int slot = count + __popc(m & lt);
-        if (slot < S.row_cap) row[slot] = entry;
-      }
+      const int slot = count + __popc(m & lt);
+      if (((m >> lane) & 1u) && slot < cap) row[slot] = entry;
       count += __popc(m);
     }
-    if (lane == 0) counts[ii] = count;
+    // keep the row padded to a multiple of 32 entries with the sentinel (record natoms holds
+    // NaN coordinates and fails every cutoff test).  Later tiles overwrite the padding as the
+    // row grows.
+    {
+      const int end = min((count + 31) & ~31, cap);
+      for (int e = count + lane; e < end; e += 32) row[e] = S.natoms;
+    }
+    if (lane == 0) sh.counts[ii] = count;
   }
 }
 
-__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int /*unused*/) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
+__device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx, int nbx, BuildShared& sh) {
   int* fl = S.flags + r * F_COUNT;
-  if (!fl[F_REBUILD0 + parity]) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(fl + F_NREBUILD, 1);
-  __shared__ float4 tile[BT_TILE];
-  __shared__ Run runs[BT_MAXRUN];
-  __shared__ int roff[BT_MAXRUN + 1];  // exclusive prefix of the run lengths
-  __shared__ int counts[BT_MAXI];
+  if (bx == 0 && threadIdx.x == 0) atomicAdd(fl + F_NREBUILD, 1);
+  float4* const tile = sh.tile;
+  Run* const runs = sh.runs;
+  int* const roff = sh.roff;
+  int* const counts = sh.counts;
   const Grid g = S.grid[r];
   const size_t base = (size_t)r * S.natoms;
   const float4* __restrict__ xw = S.xw_s + base;
@@ -368,7 +407,7 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int
   const int ny = 2 * g.reach[1] + 1, nz = 2 * g.reach[2] + 1;
   const int nrows = ny * nz;  // <= 25, two run slots each
 
-  for (int c = blockIdx.x; c < g.ncells; c += gridDim.x) {
+  for (int c = bx; c < g.ncells; c += nbx) {
     const int b0c = start[c], ni = start[c + 1] - b0c;
     if (ni == 0) continue;  // block-uniform
     if (!S.own_all) {       // decomposed run: skip cells without an owned atom
@@ -448,9 +487,12 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int
           // the list entry: sorted index (24 bits) + atom type (8 bits), see pair.cuh
           tile[u] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j | (S.type_s[base + j] << 24)));
         }
+        // pad the last 32-candidate chunk with records that pass no distance test
+        for (int u = fill + tid; u < ((fill + 31) & ~31); u += nthr)
+          tile[u] = make_float4(NAN, NAN, NAN, __int_as_float(0xffffff));  // NaN: fails `<= rlist2` even when that is +inf
         __syncthreads();
-        if (w0 || w1 || w2) build_process_tile<true>(S, g, base, tile, fill, b0, nib, counts, w0, w1, w2);
-        else build_process_tile<false>(S, g, base, tile, fill, b0, nib, counts, w0, w1, w2);
+        if (w0 || w1 || w2) build_process_tile<true>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
+        else build_process_tile<false>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
       }
       __syncthreads();
       for (int t = tid; t < nib; t += nthr) {
@@ -464,6 +506,48 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S, int
   }
 }
 
+__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S) {
+  TMD_GATE
+  __shared__ BuildShared sh;
+  phase_build(S, blockIdx.y, blockIdx.x, gridDim.x, sh);
+}
+
+// The whole rebuild as ONE cooperative launch: phases separated by grid-wide barriers.
+// Enqueued every step; when no replica asked for a rebuild every block returns at once
+// (one ~3 us launch instead of five).  Grid: as many CTAs as are co-resident.
+__global__ void __launch_bounds__(BT_WARPS * 32)
+k_rebuild(DeviceState S, const float* __restrict__ pos, int need_bounds) {
+  const int parity = (int)(S.counters[0] & 1ull);
+  __shared__ int any_s;
+  if (threadIdx.x == 0) {
+    int any = 0;
+    for (int q = 0; q < S.nrep; ++q) any |= S.flags[q * F_COUNT + F_REBUILD0 + parity];
+    any_s = any;
+  }
+  __syncthreads();
+  if (!any_s) return;  // uniform over the grid: nobody reaches a grid barrier
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int r = blockIdx.y, bx = blockIdx.x, nbx = gridDim.x;
+  const bool mine = S.flags[r * F_COUNT + F_REBUILD0 + parity] != 0;
+  __shared__ BuildShared sh;
+  __shared__ int warp_tot[32];
+  if (need_bounds) {
+    if (mine) phase_bounds(S, r, bx, nbx, pos);
+    grid.sync();
+    if (mine && bx == 0 && threadIdx.x == 0) phase_grid(S, r);
+    grid.sync();
+  }
+  if (mine) phase_bin(S, r, bx, nbx, pos);
+  grid.sync();
+  if (mine && bx == 0) phase_scan(S, r, warp_tot);
+  grid.sync();
+  if (mine) phase_place(S, r, bx, nbx);
+  grid.sync();
+  if (mine) phase_sort_pack(S, r, bx, nbx);
+  grid.sync();
+  if (mine) phase_build(S, r, bx, nbx, sh);
+}
+
 // ---- inspection: the reference's neighbour list ----------------------------------------
 // Applies the exact reference predicate to every listed pair and emits (i<j) in
 // original atom indices.  Used by the bit-exact index test.
@@ -474,7 +558,7 @@ __global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long
   if (k >= S.natoms) return;
   const Grid g = S.grid[r];
   const size_t base = (size_t)r * S.natoms;
-  const float4* xq = S.xq_s + base;
+  const float4* xq = S.xq_s + (size_t)r * (S.natoms + 1);
   const int* perm = S.perm + base;
   const int* row = S.nbr + (base + k) * (size_t)S.row_cap;
   const int n = S.nnbr[base + k];
@@ -487,7 +571,7 @@ __global__ void k_export_pairs(DeviceState S, int r, int* __restrict__ out, long
     bool ok = false;
     int oj = 0;
     if (e < n) {
-      const int j = row[e] & 0xffffff;
+      const int j = row[e] & 0xffffff;  // e < nnbr: never a padding entry
       const float4 pj = xq[j];
       float dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
       if (g.periodic) {  // always the guarded (exact) form here

@@ -65,7 +65,7 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
   if (kk < S.own_n) {
     // whole system: rows in sorted order; decomposed run: the rows of the owned atoms
     const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
-    const float4* __restrict__ xq = S.xq_s + base;
+    const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);  // (record N is the NaN sentinel the list build pads rows with)
     const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
     const int n = S.nnbr[base + k];
     const float4 pi = xq[k];

@@ -78,7 +78,6 @@ int device_alloc(T** dst, size_t n) {
   return TMD_OK;
 }
 
-inline int round_up32(long long v) { return (int)(((v + 31) / 32) * 32); }
 
 struct CtxPriv {
   bool dirty = true;
@@ -118,7 +117,7 @@ int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   d.nsub = 2;
   const size_t RN = (size_t)natoms * nreplicas;
   int rc = TMD_OK;
-  if ((rc = device_alloc(&d.xq_s, RN))) return rc;
+  if ((rc = device_alloc(&d.xq_s, RN + nreplicas))) return rc;  // +1 sentinel record per replica
   if ((rc = device_alloc(&d.type_s, RN))) return rc;
   if ((rc = device_alloc(&d.xw_s, RN))) return rc;
   if ((rc = device_alloc(&d.perm, RN))) return rc;
@@ -137,7 +136,7 @@ int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   d.own_all = 1;
   if ((rc = device_alloc(&c->ke_scratch, (size_t)nreplicas))) return rc;
   if ((rc = device_alloc(&c->e_scratch, (size_t)nreplicas * TMD_NUM_ENERGIES))) return rc;
-  TMD_CUDA(cudaMemset(d.xq_s, 0, RN * sizeof(float4)));
+  TMD_CUDA(cudaMemset(d.xq_s, 0xFF, (RN + nreplicas) * sizeof(float4)));  // NaN everywhere, incl. the sentinels
   TMD_CUDA(cudaMemset(d.type_s, 0, RN * sizeof(int)));
   TMD_CUDA(cudaMemset(d.nnbr, 0, RN * sizeof(int)));
   *out = c;
@@ -384,13 +383,13 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   else cap = 512;
   cap = std::min<long long>(cap, N);
   if (d.row_cap > cap) cap = d.row_cap;  // keep a capacity grown after an overflow
-  d.row_cap = round_up32(std::max<long long>(cap, 32));
+  d.row_cap = (int)(((std::max<long long>(cap, 64) + 63) / 64) * 64);  // rows are padded to 64-entry chunks
 
   if (ctx->pair_mask) {
-    if (N > (1 << 24) || d.ntypes > 128)
+    if (N >= (1 << 24) || d.ntypes > 128)
       return fail(TMD_ERR_UNSUPPORTED, "neighbour entries pack a 24-bit atom index and a 7-bit atom type: "
                                        "at most 16,777,216 atoms per replica and 128 atom types");
-    const size_t need = (size_t)R * N * d.row_cap;
+    const size_t need = (size_t)R * N * d.row_cap + 256;  // slack: the pair loop prefetches past a row's end
     if (need * sizeof(int) > (size_t)96 << 30)
       return fail(TMD_ERR_UNSUPPORTED, "neighbour list would exceed 96 GiB (no cutoff on a large system?)");
     if (need != priv(ctx).nbr_entries) {
@@ -453,6 +452,19 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     if ((rc = upload(&ctx->bonded_atom_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = upload(&ctx->bonded_entries, ent.data(), ent.size()))) return rc;
   }
+  // cooperative rebuild kernel: as many CTAs as can be co-resident, split over the replicas
+  ctx->coop_blocks = 0;
+  {
+    const char* env = getenv("TMD_B200_COOP");
+    int coop = 0, nsm = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (coop && !(env && env[0] == '0') &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rebuild, BT_WARPS * 32, 0) == cudaSuccess) {
+      const int total = per_sm * nsm;
+      if (total >= R) ctx->coop_blocks = std::max(1, total / R);
+    }
+  }
   ctx->call_index = 0;
   priv(ctx).dirty = false;
   return TMD_OK;
@@ -487,33 +499,43 @@ static inline dim3 owned_grid(const tmd_ctx* ctx, int threads) {
 static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, cudaStream_t st) {
   DeviceState& d = ctx->d;
   const int N = ctx->natoms, R = ctx->nrep;
-  const int parity = (int)(ctx->call_index & 1);
   ctx->call_index++;
   ctx->force_calls++;
   if (energies) TMD_CUDA(cudaMemsetAsync(energies, 0, (size_t)R * TMD_NUM_ENERGIES * sizeof(double), st));
 
   if (ctx->pair_mask) {
-    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
+    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
     TMD_LAUNCHED(ctx, "k_prepare");
-    if (!ctx->periodic && ctx->cutoff >= 0) {
-      k_bounds<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
-      TMD_LAUNCHED(ctx, "k_bounds");
-      k_grid<<<(R + 63) / 64, 64, 0, st>>>(d, parity);
-      TMD_LAUNCHED(ctx, "k_grid");
+    const int need_bounds = (!ctx->periodic && ctx->cutoff >= 0) ? 1 : 0;
+    if (ctx->coop_blocks > 0) {
+      // the whole (gated) rebuild in one cooperative launch
+      const float* pos_arg = pos;
+      int nb_arg = need_bounds;
+      void* args[] = {(void*)&d, (void*)&pos_arg, (void*)&nb_arg};
+      TMD_CUDA(cudaLaunchCooperativeKernel((const void*)k_rebuild, dim3(ctx->coop_blocks, R), dim3(BT_WARPS * 32),
+                                           args, 0, st));
+      TMD_LAUNCHED(ctx, "k_rebuild");
+    } else {
+      if (need_bounds) {
+        k_bounds<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
+        TMD_LAUNCHED(ctx, "k_bounds");
+        k_grid<<<(R + 63) / 64, 64, 0, st>>>(d);
+        TMD_LAUNCHED(ctx, "k_grid");
+      }
+      k_bin<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
+      TMD_LAUNCHED(ctx, "k_bin");
+      k_scan<<<R, 1024, 0, st>>>(d);
+      TMD_LAUNCHED(ctx, "k_scan");
+      k_place<<<atoms_grid(ctx, 256), 256, 0, st>>>(d);
+      TMD_LAUNCHED(ctx, "k_place");
+      {
+        const int blocks = std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8));
+        k_sort_pack<<<dim3(blocks, R), 256, 0, st>>>(d);
+        TMD_LAUNCHED(ctx, "k_sort_pack");
+      }
+      k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, st>>>(d);
+      TMD_LAUNCHED(ctx, "k_build_list");
     }
-    k_bin<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos, parity);
-    TMD_LAUNCHED(ctx, "k_bin");
-    k_scan<<<R, 1024, 0, st>>>(d, parity);
-    TMD_LAUNCHED(ctx, "k_scan");
-    k_place<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, parity);
-    TMD_LAUNCHED(ctx, "k_place");
-    {
-      const int blocks = std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8));
-      k_sort_pack<<<dim3(blocks, R), 256, 0, st>>>(d, parity);
-      TMD_LAUNCHED(ctx, "k_sort_pack");
-    }
-    k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, st>>>(d, parity);
-    TMD_LAUNCHED(ctx, "k_build_list");
 
     const dim3 pg((std::max(d.own_n, 1) + PAIR_WARPS - 1) / PAIR_WARPS, R);
     CtxPriv& pv = priv(ctx);
@@ -747,7 +769,7 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
   if (overflow) {
     // grow the rows, invalidate the list; the caller recomputes (standalone force call)
     // or reports the run as invalid (fused multi-step call)
-    ctx->d.row_cap = round_up32((long long)(out->max_neighbours * 1.25) + 32);
+    ctx->d.row_cap = (int)((((long long)(out->max_neighbours * 1.25) + 32 + 63) / 64) * 64);
     priv(ctx).dirty = true;
     return fail(TMD_ERR_OVERFLOW, "neighbour row capacity exceeded; capacity grown, recompute required");
   }
