@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" >/dev/null 2>&1
 timeout 300 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-for sk in 0.6 0.8 1.0 1.3; do
+for sk in 0.7 0.85 1.0; do
   TMD_B200_SKIN=$sk timeout 200 python bench.py --steps 1000 --warmup 100 --no-cpu-baseline --e2e-steps 20 > gpurun_out/tune_skin$sk.json 2>gpurun_out/tune_skin.err
   python - <<PY
 import json
@@ -9,4 +9,3 @@ d=json.load(open("gpurun_out/tune_skin$sk.json"))
 print("skin $sk: steps/s %.0f  ms/step %.4f pair_ms %.4f rebuilds %d maxnbr %d"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["state"]["rebuilds_in_timed_region"], d["state"]["max_neighbours"]))
 PY
 done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/launches_r1j.csv python bench.py --steps 20 --warmup 3 --equil 100 --no-cpu-baseline --e2e-steps 5 > gpurun_out/ncu_bench.log 2>&1; echo ncu1_exit=$?

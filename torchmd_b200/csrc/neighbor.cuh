@@ -301,8 +301,17 @@ __global__ void k_sort_pack(DeviceState S) {
 // the accepted partners (sorted indices) to the atom's 128-byte-aligned row.  The test
 // is generous (rlist carries a safety margin); the exact reference predicate is applied
 // by the pair kernel.  Row order is fixed by the run order: deterministic.
-constexpr int BT_WARPS = 8;
-constexpr int BT_TILE = 2048;   // candidates staged per pass (32 KB)
+#ifndef BT_WARPS_N
+#define BT_WARPS_N 4
+#endif
+#ifndef BT_MINBLOCKS
+#define BT_MINBLOCKS 6
+#endif
+constexpr int BT_WARPS = BT_WARPS_N;
+#ifndef BT_TILE_N
+#define BT_TILE_N 2048
+#endif
+constexpr int BT_TILE = BT_TILE_N;   // candidates staged per pass (16 B each)
 constexpr int BT_MAXRUN = 64;   // (2*2+1)^2 rows x 2 segments = 50
 constexpr int BT_MAXI = 256;    // atoms of the cell handled per pass
 
@@ -506,7 +515,7 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
   }
 }
 
-__global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S) {
+__global__ void __launch_bounds__(BT_WARPS * 32, BT_MINBLOCKS) k_build_list(DeviceState S) {
   TMD_GATE
   __shared__ BuildShared sh;
   phase_build(S, blockIdx.y, blockIdx.x, gridDim.x, sh);
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(BT_WARPS * 32) k_build_list(DeviceState S) {
 // The whole rebuild as ONE cooperative launch: phases separated by grid-wide barriers.
 // Enqueued every step; when no replica asked for a rebuild every block returns at once
 // (one ~3 us launch instead of five).  Grid: as many CTAs as are co-resident.
-__global__ void __launch_bounds__(BT_WARPS * 32)
+__global__ void __launch_bounds__(BT_WARPS * 32, BT_MINBLOCKS)
 k_rebuild(DeviceState S, const float* __restrict__ pos, int need_bounds) {
   const int parity = (int)(S.counters[0] & 1ull);
   __shared__ int any_s;

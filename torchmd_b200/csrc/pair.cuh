@@ -15,9 +15,12 @@
 
 namespace tmd {
 
-constexpr int PAIR_WARPS = 8;
+#ifndef PAIR_WARPS_N
+#define PAIR_WARPS_N 8
+#endif
+constexpr int PAIR_WARPS = PAIR_WARPS_N;
 #ifndef PAIR_MINBLOCKS
-#define PAIR_MINBLOCKS 4  // CTAs per SM the register allocation must allow (tuned on B200, see profiles/)
+#define PAIR_MINBLOCKS 6  // CTAs per SM the register allocation must allow: 40 regs (tuned on B200, see profiles/)
 #endif
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -82,9 +85,8 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
     // One interaction of atom i with a listed partner.  A list entry carries the partner's
     // sorted index in its low 24 bits and its atom type in the high 8 (packed at build
     // time), so the LJ table row is known without a second gather; `pj` is the partner's
-    // position/charge record, fetched one iteration ahead.
+    // position/charge record.
     auto interact = [&](int entry, const float4 pj) {
-      if (entry < 0) return;
       const float dx0 = sub_rn(pi.x, pj.x), dy0 = sub_rn(pi.y, pj.y), dz0 = sub_rn(pi.z, pj.z);
       float wx = dx0, wy = dy0, wz = dz0;
       float rx = 0.f, ry = 0.f, rz = 0.f;
@@ -118,26 +120,24 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
         fz -= wz * c;
       }
     };
-    auto fetch = [&](int entry) { return entry >= 0 ? xq[entry & 0xffffff] : make_float4(0.f, 0.f, 0.f, 0.f); };
-
-    // Three-stage software pipeline per lane: list entries are loaded two iterations
-    // ahead of their use (they stream from HBM once per step, evict-first), partner
-    // records one iteration ahead (L1/L2 gathers), arithmetic on the current pair.
-    int e = lane;
-    int j0 = (e < n) ? __ldcs(row + e) : -1;
-    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
-    int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-    int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
-    float4 p0 = fetch(j0), p1 = fetch(j1);
-    while (e < n) {
-      const int jnn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
-      const int jnn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
-      const float4 pn0 = fetch(jn0), pn1 = fetch(jn1);
-      interact(j0, p0);
-      interact(j1, p1);
-      j0 = jn0; j1 = jn1; p0 = pn0; p1 = pn1;
-      jn0 = jnn0; jn1 = jnn1;
-      e += 64;
+    // Lanes stride the row two entries per iteration.  The entries of the NEXT iteration are
+    // loaded before the current pairs are computed (the row streams from HBM once per step,
+    // evict-first); partner records are gathered at use and the latency is covered by
+    // occupancy: measured on B200, this simple loop at 40 registers (6 CTAs/SM) beats deeper
+    // software pipelines that need 56-64 registers (profiles/r01_pair_loop_variants.txt).
+    {
+      int e = lane;
+      int j0 = (e < n) ? __ldcs(row + e) : -1;
+      int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+      while (e < n) {
+        const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+        const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+        if (j0 >= 0) interact(j0, xq[j0 & 0xffffff]);
+        if (j1 >= 0) interact(j1, xq[j1 & 0xffffff]);
+        j0 = jn0;
+        j1 = jn1;
+        e += 64;
+      }
     }
     fx = warp_sum(fx);
     fy = warp_sum(fy);
