@@ -236,3 +236,46 @@ def test_api_errors_and_formats():
     F3 = torch.zeros_like(pos)
     f0.compute(pos, box, F3)
     assert d2[0]["external"] == 2.5 and torch.allclose(F2, F3 + 1.0, atol=1e-5)
+
+
+def test_nonperiodic_cutoff_with_distinct_replicas():
+    """No box (all-zero box: no wrapping, forces.py:361) with a cutoff -- the layout of
+    BASELINE.json config 5 (protein in vacuum, several replicas): the cell grid comes from the
+    device-side bounding box, every replica has its own positions and its own lists."""
+    from torchmd_b200 import Forces
+
+    g = load_golden("water999_eq")
+    terms = ["lj", "electrostatics", "bonds", "angles"]
+    cfg = dict(cutoff=9.0, rfa=True, switch_dist=7.5)
+    nrep = 3
+    rng = np.random.default_rng(0)
+    base = g["coords"].astype(np.float64)
+    coords = np.stack([base + rng.normal(scale=0.02 * r, size=base.shape) + 50.0 * r for r in range(nrep)]).astype(np.float32)
+    pos = torch.tensor(coords, device=DEV)
+    box = torch.zeros(nrep, 3, 3, device=DEV)
+    f = Forces(params_from_golden(g, device=DEV), terms=terms, **cfg)
+    F = torch.empty_like(pos)
+    E = f.compute(pos, box, F, returnDetails=True)
+    st = f.stats()
+    assert st["ncells"][0] > 1 and not st["overflow"]
+
+    of32 = refmd.OracleForces(params_from_golden(g), terms, **cfg)
+    of64 = refmd.OracleForces(params_from_golden(g, precision=torch.float64), terms, decision_dtype=torch.float32, **cfg)
+    F64 = torch.zeros(nrep, len(base), 3, dtype=torch.float64)
+    E64 = of64.compute(pos.cpu().double(), box.cpu().double(), F64)
+    err = (F.cpu().double() - F64).abs().max().item()
+    print(f"non-periodic x{nrep}: max|dF| {err:.3e}, max|F| {F64.abs().max().item():.1f}")
+    assert err < force_tol(F64.numpy())
+    for r in range(nrep):
+        for k in terms:
+            assert abs(E[r][k] - E64[r][k]) <= 1e-5 * abs(E64[r][k]) + 2e-3, (r, k)
+        ref_pairs = of32.neighbour_pairs(pos[r].cpu(), torch.zeros(3)).numpy().astype(np.int32)
+        assert np.array_equal(f.neighbour_pairs(pos, box, replica=r).cpu().numpy(), ref_pairs)
+    # moving one replica far away re-grids that replica only; the others stay bitwise the same.
+    # (at |x| ~ 1000 A fp32 coordinates carry 6e-5 A, i.e. ~0.1 kcal/mol/A on a stiff O-H bond)
+    pos2 = pos.clone()
+    pos2[1] += 1000.0
+    F2 = torch.empty_like(pos)
+    f.compute(pos2, box, F2)
+    assert (F2[1] - F[1]).abs().max().item() < 0.5
+    assert torch.equal(F2[0], F[0]) and torch.equal(F2[2], F[2])
