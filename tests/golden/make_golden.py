@@ -511,6 +511,69 @@ def main():
     print("adversarial: %d of %d near-cutoff pairs inside (fp32), %d (fp64)" % (res["npairs_f32"], npair, res["npairs_f64"]))
     save("adversarial_cutoff", res)
 
+    # ---- G7/G8: AMBER prmtop fixtures (configs 3 and 5 of BASELINE.json) ------------------
+    # The reference reads these through moleculekit + parmed, which this image lacks; they are
+    # read with repo torchmd_b200/amber.py and evaluated with the oracle.  The alanine-dipeptide
+    # values are pinned by the reference's STORED known answers (tests/test_torchmd.py:517,605,
+    # examples/tutorial.ipynb:105); CODATA revisions of scipy.constants move them by ~2e-4.
+    from torchmd_b200 import amber
+
+    allterms = ["bonds", "angles", "dihedrals", "impropers", "1-4", "lj", "electrostatics"]
+
+    def amber_case(name, prmtop, xyz, box, nrep, fkw):
+        sysm = amber.AmberSystem(prmtop)
+        res = {}
+        for tag, prec in (("f32", torch.float32), ("f64", torch.float64)):
+            par = amber.amber_parameters(sysm, allterms, precision=prec)
+            # fp64 values on the fp32 in/out decisions: the yardstick for an fp32 kernel
+            of = refmd.OracleForces(par, allterms, decision_dtype=torch.float32, **fkw)
+            pos = torch.tensor(xyz, dtype=prec)[None].repeat(nrep, 1, 1).contiguous()
+            bx = torch.zeros(nrep, 3, 3, dtype=prec)
+            for k in range(3):
+                bx[:, k, k] = float(box[k])
+            F = torch.zeros_like(pos)
+            E = of.compute(pos, bx, F)
+            keys = list(E[0])
+            res["energy_keys"] = np.array(keys)
+            res[f"energies_{tag}"] = np.array([[e[k] for k in keys] for e in E])
+            res[f"forces_{tag}"] = F.numpy().copy()
+            p32 = of.neighbour_pairs(pos[0], torch.diagonal(bx[0])).numpy().astype(np.int32)
+            res[f"npairs_{tag}"] = np.int64(len(p32))
+            res[f"pairs_sha256_{tag}"] = np.array(hashlib.sha256(p32.tobytes()).hexdigest())
+            if tag == "f64":  # full-precision parameters; an fp32 run rounds them the same way
+                res.update({"par_" + k: v for k, v in pack_params(par).items()})
+        res["coords"] = np.asarray(xyz, dtype=np.float32)
+        res["box"] = np.asarray(box, dtype=np.float32)
+        res["terms"] = np.array(allterms)
+        for k, v in fkw.items():
+            res["cfg_" + k] = np.array(np.nan if v is None else v)
+        res["cfg_nrep"] = np.int64(nrep)
+        res["source"] = np.array("oracle/refmd.py on parameters read by torchmd_b200/amber.py (reference needs parmed)")
+        save(name, res)
+        return res
+
+    ala = os.path.join(REF, "tests/data/prod_alanine_dipeptide_amber")
+    axyz = amber.read_bincoor(os.path.join(ala, "input.coor"))
+    r1 = amber_case("ala2_nobox_rf", os.path.join(ala, "structure.prmtop"), axyz, np.zeros(3), 2,
+                    dict(cutoff=9.0, rfa=True, switch_dist=7.5))
+    assert abs(r1["energies_f64"][0].sum() + 1722.3569) < 5e-4, r1["energies_f64"][0].sum()  # test_torchmd.py:517
+    r2 = amber_case("ala2_xsc_rf", os.path.join(ala, "structure.prmtop"), axyz, amber.read_xsc(os.path.join(ala, "input.xsc")), 1,
+                    dict(cutoff=9.0, rfa=True, switch_dist=7.5))
+    e2 = dict(zip([str(k) for k in r2["energy_keys"]], r2["energies_f64"][0]))
+    for k, v in dict(electrostatics=-2568.498, lj=359.251, bonds=3.9577, angles=2.8446, dihedrals=10.5799, impropers=1.2417).items():
+        assert abs(e2[k] - v) < 2e-3, (k, e2[k], v)  # examples/tutorial.ipynb:105 (fp32 GPU run, 4-7 digits)
+    report.append("torchmd_b200/amber.py + oracle reproduce the reference's stored alanine-dipeptide energies: "
+                  "-1722.3569 (test_torchmd.py:517) to %.1e, tutorial.ipynb:105 per-term vector to 2e-3"
+                  % abs(r1["energies_f64"][0].sum() + 1722.3569))
+    thr = os.path.join(REF, "tests/data/thrombin-ligand-amber")
+    txyz, _ = read_pdb(os.path.join(thr, "structure.pdb")) if False else (None, None)
+    pdb_xyz = []
+    for line in open(os.path.join(thr, "structure.pdb")):
+        if line.startswith(("ATOM", "HETATM")):
+            pdb_xyz.append([float(line[30:38]), float(line[38:46]), float(line[46:54])])
+    amber_case("thrombin_nobox_rf", os.path.join(thr, "structure.prmtop"), np.array(pdb_xyz, dtype=np.float32), np.zeros(3), 2,
+               dict(cutoff=7.3, rfa=True, switch_dist=None))
+
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as fh:
         fh.write("Generated by tests/golden/make_golden.py from the reference at /root/reference\n")
         fh.write("(torchmd/torchmd @ 09484183e34af78bb69b27a0149aeccf1318dbc7), torch %s, numpy %s.\n" % (torch.__version__, np.__version__))

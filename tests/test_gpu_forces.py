@@ -34,6 +34,9 @@ CASES = [
     "chain_amber_periodic",
     "chain_charmm_periodic",
     "adversarial_cutoff",
+    "ala2_nobox_rf",  # BASELINE.json config 3 (all AMBER terms), 2 replicas, no box
+    "ala2_xsc_rf",  # same system in its periodic box (the tutorial's run)
+    "thrombin_nobox_rf",  # config 5: 4676-atom protein + ligand in vacuum, cutoff 7.3, 2 replicas
 ]
 
 
