@@ -233,8 +233,11 @@ def gpu_arm(args):
         eq.step(niter=100)
     integ = Integrator(system, forces, TIMESTEP_FS, dev, gamma=GAMMA_PS, T=TEMPERATURE)
     sampler = ClockSampler(local)  # runs through the warm-up too (same load), so short runs still get samples
-    for _ in range(max(3, args.warmup) // 50 + 1):
+    t_w = time.perf_counter()
+    done = 0
+    while done < max(3, args.warmup) or time.perf_counter() - t_w < 0.6:  # >= 0.6 s under load for the sampler
         ekin, pot, T = integ.step(niter=50)
+        done += 50
 
     L = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream

@@ -186,7 +186,9 @@ def bench_decomposed(args, world, rank, local, config):
     integ.use_graph, integ._graphs = True, {}
     sampler = B.ClockSampler(local) if rank == 0 else None  # samples the warm-up too: same load
     st_a = forces.stats()
-    ekin, pot, T = integ.step(niter=max(3, args.warmup))
+    # warm-up: at least 5000 steps (>= 0.4 s under load for the clock sampler); a FIXED count, the
+    # same on every rank -- a wall-clock criterion could give ranks different numbers of collectives
+    ekin, pot, T = integ.step(niter=max(3, args.warmup, 5000))
     launches_per_step = None
     if integ.use_graph:  # kernels of one captured step (the capture itself went through the counting path)
         st_b = forces.stats()
