@@ -384,6 +384,12 @@ def main():
     save("argon100_nocut", force_case(a100, aff, ["lj"], cutoff=None, rfa=False, switch_dist=None))
     save("argon100_cut", force_case(a100, aff, ["lj"], cutoff=9.0, rfa=False, switch_dist=7.5))
 
+    # repulsion / repulsionCG terms (forces.py:418-450).  The reference only builds the A/B tables
+    # when "lj" is among the terms (forces.py:45-46) -- repulsion alone raises AttributeError there --
+    # so the runnable combination is the mix.
+    save("argon100_lj_rep_mix", force_case(a100, aff, ["lj", "repulsion", "repulsioncg"], cutoff=12.0, rfa=False, switch_dist=10.0))
+    save("argon100_lj_rep_nocut", force_case(a100, aff, ["lj", "repulsioncg", "repulsion"], cutoff=None, rfa=False, switch_dist=None))
+
     # ---- G3: synthetic water, 999 atoms, equilibrated with the reference --------
     d = testsystems.water_box(333, seed=0)
     # our array-built parameters must equal the reference builder's output

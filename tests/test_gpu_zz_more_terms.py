@@ -1,0 +1,31 @@
+"""Less common pair terms through the CUDA path: repulsion and repulsionCG (forces.py:418-450) alone
+mixed with LJ (the reference builds the A/B tables only when "lj" is enabled, forces.py:45-46, so that
+is the runnable combination) -- the run-time-flag variant of the pair kernel.  Golden vectors from the
+unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from test_gpu_forces import force_tol, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["argon100_lj_rep_mix", "argon100_lj_rep_nocut"])
+def test_repulsion_terms(name):
+    g = load_golden(name)
+    f, pos, box, F, E = run_gpu(g)
+    ref = g["forces_f64"]
+    err = np.abs(F.cpu().numpy().astype(np.float64) - ref).max()
+    scale = max(np.abs(ref).max(), 1e-30)
+    print(f"{name}: max|dF| {err:.3e} (max|F| {scale:.3e})")
+    assert err <= max(force_tol(ref) * 1e-2, 2e-6 * scale)  # tiny forces: relative fp32 bound
+    keys = [str(k) for k in g["energy_keys"]]
+    for c, k in enumerate(keys):
+        e_ref = g["energies_f64"][0, c]
+        assert abs(E[0][k] - e_ref) <= 1e-5 * abs(e_ref) + 1e-9, (k, E[0][k], e_ref)
+    pairs = f.neighbour_pairs(pos, box).cpu().numpy()
+    assert len(pairs) == int(g["npairs_f32"])
+    if "pairs_f32" in g:
+        assert np.array_equal(pairs, g["pairs_f32"])
