@@ -29,3 +29,20 @@ def test_repulsion_terms(name):
     assert len(pairs) == int(g["npairs_f32"])
     if "pairs_f32" in g:
         assert np.array_equal(pairs, g["pairs_f32"])
+
+
+def test_device_cell_grid_matches_host_description():
+    """The grid the library builds on the device equals torchmd_b200.neighbourlist.cell_grid."""
+    from torchmd_b200 import Forces, System, testsystems
+    from torchmd_b200.neighbourlist import cell_grid, neighbour_list
+
+    sysd = testsystems.water_box(1000, seed=5)
+    par = testsystems.water_parameters(sysd, device="cuda:0")
+    system = System(len(sysd["coords"]), 1, torch.float32, "cuda:0")
+    system.set_positions(sysd["coords"])
+    system.set_box(sysd["box"])
+    f = Forces(par, terms=["lj", "electrostatics"], cutoff=9.0, rfa=True, switch_dist=7.5, skin=1.0)
+    pairs = neighbour_list(f, system.pos, system.box)
+    want = cell_grid([float(x) for x in sysd["box"]], cutoff=9.0, skin=1.0)
+    assert f.stats()["ncells"] == want["ncell"]
+    assert pairs.shape[1] == 2 and bool((pairs[:, 0] < pairs[:, 1]).all())

@@ -167,3 +167,18 @@ def test_synthetic_inputs_are_deterministic():
     assert len(par.get_exclusions()) == 128 + 64
     ar = testsystems.argon_box(50, seed=1)
     assert ar["coords"].shape == (50, 3)
+
+
+def test_cell_grid_matches_the_library_rules():
+    from torchmd_b200.neighbourlist import cell_grid
+
+    g = cell_grid([99.93, 99.93, 99.93], cutoff=9.0, skin=1.0)
+    assert g["ncell"] == (19, 19, 19) and g["reach"] == (2, 2, 2)
+    assert all(w >= g["rlist"] / 2 for w in g["width"])
+    small = cell_grid([16.919, 16.633, 16.639], cutoff=7.3)  # tests/water: too short for 5 cells
+    assert small["ncell"] == (1, 1, 1) and small["reach"] == (0, 0, 0)
+    slab = cell_grid([200.0, 30.0, 12.0], cutoff=9.0, skin=1.0)
+    assert slab["ncell"][0] == 39 and slab["ncell"][1] == 5 and slab["ncell"][2] == 1
+    # the reference stub would leave a 0.93 A sliver as the last bin of a 99.93 A box;
+    # here every cell has the same width and the widths tile the box
+    assert abs(g["width"][0] * g["ncell"][0] - 99.93) < 1e-9
