@@ -112,10 +112,8 @@ struct tmd_ctx {
   int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
   std::vector<float> box_host;       // (nrep,3)
   std::vector<float> charges_host;   // unscaled charges
-  uint64_t call_index = 0;           // parity selects the rebuild flag
   int64_t launches = 0;
   int64_t force_calls = 0;
-  bool overflow_reported = false;
   double* ke_scratch = nullptr;      // (nrep) doubles for the host entry
   double* e_scratch = nullptr;       // (nrep, TMD_NUM_ENERGIES)
 };

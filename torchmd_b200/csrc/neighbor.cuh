@@ -14,12 +14,17 @@
 //   k_place       counting-sort scatter.
 //   k_sort_pack   order every cell by original atom index (deterministic),
 //                 write the sorted records and the inverse permutation.
-//   k_build_list  full Verlet list: for every atom all partners within
-//                 cutoff+skin that are not excluded, one 128-byte-aligned row
-//                 per atom so a warp streams a row with coalesced loads.
+//   k_build_list  full Verlet list: one CTA per cell stages the surrounding cells in
+//                 shared memory (already shifted by their periodic image) and writes,
+//                 for every atom of the cell, all partners within cutoff+skin that are
+//                 not excluded into one 128-byte-aligned row per atom.
+//   k_rebuild     the five kernels above as the phases of ONE cooperative launch
+//                 (grid-wide barriers in between); opt-in, see tmd_b200.cu.
 //
 // Every rebuild kernel returns immediately unless the replica's rebuild flag is
-// set, so the host can enqueue them unconditionally (no host round trip).
+// set, so the host can enqueue them unconditionally (no host round trip).  The
+// flag, its parity and every counter live on the device: a captured CUDA graph of
+// one step is replayable.
 #pragma once
 #include <cooperative_groups.h>
 

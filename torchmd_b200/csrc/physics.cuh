@@ -81,13 +81,6 @@ TMD_HD float rsqrt_fast(float a) {
 #endif
 }
 
-TMD_HD float rcp_rn(float a) {
-#if defined(__CUDA_ARCH__)
-  return __frcp_rn(a);
-#else
-  return 1.0f / a;
-#endif
-}
 // 1/sqrt(a) to ~1 ulp: hardware approximation (2 ulp) + one Newton step.  The r^-12
 // wall amplifies the relative error of 1/r thirteen-fold, so the raw approximation
 // alone would cost ~5e-5 kcal/mol/A on a close O-O pair.

@@ -467,7 +467,6 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       if (total >= R) ctx->coop_blocks = std::max(1, total / R);
     }
   }
-  ctx->call_index = 0;
   priv(ctx).dirty = false;
   return TMD_OK;
 }
@@ -501,7 +500,6 @@ static inline dim3 owned_grid(const tmd_ctx* ctx, int threads) {
 static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, cudaStream_t st) {
   DeviceState& d = ctx->d;
   const int N = ctx->natoms, R = ctx->nrep;
-  ctx->call_index++;
   ctx->force_calls++;
   if (energies) TMD_CUDA(cudaMemsetAsync(energies, 0, (size_t)R * TMD_NUM_ENERGIES * sizeof(double), st));
 
