@@ -78,4 +78,92 @@ void hc_torsion(int n, const float* r12, const float* r23, const float* r34, con
   }
 }
 
+// ---- fixed-point separations (k_pair_fx) ---------------------------------------------
+// class per pair: 0 outside, 1 inside, 2 in the decision band (kernel re-does the reference
+// arithmetic); w/s are the fixed-point values.  Margin coefficients exactly as finalize() does.
+void hc_fx_decide(int n, const float* pi, const float* pj, const float* box, float s_max, double rmax, float pmax,
+                  float* w_out, float* s_out, int* cls_out, float* margin_out) {
+  double lmax = 0, c0, c1, inv[3];
+  float unit[3];
+  for (int k = 0; k < 3; ++k) {
+    unit[k] = (float)((double)box[k] / 4294967296.0);
+    inv[k] = 4294967296.0 / (double)box[k];
+    if (box[k] > lmax) lmax = box[k];
+  }
+  fx_margin(rmax, lmax, &c0, &c1);
+  const float fc0 = (float)(c0 * 1.0000002), fc1 = (float)(c1 * 1.0000002);
+  const float margin = fmaf(fc1, pmax, fc0);
+  *margin_out = margin;
+  const float s_hi = s_max + margin, s_lo = s_max - margin;
+  for (int q = 0; q < n; ++q) {
+    float w[3];
+    for (int k = 0; k < 3; ++k)
+      w[k] = fx_delta(fx_encode(pi[3 * q + k], inv[k]), fx_encode(pj[3 * q + k], inv[k]), unit[k]);
+    const float s = fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0]));
+    w_out[3 * q] = w[0]; w_out[3 * q + 1] = w[1]; w_out[3 * q + 2] = w[2];
+    s_out[q] = s;
+    cls_out[q] = (s < s_lo) ? 1 : ((s <= s_hi) ? 2 : 0);
+  }
+}
+
+// Host emulation of the pair kernels' VALUE arithmetic over a given list of in-cutoff pairs
+// (i<j, LJ+switch+RF or any term set): variant 0 = k_pair (reference-rounded separation,
+// sub_err across the boundary), 1 = k_pair_fx (fixed-point separation).  Forces are
+// accumulated in fp32 like the kernel (different order).  For error budgeting only.
+void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const float* pos, const float* qs,
+                    const int* type, int ntypes, const float* AB, const float* box, unsigned terms, float cutoff,
+                    int has_switch, float switch_dist, int rfa, float krf, float crf, float* forces) {
+  PairParams pp{};
+  pp.terms = terms;
+  pp.has_cutoff = 1;
+  pp.cutoff = cutoff;
+  pp.has_switch = has_switch;
+  pp.switch_dist = switch_dist;
+  pp.inv_sw_width = has_switch ? 1.0f / (cutoff - switch_dist) : 0.f;
+  pp.rfa = rfa;
+  pp.krf = krf;
+  pp.crf = crf;
+  pp.two_krf = 2.0f * krf;
+  const bool mode1 = (terms == (T_LJ | T_ELEC) && has_switch && rfa);
+  float unit[3], iL[3];
+  double inv[3];
+  for (int k = 0; k < 3; ++k) {
+    unit[k] = (float)((double)box[k] / 4294967296.0);
+    inv[k] = 4294967296.0 / (double)box[k];
+    iL[k] = 1.0f / box[k];
+  }
+  for (int e = 0; e < natoms * 3; ++e) forces[e] = 0.f;
+  for (int q = 0; q < npairs; ++q) {
+    const int i = pairs[2 * q], j = pairs[2 * q + 1];
+    float w[3], s;
+    if (variant == 1) {
+      for (int k = 0; k < 3; ++k) w[k] = fx_delta(fx_encode(pos[3 * i + k], inv[k]), fx_encode(pos[3 * j + k], inv[k]), unit[k]);
+      s = fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0]));
+    } else {
+      bool straddle = false;
+      float d0[3];
+      for (int k = 0; k < 3; ++k) {
+        float r;
+        d0[k] = sub_rn(pos[3 * i + k], pos[3 * j + k]);
+        w[k] = min_image_exact(d0[k], box[k], iL[k], r);
+        straddle |= (r != 0.f);
+      }
+      s = norm2_ref(w[0], w[1], w[2]);
+      if (straddle) {
+        for (int k = 0; k < 3; ++k) w[k] += sub_err(pos[3 * i + k], pos[3 * j + k], d0[k]);
+        s = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+      }
+    }
+    const float* ab = AB + 2 * (type[i] * ntypes + type[j]);
+    float a = 0, b = 0, c = 0, d = 0, rinv;
+    const float dedr = mode1 ? pair_terms<1>(pp, s, qs[i] * qs[j], ab[0], ab[1], a, b, c, d, rinv)
+                             : pair_terms<0>(pp, s, qs[i] * qs[j], ab[0], ab[1], a, b, c, d, rinv);
+    const float cf = dedr * rinv;
+    for (int k = 0; k < 3; ++k) {
+      forces[3 * i + k] -= w[k] * cf;
+      forces[3 * j + k] += w[k] * cf;
+    }
+  }
+}
+
 }  // extern "C"

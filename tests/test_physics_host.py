@@ -174,3 +174,113 @@ def test_bond_angle_torsion_match_oracle(hc):
         ok = (cA > 0.3) & (cB > 0.3)
         assert np.abs(e[ok] - eo.numpy()[ok]).max() < 5e-5 * max(1, eo.abs().max().item())
         assert np.abs(ft[ok] - fo[ok]).max() < 2e-4 * max(1, np.abs(fo[ok]).max())
+
+
+# ---- fixed-point separations of the periodic pair kernel (k_pair_fx) -----------------------
+def fx_decide(hc, pi, pj, box, cutoff, rmax, pmax):
+    n = len(pi)
+    w = np.zeros((n, 3), F32)
+    s = np.zeros(n, F32)
+    cls = np.zeros(n, np.int32)
+    margin = C.c_float(0)
+    smax = hc.hc_squared_threshold(F32(cutoff))
+    hc.hc_fx_decide(n, p(np.ascontiguousarray(pi, F32)), p(np.ascontiguousarray(pj, F32)), p(box.astype(F32)),
+                    C.c_float(smax), C.c_double(rmax), C.c_float(pmax), p(w), p(s), p(cls), C.byref(margin))
+    return w, s, cls, margin.value
+
+
+def test_fx_separation_is_the_exact_minimum_image(hc):
+    """Integer subtraction of the fixed-point coordinates == fp64 minimum image of the fp32
+    positions, also for atoms that drifted several boxes away and across the boundary."""
+    rng = np.random.default_rng(5)
+    box = np.array([99.93, 87.41, 120.07], F32)
+    n = 200000
+    pi = (rng.uniform(0, 1, (n, 3)) * box + rng.integers(-6, 7, (n, 3)) * box).astype(F32)
+    d = rng.normal(size=(n, 3))
+    d *= (rng.uniform(0.5, 11.0, n) / np.linalg.norm(d, axis=1))[:, None]
+    pj = (pi.astype(np.float64) - d + rng.integers(-6, 7, (n, 3)) * box.astype(np.float64)).astype(F32)
+    w, s, _, _ = fx_decide(hc, pi, pj, box, 9.0, 11.0, 8 * 120.07)
+    L = box.astype(np.float64)
+    d64 = pi.astype(np.float64) - pj.astype(np.float64)
+    w64 = d64 - L * np.round(d64 / L)
+    err = np.abs(w - w64)
+    # quantisation L/2^32 per coordinate (x2) + three fp32 roundings of |w|
+    bound = 2 * L.max() / 2**32 + 3 * 2.0**-24 * np.abs(w64) + 1e-12
+    assert (err <= bound).all(), (err - bound).max()
+    assert err.max() < 3e-6
+
+
+def test_fx_decision_band_is_sound(hc):
+    """Outside the band the fixed-point decision IS the reference's; the band is thin."""
+    g = load_golden("adversarial_cutoff")
+    xyz, box = g["coords"], g["box"]
+    pi, pj = xyz[0::2], xyz[1::2]
+    ref = np.zeros(len(pi), bool)
+    ref[g["pairs_f32"][:, 0] // 2] = True
+    pmax = float(np.abs(xyz).max())
+    _, _, cls, margin = fx_decide(hc, pi, pj, box, 9.0, 11.0, pmax)
+    assert ((cls == 2) | ((cls == 1) == ref)).all()
+    assert (cls == 2).any()  # the adversarial pairs sit within ulps of the cutoff: they must land in the band
+    assert margin < 0.02
+
+    # random pairs in a production-size box, atoms anywhere within +-4 boxes
+    rng = np.random.default_rng(6)
+    box = np.array([99.93, 99.93, 99.93], F32)
+    n = 400000
+    pi = (rng.uniform(-4, 5, (n, 3)) * box).astype(F32)
+    d = rng.normal(size=(n, 3))
+    d *= (rng.uniform(8.9, 9.1, n) / np.linalg.norm(d, axis=1))[:, None]  # all near the cutoff
+    pj = (pi.astype(np.float64) - d + rng.integers(-2, 3, (n, 3)) * box.astype(np.float64)).astype(F32)
+    pmax = float(max(np.abs(pi).max(), np.abs(pj).max()))
+    _, s, cls, margin = fx_decide(hc, pi, pj, box, 9.0, 11.0, pmax)
+    _, sref, inside = decide(hc, pi, pj, box, 9.0)
+    assert ((cls == 2) | ((cls == 1) == inside)).all()
+    assert np.abs(s - sref).max() <= margin  # the bound the band is built from
+    # band half-width in r is margin / (2 rc): a 0.2 A window around the cutoff holds a few % of it
+    assert (cls == 2).mean() < 0.05
+
+
+def _water_pair_setup(name="water999_eq"):
+    g = load_golden(name)
+    cfg = golden_cfg(g)
+    par64 = __import__("conftest").params_from_golden(g, precision=torch.float64)
+    terms = ["lj", "electrostatics"]
+    of = refmd.OracleForces(par64, terms, decision_dtype=torch.float32, cutoff=cfg["cutoff"], rfa=cfg["rfa"],
+                            switch_dist=cfg["switch_dist"])
+    return g, cfg, par64, of
+
+
+@pytest.mark.parametrize("drift", [False, True])
+def test_fx_pair_forces_meet_the_tolerance(hc, drift):
+    """Host emulation of both pair kernels' value arithmetic on the equilibrated 999-atom water
+    box against the fp64 oracle (same fp32 pair set): the fixed-point path must be at least as
+    accurate as the float path, also when molecules have drifted out of the primary box."""
+    g, cfg, par64, of = _water_pair_setup()
+    pos = g["coords"].astype(F32).copy()
+    box = g["box"].astype(F32)
+    if drift:
+        rng = np.random.default_rng(7)
+        shift = rng.integers(-3, 4, (len(pos) // 3, 3)).repeat(3, axis=0)  # whole molecules
+        pos = (pos.astype(np.float64) + shift * box.astype(np.float64)).astype(F32)
+    pos_t = torch.tensor(pos)[None]
+    box_t = torch.diag(torch.tensor(box))[None]
+    f64 = torch.zeros(1, len(pos), 3, dtype=torch.float64)
+    of.compute(pos_t.double(), box_t.double(), f64)
+    pairs = of.neighbour_pairs(pos_t[0], torch.tensor(box)).numpy().astype(np.int32)
+    types = g["par_types"].astype(np.int32)
+    nt = int(types.max()) + 1
+    AB = np.stack([par64.A.numpy(), par64.B.numpy()], -1).astype(F32).reshape(nt, nt, 2)
+    qs = (g["par_charges"] * math.sqrt(refmd.COULOMB)).astype(F32)
+    eps, rc = 78.5, cfg["cutoff"]
+    krf = (1 / rc**3) * (eps - 1) / (2 * eps + 1)
+    crf = (1 / rc) * (3 * eps) / (2 * eps + 1)
+    errs = []
+    for variant in (0, 1):
+        out = np.zeros((len(pos), 3), F32)
+        hc.hc_pair_forces(variant, len(pos), len(pairs), p(np.ascontiguousarray(pairs)), p(pos), p(qs), p(types), nt,
+                          p(np.ascontiguousarray(AB)), p(box), (1 << 5) | (1 << 6), C.c_float(rc), 1,
+                          C.c_float(cfg["switch_dist"]), 1, C.c_float(krf), C.c_float(crf), p(out))
+        errs.append(np.abs(out.astype(np.float64) - f64[0].numpy()).max())
+    print(f"max |dF| vs fp64 oracle: float path {errs[0]:.2e}, fixed-point path {errs[1]:.2e} (drift={drift})")
+    assert errs[1] < 1e-4
+    assert errs[1] <= errs[0] * 1.25 + 5e-6

@@ -22,6 +22,10 @@ struct Grid {
   float invL[3];    // 1/L
   float origin[3];  // lower corner (non-periodic); 0 for periodic
   float inv_w[3];   // 1 / cell width
+  // fixed-point coordinates of the periodic pair kernel (physics.cuh, fx_encode)
+  float fx_unit[3];     // L / 2^32
+  float fx_c0, fx_c1;   // |s_fx - s_ref| <= fx_c0 + fx_c1 * max|coordinate|
+  double fx_inv[3];     // 2^32 / L
 };
 
 // Flags/counters per replica (device ints).
@@ -32,6 +36,7 @@ enum {
   F_NREBUILD = 3,
   F_MAXNBR = 4,
   F_FARPOS = 5,    // a position was further than 2000 box lengths from the origin
+  F_PMAX = 6,      // bits of the largest |coordinate| seen since the box was set (+inf if one was not finite)
   F_COUNT = 8
 };
 
@@ -54,6 +59,7 @@ struct DeviceState {
   int ntypes;
   // per replica dynamic data (index [rep*natoms + k])
   float4* xq_s;          // sorted: raw x,y,z + scaled charge
+  int4* xf_s;            // sorted: fixed-point x,y,z (fx_encode) + bits of the scaled charge; null = not in use
   int* type_s;           // sorted atom type
   float4* xw_s;          // sorted: coordinates folded into the box at the last build (list build only)
   int* perm;             // sorted slot -> original atom
@@ -110,6 +116,7 @@ struct tmd_ctx {
   bool safe_image = false;           // guard-free minimum image valid (see min_image_fast)
   int coop_blocks = 0;               // CTAs per replica of the cooperative rebuild kernel (0: separate kernels)
   int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
+  int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
   std::vector<float> box_host;       // (nrep,3)
   std::vector<float> charges_host;   // unscaled charges
   int64_t launches = 0;

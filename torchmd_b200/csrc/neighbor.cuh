@@ -81,6 +81,17 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
   }
   const int k = S.inv[a];
   S.xq_s[(size_t)r * (S.natoms + 1) + k] = make_float4(x, y, z, S.q[i]);
+  if (S.xf_s) {  // fixed-point records of the periodic pair kernel (physics.cuh, fx_encode)
+    const Grid* g = S.grid + r;
+    S.xf_s[(size_t)r * (S.natoms + 1) + k] =
+        make_int4(fx_encode(x, g->fx_inv[0]), fx_encode(y, g->fx_inv[1]), fx_encode(z, g->fx_inv[2]),
+                  __float_as_int(S.q[i]));
+    float m = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    if (!(fabsf(x) < INFINITY) || !(fabsf(y) < INFINITY) || !(fabsf(z) < INFINITY)) m = INFINITY;
+    const unsigned am = __activemask();
+    const int mb = __reduce_max_sync(am, __float_as_int(m));  // non-negative floats order like ints
+    if ((threadIdx.x & 31) == __ffs(am) - 1 && mb > fl[F_PMAX]) atomicMax(fl + F_PMAX, mb);
+  }
 }
 
 // ---- rebuild phases -----------------------------------------------------------------
@@ -252,6 +263,12 @@ __device__ __forceinline__ void phase_sort_pack(const DeviceState& S, int r, int
       const float4 p = S.pos_ref[base + i];
       S.inv[base + i] = b + e;
       S.xq_s[(size_t)r * (S.natoms + 1) + b + e] = make_float4(p.x, p.y, p.z, S.q[i]);
+      if (S.xf_s) {
+        const Grid* g = S.grid + r;
+        S.xf_s[(size_t)r * (S.natoms + 1) + b + e] =
+            make_int4(fx_encode(p.x, g->fx_inv[0]), fx_encode(p.y, g->fx_inv[1]), fx_encode(p.z, g->fx_inv[2]),
+                      __float_as_int(S.q[i]));
+      }
       S.type_s[base + b + e] = S.type[i];
       float wx = p.x, wy = p.y, wz = p.z;  // coordinates folded into [0, L] for the list build
       if (gper) {

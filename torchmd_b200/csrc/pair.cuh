@@ -161,4 +161,142 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
   }
 }
 
+// ---- periodic boxes: fixed-point separations -------------------------------------------
+// Same mapping and list as k_pair.  The partner records hold fixed-point coordinates
+// (physics.cuh, fx_encode): the separation is one integer subtraction per component --
+// minimum image included, exact to L/2^32 -- instead of the reference's rounded
+// subtract / multiply / round / multiply / subtract chain, and pairs that straddle the box
+// need no compensation.  The decision stays the reference's: outside the band
+// s_max -+ margin the two squared distances provably agree; inside it (about 1e-4 of the
+// pairs) the reference arithmetic is re-done on the original positions.
+// SMALLT: the LJ table (<= 16 types) is staged in shared memory.
+constexpr int FX_SMALLT_MAX = 16;
+#ifndef PAIR_FX_MINBLOCKS
+#define PAIR_FX_MINBLOCKS PAIR_MINBLOCKS
+#endif
+
+// Partner record of a replica's fixed-point array at byte offset `off` from `base` (an
+// integer the compiler cannot see through, so the replica's base stays in a register pair
+// instead of being re-derived per pair).
+__device__ __forceinline__ int4 fx_record(unsigned long long base, unsigned off) {
+  int4 v;
+  asm("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(base + off));
+  return v;
+}
+
+template <bool ENERGY, int MODE, bool SMALLT>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX_MINBLOCKS)
+k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energies) {
+  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int kk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  const int N = S.natoms;
+  const size_t base = (size_t)r * N;
+  const PairParams pp = S.pp;
+  float e_el = 0.f, e_lj = 0.f, e_rep = 0.f, e_cg = 0.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
+
+  __shared__ float2 ab_s[SMALLT ? FX_SMALLT_MAX * FX_SMALLT_MAX : 1];
+  if (SMALLT) {
+    static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX <= PAIR_WARPS * 32, "one table entry per thread");
+    if ((int)threadIdx.x < S.ntypes * S.ntypes) ab_s[threadIdx.x] = S.AB[threadIdx.x];
+    __syncthreads();
+  }
+
+  if (kk < S.own_n) {
+    const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
+    const int4* __restrict__ xf = S.xf_s + (size_t)r * (N + 1);
+    unsigned long long xf_base = reinterpret_cast<unsigned long long>(xf);
+    asm volatile("" : "+l"(xf_base));
+    const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+    const int n = S.nnbr[base + k];
+    const int4 pi = xf[k];
+    const float qi = __int_as_float(pi.w);
+    const int ti = S.type_s[base + k] * S.ntypes;
+    const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 8u;  // this atom's row of the staged table
+    const bool need_ab = MODE == 1 ? true : (pp.terms & (T_LJ | T_REP | T_REPCG)) != 0;
+    const Grid* g = S.grid + r;
+    const float ux = g->fx_unit[0], uy = g->fx_unit[1], uz = g->fx_unit[2];
+    // decision band around the reference's threshold; a non-finite coordinate somewhere
+    // (margin = inf) sends every pair to the reference arithmetic
+    const float margin = fmaf(g->fx_c1, __int_as_float(S.flags[r * F_COUNT + F_PMAX]), g->fx_c0);
+    const float s_hi = pp.s_max + margin, s_lo = pp.s_max - margin;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+
+    float s_skipped = INFINITY;  // smallest squared distance not taken below: <= s_hi means a pair sits in the decision band
+    auto accumulate = [&](int entry, float wx, float wy, float wz, float s, float qj) {
+      float2 ab = make_float2(0.f, 0.f);
+      if (need_ab) {
+        if (SMALLT) {
+          asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ab.x), "=f"(ab.y) : "r"(ab_row + (((unsigned)entry >> 24) << 3)));
+        } else {
+          ab = __ldg(S.AB + ti + (entry >> 24));
+        }
+      }
+      float rinv;
+      const float dedr = pair_terms<MODE>(pp, s, qi * qj, ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
+      const float c = dedr * rinv;  // force on i is -unit*dE/dr = -(w/r) dE/dr
+      fx -= wx * c;
+      fy -= wy * c;
+      fz -= wz * c;
+    };
+    auto interact = [&](int entry, const int4 pj) {
+      const float wx = fx_delta(pi.x, pj.x, ux), wy = fx_delta(pi.y, pj.y, uy), wz = fx_delta(pi.z, pj.z, uz);
+      const float s = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+      if (s < s_lo) accumulate(entry, wx, wy, wz, s, __int_as_float(pj.w));
+      else s_skipped = fminf(s_skipped, s);
+    };
+    {
+      int e = lane;
+      int j0 = (e < n) ? __ldcs(row + e) : -1;
+      int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+      while (e < n) {
+        const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+        const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+        if (j0 >= 0) interact(j0, fx_record(xf_base, ((unsigned)j0 << 4) & 0x0ffffff0u));
+        if (j1 >= 0) interact(j1, fx_record(xf_base, ((unsigned)j1 << 4) & 0x0ffffff0u));
+        j0 = jn0;
+        j1 = jn1;
+        e += 64;
+      }
+    }
+    if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
+      // rare (a few percent of the rows): re-scan the row and give the pairs inside the band
+      // the reference's own decision on the original positions
+      const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
+      for (int e = lane; e < n; e += 32) {
+        const int entry = row[e];
+        const int j = entry & 0xffffff;
+        const int4 pj = xf[j];
+        const float wx = fx_delta(pi.x, pj.x, ux), wy = fx_delta(pi.y, pj.y, uy), wz = fx_delta(pi.z, pj.z, uz);
+        const float s = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+        if (!(s < s_lo) && s <= s_hi) {
+          const float4 a = xq[k], b = xq[j];
+          if (ref_inside(a.x, a.y, a.z, b.x, b.y, b.z, g->L[0], g->L[1], g->L[2], g->invL[0], g->invL[1],
+                         g->invL[2], pp.s_max))
+            accumulate(entry, wx, wy, wz, s, __int_as_float(pj.w));
+        }
+      }
+    }
+    fx = warp_sum(fx);
+    fy = warp_sum(fy);
+    fz = warp_sum(fz);
+    if (lane == 0) {
+      float* f = forces + (base + S.perm[base + k]) * 3;
+      f[0] = fx;
+      f[1] = fy;
+      f[2] = fz;
+    }
+  }
+  if (ENERGY) {
+    __shared__ double red[PAIR_WARPS];
+    double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
+    const uint32_t terms = MODE == 1 ? (T_LJ | T_ELEC) : pp.terms;
+    if (terms & T_ELEC) block_accumulate<PAIR_WARPS>(0.5 * (double)e_el, E + TMD_E_ELECTROSTATICS, red);
+    if (terms & T_LJ) block_accumulate<PAIR_WARPS>(0.5 * (double)e_lj, E + TMD_E_LJ, red);
+    if (terms & T_REP) block_accumulate<PAIR_WARPS>(0.5 * (double)e_rep, E + TMD_E_REPULSION, red);
+    if (terms & T_REPCG) block_accumulate<PAIR_WARPS>(0.5 * (double)e_cg, E + TMD_E_REPULSIONCG, red);
+  }
+}
+
 }  // namespace tmd

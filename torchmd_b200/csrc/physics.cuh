@@ -158,6 +158,58 @@ TMD_HD float norm2_ref(float x, float y, float z) {
   return fma_rn(z, z, fma_rn(y, y, mul_rn(x, x)));
 }
 
+// The reference's cutoff decision for one pair of a periodic box, from the original fp32
+// positions (guarded minimum image: valid for any separation).
+TMD_HD bool ref_inside(float xi, float yi, float zi, float xj, float yj, float zj,
+                       float Lx, float Ly, float Lz, float iLx, float iLy, float iLz, float s_max) {
+  const float wx = min_image(sub_rn(xi, xj), Lx, iLx);
+  const float wy = min_image(sub_rn(yi, yj), Ly, iLy);
+  const float wz = min_image(sub_rn(zi, zj), Lz, iLz);
+  return norm2_ref(wx, wy, wz) <= s_max;
+}
+
+// ---- fixed-point periodic coordinates ---------------------------------------------------
+// For the pair kernel of a periodic box a coordinate x along a dimension of length L is
+// also kept as the 32-bit integer  X = round(x * 2^32 / L) mod 2^32  (computed in fp64 from
+// the caller's fp32 position, once per atom and step).  The two's-complement difference
+// X_i - X_j then IS the minimum-image separation in units of L / 2^32 (2.3e-8 A for
+// L = 100 A): exact, no image search, no loss of low bits across the boundary or for atoms
+// that drifted several boxes away -- the VALUES get better than the reference's own fp32
+// path.  The cutoff DECISION must still be the reference's; the squared distance s_fx
+// computed this way differs from the reference's rounded s_ref by at most
+//     m = c0 + c1 * P,      P = largest |coordinate| in the system
+// (fx_margin below), so  s_fx < s_max - m  =>  inside,  s_fx > s_max + m  =>  outside, and only
+// the ~1e-4 of the pairs in between re-do the reference's arithmetic on the original
+// positions (ref_inside).
+TMD_HD int32_t fx_encode(float x, double inv_unit) {
+#if defined(__CUDA_ARCH__)
+  return (int32_t)(uint32_t)(unsigned long long)__double2ll_rn((double)x * inv_unit);  // saturating, NaN -> 0
+#else
+  const double v = (double)x * inv_unit;
+  if (!(fabs(v) < 9.0e18)) return 0;
+  return (int32_t)(uint32_t)(unsigned long long)llrint(v);
+#endif
+}
+TMD_HD float fx_delta(int32_t a, int32_t b, float unit) {
+  return (float)(int32_t)((uint32_t)a - (uint32_t)b) * unit;
+}
+
+// Bound on |s_fx - s_ref| for every pair whose true minimum-image distance is <= rmax
+// (host only; u = 2^-24 is the relative error of one rounded fp32 operation).
+//   reference (forces.py:360-372): d = fl(p_i - p_j), |d| <= 2P, error <= 2uP;
+//   m = fl(L * n), |L n| <= 2P + L/2, error <= u (2P + L);  w = fl(d - m), error <= u L / 2
+//   (n = round(fl(d / L)) is the true image count for these pairs);  so each component of
+//   w_ref is within  e_ref = u (4P + 1.5 L)  of the exact separation.
+//   fixed point: quantisation <= L 2^-32, then int->float, *unit (itself rounded): 3u |w|.
+//   s = x*x + y*y + z*z: at most 3 roundings of a sum of positive terms on either side.
+// |s_a - s_b| <= 2 rmax sqrt(3) (e_ref + e_fx) + 6u rmax^2, doubled for second-order terms.
+inline void fx_margin(double rmax, double Lmax, double* c0, double* c1) {
+  const double u = 1.0 / 16777216.0, q = 1.7320508075688772;
+  const double e_fix = Lmax / 4294967296.0 + 3.0 * u * rmax;
+  *c0 = 2.0 * (2.0 * rmax * q * (1.5 * u * Lmax + e_fix) + 6.0 * u * rmax * rmax);
+  *c1 = 2.0 * (2.0 * rmax * q * 4.0 * u);
+}
+
 // ---- pair parameters (uniform per launch) -----------------------------------------
 struct PairParams {
   uint32_t terms;     // TMD_TERM(...) mask of pair terms

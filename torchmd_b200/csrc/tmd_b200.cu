@@ -153,7 +153,7 @@ int tmd_destroy(tmd_ctx* ctx) {
                   ctx->bonds.idx, ctx->bonds.prm, ctx->angles.idx, ctx->angles.prm,
                   ctx->torsions[0].idx, ctx->torsions[0].term_ptr, ctx->torsions[0].terms,
                   ctx->torsions[1].idx, ctx->torsions[1].term_ptr, ctx->torsions[1].terms,
-                  ctx->pairs14.idx, ctx->pairs14.prm, ctx->bonded_atom_ptr, ctx->bonded_entries};
+                  ctx->pairs14.idx, ctx->pairs14.prm, ctx->bonded_atom_ptr, ctx->bonded_entries, ctx->xf_buf};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
@@ -376,6 +376,34 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   d.check_far = ctx->safe_image ? 1 : 0;
   ctx->pair_mode = (ctx->pair_mask == (T_LJ | T_ELEC) && d.pp.has_switch && d.pp.rfa) ? 1 : 0;
 
+  // Fixed-point separations in the pair kernel (k_pair_fx): periodic box with the guard-free
+  // image condition.  Opt-in (TMD_B200_FX=1) until it has been through the B200 parity suite.
+  d.xf_s = nullptr;
+  {
+    const char* env = getenv("TMD_B200_FX");
+    if (env && env[0] == '1' && ctx->safe_image && ctx->pair_mask) {
+      const size_t n = (size_t)R * N + R;
+      if ((rc = device_alloc(&ctx->xf_buf, n))) return rc;
+      TMD_CUDA(cudaMemset(ctx->xf_buf, 0, n * sizeof(int4)));
+      d.xf_s = ctx->xf_buf;
+      const double rmax = ctx->cutoff + 2.0 * ctx->skin + 2.0 * margin;  // no listed pair is further apart
+      for (int r = 0; r < R; ++r) {
+        Grid& g = grids[r];
+        double lmax = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          const double L = (double)g.L[k];
+          g.fx_unit[k] = (float)(L / 4294967296.0);
+          g.fx_inv[k] = 4294967296.0 / L;
+          lmax = std::max(lmax, L);
+        }
+        double c0, c1;
+        fx_margin(rmax, lmax, &c0, &c1);
+        g.fx_c0 = (float)(c0 * 1.0000002);  // never round the bound down
+        g.fx_c1 = (float)(c1 * 1.0000002);
+      }
+    }
+  }
+
   // neighbour row capacity
   long long cap;
   if (!has_cut) cap = N;
@@ -476,9 +504,24 @@ static void launch_pair_mode(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forc
   if (ctx->pair_mode == 1) k_pair<E, P, SAFE, 1><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
   else k_pair<E, P, SAFE, 0><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
 }
+template <bool E>
+static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
+  const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
+  const int th = PAIR_WARPS * 32;
+  if (ctx->pair_mode == 1) {
+    if (small) k_pair_fx<E, 1, true><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+    else k_pair_fx<E, 1, false><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+  } else {
+    if (small) k_pair_fx<E, 0, true><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+    else k_pair_fx<E, 0, false><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+  }
+}
 static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
   const bool e = energies != nullptr;
-  if (!ctx->periodic) {
+  if (ctx->d.xf_s) {
+    if (e) launch_pair_fx<true>(ctx, pg, st, forces, energies);
+    else launch_pair_fx<false>(ctx, pg, st, forces, energies);
+  } else if (!ctx->periodic) {
     if (e) launch_pair_mode<true, false, false>(ctx, pg, st, forces, energies);
     else launch_pair_mode<false, false, false>(ctx, pg, st, forces, energies);
   } else if (ctx->safe_image) {
