@@ -1,0 +1,135 @@
+"""Parity of the fixed-point pair kernel (k_pair_fx, TMD_B200_FX=1) with the oracle and
+with the default float kernel.
+
+STATUS: the kernel was written after the round's GPU budget was spent.  Its arithmetic
+is checked on the host (tests/test_physics_host.py, hostcheck shim) but it has not run on
+a B200 yet, so it is opt-in in the library and these tests only run with
+TMD_B200_VALIDATE=1 (scripts/gpu_validate_new.sh).  Same tolerances as
+test_gpu_forces.py: pairs bit-exact, forces < 1e-4 kcal/mol/A against the fp64 oracle on
+the fp32 pair set.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg, golden_system_tensors, load_golden, params_from_golden
+from oracle import refmd
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
+                       reason="fixed-point pair kernel: not yet validated on a B200 (set TMD_B200_VALIDATE=1)"),
+]
+DEV = "cuda:0"
+PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water999_eq", "chain_amber_periodic",
+                  "chain_charmm_periodic", "adversarial_cutoff", "ala2_xsc_rf"]
+
+
+def make_forces(g, fx, **kw):
+    from torchmd_b200 import Forces
+
+    old = os.environ.get("TMD_B200_FX")
+    os.environ["TMD_B200_FX"] = "1" if fx else "0"
+    try:
+        par = params_from_golden(g, precision=torch.float32, device=DEV)
+        f = Forces(par, terms=[str(t) for t in g["terms"]], **golden_cfg(g), **kw)
+        pos, box = golden_system_tensors(g, torch.float32, DEV)
+        F = torch.full_like(pos, 7.0)
+        E = f.compute(pos, box, F, returnDetails=True)  # the context reads the switch when it is finalised here
+    finally:
+        if old is None:
+            os.environ.pop("TMD_B200_FX", None)
+        else:
+            os.environ["TMD_B200_FX"] = old
+    return f, pos, box, F, E
+
+
+@pytest.mark.parametrize("name", PERIODIC_CASES)
+def test_fixed_point_kernel_matches_golden(name):
+    g = load_golden(name)
+    f, pos, box, F, E = make_forces(g, True)
+    f0, _, _, F0, E0 = make_forces(g, False)
+    ref = g["forces_f64"]
+    scale = max(1.0, float(np.abs(ref).max()) / 100.0)
+    err = np.abs(F.cpu().numpy().astype(np.float64) - ref).max()
+    err0 = np.abs(F0.cpu().numpy().astype(np.float64) - ref).max()
+    print(f"{name}: max|dF| vs fp64 reference: fixed-point {err:.3e}, float kernel {err0:.3e}")
+    dev = np.abs(g["forces_f32"].astype(np.float64) - ref).max()
+    assert err < max(1e-4 * scale, 1.2 * dev)
+    assert err <= err0 * 1.3 + 1e-5 * scale, "the fixed-point path must not be less accurate than the float path"
+    keys = [str(k) for k in g["energy_keys"]]
+    for r in range(len(E)):
+        for c, k in enumerate(keys):
+            e_ref = g["energies_f64"][r, c]
+            assert abs(E[r][k] - e_ref) <= 1e-5 * abs(e_ref) + 2e-3, (k, E[r][k], e_ref)
+    if "pairs_f32" in g:
+        assert np.array_equal(f.neighbour_pairs(pos, box).cpu().numpy(), g["pairs_f32"])
+    # deterministic
+    F1 = F.clone()
+    f.compute(pos, box, F)
+    assert torch.equal(F, F1)
+
+
+def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
+    """Molecules several boxes away from the primary cell: the float path loses ~1e-3 there
+    (fl(L*n) for |n|>=3), the fixed-point path must stay below 1e-4."""
+    from torchmd_b200 import Forces
+
+    g = load_golden("water999_eq")
+    cfg = golden_cfg(g)
+    rng = np.random.default_rng(7)
+    box = g["box"].astype(np.float64)
+    shift = rng.integers(-3, 4, (len(g["coords"]) // 3, 3)).repeat(3, axis=0)
+    coords = (g["coords"].astype(np.float64) + shift * box).astype(np.float32)
+    par64 = params_from_golden(g, precision=torch.float64)
+    terms = [str(t) for t in g["terms"]]
+    of = refmd.OracleForces(par64, terms, decision_dtype=torch.float32, **cfg)
+    pos_c = torch.tensor(coords)[None]
+    box_c = torch.diag(torch.tensor(g["box"]))[None]
+    f64 = torch.zeros(1, len(coords), 3, dtype=torch.float64)
+    of.compute(pos_c.double(), box_c.double(), f64)
+    of32 = refmd.OracleForces(params_from_golden(g, precision=torch.float32), terms, **cfg)
+    pairs_ref = of32.neighbour_pairs(pos_c[0], torch.tensor(g["box"])).numpy().astype(np.int32)
+
+    os.environ["TMD_B200_FX"] = "1"
+    try:
+        f = Forces(params_from_golden(g, precision=torch.float32, device=DEV), terms=terms, **cfg)
+        pos, bx = pos_c.to(DEV), box_c.to(DEV)
+        F = torch.zeros_like(pos)
+        f.compute(pos, bx, F)
+    finally:
+        os.environ.pop("TMD_B200_FX", None)
+    err = (F.cpu().double() - f64).abs().max().item()
+    print(f"drifted molecules: max|dF| vs fp64 oracle {err:.3e}")
+    assert err < 1e-4
+    assert np.array_equal(f.neighbour_pairs(pos, bx).cpu().numpy(), pairs_ref)
+
+
+def test_fixed_point_trajectory_tracks_float_kernel():
+    """100 NVE steps: same neighbour decisions, forces equal to ~1e-5, so the trajectories stay
+    within the fp32 divergence of two correct implementations."""
+    from torchmd_b200 import Forces, Integrator, System
+
+    g = load_golden("water999_eq")
+    cfg = golden_cfg(g)
+    out = []
+    for fx in (False, True):
+        os.environ["TMD_B200_FX"] = "1" if fx else "0"
+        try:
+            par = params_from_golden(g, precision=torch.float32, device=DEV)
+            s = System(len(g["coords"]), 1, torch.float32, DEV)
+            s.set_positions(g["coords"])
+            s.set_box(g["box"])
+            s.set_velocities(torch.tensor(g["vel"])[None])
+            f = Forces(par, terms=[str(t) for t in g["terms"]], **cfg)
+            integ = Integrator(s, f, 1.0, DEV, gamma=None, T=None)
+            ek, ep, T = integ.step(niter=100)
+            out.append((s.pos.cpu().clone(), float(ek[0]), float(ep[0])))
+        finally:
+            os.environ.pop("TMD_B200_FX", None)
+    dp = (out[0][0] - out[1][0]).abs().max().item()
+    print(f"NVE 100 steps: max |dpos| fixed-point vs float kernel {dp:.3e}; Epot {out[0][2]:.4f} / {out[1][2]:.4f}")
+    assert dp < 5e-3
+    assert abs(out[0][2] - out[1][2]) < 0.05
