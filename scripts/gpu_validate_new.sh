@@ -24,3 +24,15 @@ import json
 d=json.load(open("gpurun_out/validate_bench_fx5.json"))
 print("FX=1, 5 CTAs/SM (48 regs): steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
 PY
+# 4. list build with chunk culling (-DBT_CULL=1): whole GPU suite + bench against the variant library
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
+TMD_B200_LIB=/tmp/var/lib_cull.so timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_cull_suite.log 2>&1; echo "cull suite rc=$?"
+tail -3 gpurun_out/validate_cull_suite.log
+for fx in 0 1; do
+  TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_cull_fx$fx.json 2> gpurun_out/validate_bench_cull_fx$fx.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/validate_bench_cull_fx$fx.json"))
+print("CULL=1 FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
+PY
+done

@@ -342,12 +342,48 @@ struct Run {
   float sx, sy, sz;
 };
 
+// BT_CULL=1: every 32-candidate chunk of the tile gets a bounding box; an atom only walks
+// the chunks whose box comes within the list radius (the sweep volume is ~5x the list
+// sphere, so most chunks cannot contribute).  Skipped chunks hold no accepted candidate,
+// so the rows are identical to the unculled build.  Off until validated on a B200.
+#ifndef BT_CULL
+#define BT_CULL 0
+#endif
+constexpr int BT_CHUNKS = BT_TILE / 32;
+static_assert(BT_CHUNKS <= 64, "the per-atom chunk mask is 64 bits");
+
 struct BuildShared {
   float4 tile[BT_TILE];
   Run runs[BT_MAXRUN];
   int roff[BT_MAXRUN + 1];  // exclusive prefix of the run lengths
   int counts[BT_MAXI];
+#if BT_CULL
+  float bb[BT_CHUNKS][6];   // per chunk: min x,y,z, max x,y,z over its finite records
+#endif
 };
+
+#if BT_CULL
+// bounding boxes of the staged chunks (one warp per chunk; NaN records are left out: they
+// fail every distance test anyway)
+__device__ __forceinline__ void build_chunk_boxes(BuildShared& sh, int fill) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nchunks = (fill + 31) >> 5;
+  for (int c = warp; c < nchunks; c += BT_WARPS) {
+    const float4 p = sh.tile[c * 32 + lane];
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const bool ok = v[d] == v[d];
+      const int lo = __reduce_min_sync(0xffffffffu, enc_float(ok ? v[d] : INFINITY));
+      const int hi = __reduce_max_sync(0xffffffffu, enc_float(ok ? v[d] : -INFINITY));
+      if (lane == 0) {
+        sh.bb[c][d] = dec_float(lo);
+        sh.bb[c][3 + d] = dec_float(hi);
+      }
+    }
+  }
+}
+#endif
 
 template <bool WRAP>
 __device__ __forceinline__ void build_process_tile(const DeviceState& S, const Grid& g, size_t base,
@@ -383,11 +419,47 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     }
     int* __restrict__ row = S.nbr + (base + k) * (size_t)cap;
     int count = sh.counts[ii];
+#if BT_CULL
+    // chunks whose bounding box is within the list radius of this atom (lane c tests chunks
+    // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling
+    unsigned long long visit;
+    {
+      const int nchunks = (fill + 31) >> 5;
+      unsigned mh[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        bool v = false;
+        if (c < nchunks) {
+          const float* bb = sh.bb[c];
+          float dx = fmaxf(fmaxf(bb[0] - pi.x, pi.x - bb[3]), 0.f);
+          float dy = fmaxf(fmaxf(bb[1] - pi.y, pi.y - bb[4]), 0.f);
+          float dz = fmaxf(fmaxf(bb[2] - pi.z, pi.z - bb[5]), 0.f);
+          if (WRAP) {
+            if (w0) dx = 0.f;
+            if (w1) dy = 0.f;
+            if (w2) dz = 0.f;
+          }
+          // the per-pair test below rounds differently (differences of the same operands, then
+          // squares): 1e-5 relative slack keeps this one conservative
+          v = (dx * dx + dy * dy + dz * dz) * 0.99999f <= rl2;
+        }
+        mh[h] = __ballot_sync(0xffffffffu, v);
+      }
+      visit = (unsigned long long)mh[0] | ((unsigned long long)mh[1] << 32);
+    }
+#pragma unroll 1
+    while (visit) {
+      const int c0 = (__ffsll((long long)visit) - 1) << 5;
+      visit &= visit - 1;
+      const float4 pj = sh.tile[c0 + lane];
+#else
     const float4* __restrict__ tp = sh.tile + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < fill; c0 += 32, tp += 32) {
       // candidates beyond `fill` in the last chunk: the tile is padded with far-away records
       const float4 pj = *tp;
+#endif
       const int entry = __float_as_int(pj.w);
       const int j = entry & 0xffffff;
       float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
@@ -522,6 +594,10 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
         for (int u = fill + tid; u < ((fill + 31) & ~31); u += nthr)
           tile[u] = make_float4(NAN, NAN, NAN, __int_as_float(0xffffff));  // NaN: fails `<= rlist2` even when that is +inf
         __syncthreads();
+#if BT_CULL
+        build_chunk_boxes(sh, fill);
+        __syncthreads();
+#endif
         if (w0 || w1 || w2) build_process_tile<true>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
         else build_process_tile<false>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
       }
