@@ -160,7 +160,8 @@ def workload_config(ngpus):
         "flexible bonds+angles, Langevin 300 K gamma 0.1/ps, dt 1 fs, 1 replica",
         "natoms": 3 * N_WATERS,
         "pair_kernel": "fixed-point separations (TMD_B200_FX=1)" if os.environ.get("TMD_B200_FX", "")[:1] == "1" else "float separations (default)",
-        "parallelism": "single GPU" if ngpus == 1 else f"spatial slabs over {ngpus} GPUs, position all-gather",
+        "parallelism": "single GPU" if ngpus == 1 else (f"spatial slabs over {ngpus} GPUs, " + ("positions pushed to all ranks over NVLink peer memory by the integration kernel"
+                                                   if os.environ.get("TMD_B200_EXCHANGE", "").lower() == "p2p" else "position all-gather")),
         "l2": "no flush between steps: consecutive MD steps are data-dependent; the neighbour list streamed by the "
         "pair kernel (>150 MB) exceeds the 126 MB L2",
     }

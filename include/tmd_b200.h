@@ -159,6 +159,43 @@ int tmd_md_steps_host(tmd_ctx* ctx, int niter, float* pos_host, float* vel_host,
  * (the reference is single-device). */
 int tmd_set_owned_atoms(tmd_ctx* ctx, int first_atom, int count);
 
+/* ---- decomposed runs: integrate + position exchange over NVLink peer memory ------------
+ *
+ * Instead of a collective between tmd_vv_first and tmd_forces, the integration kernel of
+ * every rank stores the new positions of its owned atoms straight into the position
+ * buffers of ALL ranks (peer-to-peer stores through NVLink / NVSwitch), then raises a flag
+ * in every rank's flag array; a one-warp kernel on each rank waits until all flags of the
+ * step have arrived.  One launch + one tiny wait per step, no library collective on the
+ * path.  Positions live in two buffers per rank (read buffer / write buffer alternate each
+ * step) allocated by the context and shared between the processes of one node through CUDA
+ * IPC.  Single replica.  No reference counterpart.
+ *
+ * Set-up, once: every rank calls tmd_dd_create (after tmd_set_owned_atoms), all-gathers the
+ * 64-byte handles with whatever transport it has (torch.distributed), then tmd_dd_connect.
+ * Per step, parity p = 0,1,0,...:  tmd_dd_vv_first_push(p)  tmd_dd_wait  tmd_dd_forces(1-p)
+ * tmd_vv_second.  All four only enqueue; every per-step counter is device resident, so a
+ * captured CUDA graph of a step of given parity can be replayed. */
+#define TMD_MAX_PEERS 16
+#define TMD_IPC_HANDLE_BYTES 64
+
+/* Allocates the two position buffers and the flag array of this rank; handle_out receives
+ * TMD_IPC_HANDLE_BYTES bytes to be sent to the other ranks. [sync] */
+int tmd_dd_create(tmd_ctx* ctx, int rank, int world, unsigned char* handle_out_host);
+/* handles_host: world * TMD_IPC_HANDLE_BYTES bytes, rank order (own entry ignored).  Opens the
+ * peers' buffers in this process. [sync] */
+int tmd_dd_connect(tmd_ctx* ctx, const unsigned char* handles_host);
+/* Copy caller positions (1,N,3) into / out of position buffer `which` (0 or 1). */
+int tmd_dd_load(tmd_ctx* ctx, int which, const float* pos_dev, tmd_stream stream);
+int tmd_dd_store(tmd_ctx* ctx, int which, float* pos_dev, tmd_stream stream);
+/* _first_VV (integrator.py:61-64) on the owned atoms: reads positions from buffer which_in,
+ * writes the new ones into buffer 1-which_in of EVERY rank, then signals all ranks. */
+int tmd_dd_vv_first_push(tmd_ctx* ctx, int which_in, float* vel_dev, const float* forces_dev,
+                         const float* masses_dev, double dt, tmd_stream stream);
+/* Wait (on the device) until every rank's stores of this step have landed here. */
+int tmd_dd_wait(tmd_ctx* ctx, tmd_stream stream);
+/* tmd_forces on position buffer `which`. */
+int tmd_dd_forces(tmd_ctx* ctx, int which, float* forces_dev, double* energies_dev, tmd_stream stream);
+
 /* ---- inspection ------------------------------------------------------------ */
 
 /* The reference's neighbour list for one replica: every non-excluded pair

@@ -48,6 +48,8 @@ class Stats(C.Structure):
 
 
 _P = C.c_void_p
+IPC_HANDLE_BYTES = 64  # TMD_IPC_HANDLE_BYTES
+MAX_PEERS = 16  # TMD_MAX_PEERS
 _SIGNATURES = {
     "tmd_last_error": (C.c_char_p, []),
     "tmd_version": (C.c_int, []),
@@ -70,6 +72,13 @@ _SIGNATURES = {
     "tmd_export_pairs": (C.c_int, [_P, _P, C.c_int, _P, C.c_int64, _P, _P]),
     "tmd_get_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "tmd_set_owned_atoms": (C.c_int, [_P, C.c_int, C.c_int]),
+    "tmd_dd_create": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "tmd_dd_connect": (C.c_int, [_P, _P]),
+    "tmd_dd_load": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmd_dd_store": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmd_dd_vv_first_push": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_double, _P]),
+    "tmd_dd_wait": (C.c_int, [_P, _P]),
+    "tmd_dd_forces": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "tmd_profile_begin": (C.c_int, [_P, C.c_int]),
     "tmd_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), _P]),
 }

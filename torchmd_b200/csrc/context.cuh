@@ -37,6 +37,7 @@ enum {
   F_MAXNBR = 4,
   F_FARPOS = 5,    // a position was further than 2000 box lengths from the origin
   F_PMAX = 6,      // bits of the largest |coordinate| seen since the box was set (+inf if one was not finite)
+  F_PEERWAIT = 7,  // (replica 0) the wait for the peers' position stores timed out
   F_COUNT = 8
 };
 
@@ -117,6 +118,13 @@ struct tmd_ctx {
   int coop_blocks = 0;               // CTAs per replica of the cooperative rebuild kernel (0: separate kernels)
   int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
   int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
+  // peer-to-peer position exchange (tmd_dd_*): one cudaMalloc holding [pos0 | pos1 | flags | sync]
+  int dd_rank = -1, dd_world = 0;
+  bool dd_connected = false;
+  void* dd_base = nullptr;                    // this rank's allocation
+  void* dd_peer_base[TMD_MAX_PEERS] = {};     // the peers' allocations as mapped here (own entry = dd_base)
+  size_t dd_pos_bytes = 0;                    // bytes of one position buffer (offset of the second)
+  unsigned* dd_sync = nullptr;                // local: [0] block ticket, [1] push epoch, [2] wait epoch
   std::vector<float> box_host;       // (nrep,3)
   std::vector<float> charges_host;   // unscaled charges
   int64_t launches = 0;

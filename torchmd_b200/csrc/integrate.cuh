@@ -34,6 +34,85 @@ k_vv_first(int natoms, int lo, int cnt, unsigned long long* counters, float* __r
   }
 }
 
+// ---- fused integrate + exchange (decomposed runs, include/tmd_b200.h tmd_dd_*) -----------
+struct PeerTable {
+  float* pos[TMD_MAX_PEERS];        // the buffer written this step, on every rank (own rank included)
+  unsigned* flags[TMD_MAX_PEERS];   // flag array of every rank: flags[p][q] = last step rank q finished pushing to p
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// k_vv_first for the owned atoms, new positions stored into every rank's write buffer; the
+// last block to finish publishes this rank's step number in every rank's flag array.
+// sync: [0] block ticket (returns to 0), [1] steps pushed so far.
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_vv_first_push(int natoms, int lo, int cnt, unsigned long long* counters, const float* __restrict__ pos_in,
+                float* __restrict__ vel, const float* __restrict__ forces, const float* __restrict__ masses,
+                float dt, float hdt, PeerTable pt, unsigned* __restrict__ sync) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;  // single replica
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[1] += 1;  // Philox position of this step
+  if (i < lo + cnt) {
+    const float m = masses[i];
+    const size_t a = (size_t)i * 3;
+    float x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float acc = div_rn(forces[a + d], m);
+      const float v = vel[a + d];
+      const float drift = add_rn(mul_rn(v, dt), mul_rn(mul_rn(mul_rn(0.5f, acc), dt), dt));
+      x[d] = add_rn(pos_in[a + d], drift);
+      vel[a + d] = add_rn(v, mul_rn(hdt, acc));
+    }
+    for (int p = 0; p < pt.world; ++p) {
+      float* dst = pt.pos[p] + a;
+      dst[0] = x[0];
+      dst[1] = x[1];
+      dst[2] = x[2];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this block's stores (ordered before the barrier) precede the ticket
+    const unsigned done = atomicAdd(sync + 0, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence_system();
+      sync[0] = 0;
+      const unsigned epoch = sync[1] + 1u;
+      sync[1] = epoch;
+      for (int p = 0; p < pt.world; ++p) st_release_sys(pt.flags[p] + pt.rank, epoch);
+    }
+  }
+}
+
+// One warp: lane q waits for rank q's flag of the current step.  sync[2]: steps waited for so far.
+__global__ void k_wait_peers(const unsigned* __restrict__ flags_local, unsigned* __restrict__ sync, int world,
+                             int* __restrict__ errflag) {
+  const int q = threadIdx.x;
+  unsigned target = 0;
+  if (q == 0) target = sync[2] + 1u;
+  target = __shfl_sync(0xffffffffu, target, 0);
+  if (q < world) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flags_local + q) - target) < 0) {
+      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer died or the step counts diverged
+        *errflag = 1;
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+  __syncwarp();
+  if (q == 0) sync[2] = target;
+}
+
 // Philox4x32-10 counter-based generator (Salmon et al., SC'11).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -94,6 +94,24 @@ struct tmd_ctx_full : tmd_ctx {
   CtxPriv priv;
 };
 static inline CtxPriv& priv(tmd_ctx* c) { return static_cast<tmd_ctx_full*>(c)->priv; }
+// ---- peer-to-peer position exchange --------------------------------------------------------
+static inline float* dd_pos_of(tmd_ctx* ctx, int peer, int which) {
+  return reinterpret_cast<float*>(static_cast<char*>(ctx->dd_peer_base[peer]) + (size_t)which * ctx->dd_pos_bytes);
+}
+static inline unsigned* dd_flags_of(tmd_ctx* ctx, int peer) {
+  return reinterpret_cast<unsigned*>(static_cast<char*>(ctx->dd_peer_base[peer]) + 2 * ctx->dd_pos_bytes);
+}
+static void dd_release(tmd_ctx* ctx) {
+  for (int p = 0; p < ctx->dd_world; ++p)
+    if (p != ctx->dd_rank && ctx->dd_peer_base[p]) cudaIpcCloseMemHandle(ctx->dd_peer_base[p]);
+  if (ctx->dd_base) cudaFree(ctx->dd_base);
+  ctx->dd_base = nullptr;
+  for (void*& b : ctx->dd_peer_base) b = nullptr;
+  ctx->dd_connected = false;
+  ctx->dd_world = 0;
+  ctx->dd_rank = -1;
+}
+
 
 extern "C" {
 
@@ -156,6 +174,7 @@ int tmd_destroy(tmd_ctx* ctx) {
                   ctx->pairs14.idx, ctx->pairs14.prm, ctx->bonded_atom_ptr, ctx->bonded_entries, ctx->xf_buf};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  dd_release(ctx);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
   delete static_cast<tmd_ctx_full*>(ctx);
   return TMD_OK;
@@ -750,6 +769,102 @@ int tmd_set_owned_atoms(tmd_ctx* ctx, int first_atom, int count) {
   return TMD_OK;
 }
 
+// ---- peer-to-peer position exchange (helpers above, next to priv()) ------------------------
+int tmd_dd_create(tmd_ctx* ctx, int rank, int world, unsigned char* handle_out) {
+  if (!ctx || !handle_out || world < 1 || world > TMD_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(TMD_ERR_ARG, "tmd_dd_create: bad arguments (at most 16 ranks)");
+  if (ctx->nrep != 1) return fail(TMD_ERR_UNSUPPORTED, "tmd_dd_create: decomposed runs take one replica");
+  static_assert(sizeof(cudaIpcMemHandle_t) == TMD_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard guard(ctx->device);
+  dd_release(ctx);
+  ctx->dd_pos_bytes = (((size_t)ctx->natoms * 3 * sizeof(float)) + 255) / 256 * 256;
+  const size_t bytes = 2 * ctx->dd_pos_bytes + 256 /* flags */ + 256 /* sync */;
+  TMD_CUDA(cudaMalloc(&ctx->dd_base, bytes));
+  TMD_CUDA(cudaMemset(ctx->dd_base, 0, bytes));
+  TMD_CUDA(cudaDeviceSynchronize());
+  ctx->dd_rank = rank;
+  ctx->dd_world = world;
+  ctx->dd_peer_base[rank] = ctx->dd_base;
+  ctx->dd_sync = reinterpret_cast<unsigned*>(static_cast<char*>(ctx->dd_base) + 2 * ctx->dd_pos_bytes + 256);
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  if (world > 1) TMD_CUDA(cudaIpcGetMemHandle(&h, ctx->dd_base));
+  memcpy(handle_out, &h, sizeof(h));
+  return TMD_OK;
+}
+
+int tmd_dd_connect(tmd_ctx* ctx, const unsigned char* handles) {
+  if (!ctx || !handles) return fail(TMD_ERR_ARG, "tmd_dd_connect: null pointer");
+  if (!ctx->dd_base) return fail(TMD_ERR_STATE, "tmd_dd_connect: tmd_dd_create has not been called");
+  DeviceGuard guard(ctx->device);
+  for (int p = 0; p < ctx->dd_world; ++p) {
+    if (p == ctx->dd_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)p * TMD_IPC_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    TMD_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->dd_peer_base[p] = ptr;
+  }
+  ctx->dd_connected = true;
+  return TMD_OK;
+}
+
+#define TMD_DD_READY(name)                                                                     \
+  if (!ctx) return fail(TMD_ERR_ARG, name ": null context");                                   \
+  if (!ctx->dd_connected) return fail(TMD_ERR_STATE, name ": tmd_dd_create / tmd_dd_connect first"); \
+  DeviceGuard guard(ctx->device);
+
+int tmd_dd_load(tmd_ctx* ctx, int which, const float* pos, tmd_stream stream) {
+  TMD_DD_READY("tmd_dd_load")
+  if (!pos || (which != 0 && which != 1)) return fail(TMD_ERR_ARG, "tmd_dd_load: bad arguments");
+  TMD_CUDA(cudaMemcpyAsync(dd_pos_of(ctx, ctx->dd_rank, which), pos, (size_t)ctx->natoms * 3 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TMD_OK;
+}
+
+int tmd_dd_store(tmd_ctx* ctx, int which, float* pos, tmd_stream stream) {
+  TMD_DD_READY("tmd_dd_store")
+  if (!pos || (which != 0 && which != 1)) return fail(TMD_ERR_ARG, "tmd_dd_store: bad arguments");
+  TMD_CUDA(cudaMemcpyAsync(pos, dd_pos_of(ctx, ctx->dd_rank, which), (size_t)ctx->natoms * 3 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TMD_OK;
+}
+
+int tmd_dd_vv_first_push(tmd_ctx* ctx, int which_in, float* vel, const float* forces, const float* masses, double dt,
+                         tmd_stream stream) {
+  TMD_DD_READY("tmd_dd_vv_first_push")
+  if (!vel || !forces || !masses || (which_in != 0 && which_in != 1))
+    return fail(TMD_ERR_ARG, "tmd_dd_vv_first_push: bad arguments");
+  PeerTable pt;
+  memset(&pt, 0, sizeof(pt));
+  pt.world = ctx->dd_world;
+  pt.rank = ctx->dd_rank;
+  for (int p = 0; p < ctx->dd_world; ++p) {
+    pt.pos[p] = dd_pos_of(ctx, p, 1 - which_in);
+    pt.flags[p] = dd_flags_of(ctx, p);
+  }
+  const unsigned blocks = (unsigned)((std::max(ctx->d.own_n, 1) + INTEG_THREADS - 1) / INTEG_THREADS);
+  k_vv_first_push<<<blocks, INTEG_THREADS, 0, (cudaStream_t)stream>>>(
+      ctx->natoms, ctx->d.own_lo, ctx->d.own_n, ctx->d.counters, dd_pos_of(ctx, ctx->dd_rank, which_in), vel, forces,
+      masses, (float)dt, (float)(0.5 * dt), pt, ctx->dd_sync);
+  TMD_LAUNCHED(ctx, "k_vv_first_push");
+  return TMD_OK;
+}
+
+int tmd_dd_wait(tmd_ctx* ctx, tmd_stream stream) {
+  TMD_DD_READY("tmd_dd_wait")
+  k_wait_peers<<<1, 32, 0, (cudaStream_t)stream>>>(dd_flags_of(ctx, ctx->dd_rank), ctx->dd_sync, ctx->dd_world,
+                                                    ctx->d.flags + F_PEERWAIT);
+  TMD_LAUNCHED(ctx, "k_wait_peers");
+  return TMD_OK;
+}
+
+int tmd_dd_forces(tmd_ctx* ctx, int which, float* forces, double* energies, tmd_stream stream) {
+  TMD_DD_READY("tmd_dd_forces")
+  if (which != 0 && which != 1) return fail(TMD_ERR_ARG, "tmd_dd_forces: bad arguments");
+  return tmd_forces(ctx, dd_pos_of(ctx, ctx->dd_rank, which), forces, energies, stream);
+}
+
 int tmd_profile_begin(tmd_ctx* ctx, int max_samples) {
   if (!ctx || max_samples <= 0) return fail(TMD_ERR_ARG, "tmd_profile_begin: bad arguments");
   DeviceGuard guard(ctx->device);
@@ -804,6 +919,9 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
     overflow |= fl[r * F_COUNT + F_OVERFLOW] != 0;
   }
   out->overflow = overflow;
+  if (fl[F_PEERWAIT])
+    return fail(TMD_ERR_STATE, "the wait for the other ranks' position stores timed out (a rank stopped or the "
+                               "ranks ran different numbers of steps): the decomposed run is invalid");
   for (int r = 0; r < ctx->nrep; ++r)
     if (fl[r * F_COUNT + F_FARPOS])
       return fail(TMD_ERR_UNSUPPORTED,

@@ -21,7 +21,18 @@ atom index, whole trajectories -- are bitwise identical to the single-GPU run.
 One MD step (kernels + the all-gather) is captured once as a CUDA graph and replayed:
 every per-step quantity that changes (rebuild flag parity, Philox step) lives on the
 device, so the graph is replayable and the host issues one launch per step.
+
+``exchange="p2p"`` (or TMD_B200_EXCHANGE=p2p) replaces the all-gather by the fused
+integrate + exchange kernel of the library (include/tmd_b200.h, tmd_dd_*): the first
+half-kick of every rank stores its new positions directly into all ranks' position
+buffers through NVLink peer memory and raises a flag; a one-warp kernel waits for the
+flags.  Positions then live in two library-owned buffers per rank (read / write buffer
+alternate every step) and ``system.pos`` is synchronised at the ends of ``step()``.
+Written after round 1's GPU budget was spent: opt-in until validated on a multi-GPU box.
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -74,9 +85,12 @@ class DecomposedIntegrator:
     construction ``system.pos`` aliases a padded gather buffer.  Single replica only.
     """
 
-    def __init__(self, system, forces, timestep, device, gamma=None, T=None, group=None, use_graph=True):
+    def __init__(self, system, forces, timestep, device, gamma=None, T=None, group=None, use_graph=True, exchange=None):
         if system.pos.shape[0] != 1:
             raise NotImplementedError("decomposed runs take one replica; shard replicas across ranks instead")
+        self.exchange = (exchange or os.environ.get("TMD_B200_EXCHANGE", "allgather")).lower()
+        if self.exchange not in ("allgather", "p2p"):
+            raise ValueError(f"unknown exchange {self.exchange!r}: 'allgather' or 'p2p'")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -98,9 +112,49 @@ class DecomposedIntegrator:
         self.ke = torch.zeros(nrep, dtype=torch.float64, device=system.pos.device)
         self.use_graph = use_graph
         self._graphs = {}
+        self._parity = 0  # p2p: which of the two position buffers holds the current positions
+        if self.exchange == "p2p":
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Allocate this rank's exchange buffers and map every peer's (CUDA IPC handles travel
+        through one all-gather at set-up; nothing else does)."""
+        L = _lib.lib()
+        if self.world > _lib.MAX_PEERS:
+            raise NotImplementedError(f"peer-to-peer exchange supports up to {_lib.MAX_PEERS} ranks")
+        dev = self.system.pos.device
+        handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        _lib.check(L.tmd_dd_create(self.ctx, self.rank, self.world, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        everyone = torch.empty(self.world * _lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        if self.world > 1:
+            dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        else:
+            everyone.copy_(mine)
+        raw = bytes(everyone.cpu().numpy().tobytes())
+        table = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        _lib.check(L.tmd_dd_connect(self.ctx, table))
+        if self.world > 1:
+            dist.barrier(group=self.group)  # every rank has mapped every buffer before anyone stores into one
 
     # one MD step on the current stream; with_energy: also this rank's energy / KE share
-    def _enqueue_step(self, with_energy):
+    def _enqueue_step_p2p(self, with_energy, parity):
+        s, ig, L = self.system, self.integ, _lib.lib()
+        stream = torch.cuda.current_stream(s.pos.device).cuda_stream
+        thermostat = bool(ig.T)
+        gamma = float(ig.gamma) if thermostat else -1.0
+        vcoeff = ig.vcoeff.data_ptr() if thermostat else None
+        _lib.check(L.tmd_dd_vv_first_push(self.ctx, parity, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
+        _lib.check(L.tmd_dd_wait(self.ctx, stream))
+        _lib.check(L.tmd_dd_forces(self.ctx, 1 - parity, s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
+        _lib.check(
+            L.tmd_vv_second(self.ctx, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, gamma, vcoeff,
+                            None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
+        )
+
+    def _enqueue_step(self, with_energy, parity=0):
+        if self.exchange == "p2p":
+            return self._enqueue_step_p2p(with_energy, parity)
         s, ig, L = self.system, self.integ, _lib.lib()
         stream = torch.cuda.current_stream(s.pos.device).cuda_stream
         thermostat = bool(ig.T)
@@ -114,17 +168,19 @@ class DecomposedIntegrator:
                             None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
         )
 
-    def _graph(self, with_energy):
-        """Capture one step (kernels + all-gather) once; None if capture is not possible."""
-        if with_energy in self._graphs:
-            return self._graphs[with_energy]
+    def _graph(self, with_energy, parity=0):
+        """Capture one step (kernels + exchange) once per variant; None if capture is not possible.
+        A p2p step reads one position buffer and writes the other, so each parity is its own graph."""
+        key = (with_energy, parity) if self.exchange == "p2p" else with_energy
+        if key in self._graphs:
+            return self._graphs[key]
         g = None
         if self.use_graph:
             try:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue_step(with_energy)
+                    self._enqueue_step(with_energy, parity)
                 # the capture only records; state was not advanced
             except Exception as err:  # pragma: no cover - depends on the NCCL build
                 if self.rank == 0:
@@ -134,18 +190,28 @@ class DecomposedIntegrator:
                 g = None
                 self.use_graph = False
                 torch.cuda.synchronize()
-        self._graphs[with_energy] = g
+        self._graphs[key] = g
         return g
 
     def step(self, niter=1):
         """niter MD steps; returns (Ekin, pot, T) of the whole system like Integrator.step."""
+        p2p = self.exchange == "p2p"
+        L = _lib.lib()
+        if p2p:  # the caller may have edited system.pos since the last call
+            stream = torch.cuda.current_stream(self.system.pos.device).cuda_stream
+            _lib.check(L.tmd_dd_load(self.ctx, self._parity, self.system.pos.data_ptr(), stream))
         for it in range(niter):
             last = it == niter - 1
-            g = self._graph(last)
+            g = self._graph(last, self._parity)
             if g is not None:
                 g.replay()
             else:
-                self._enqueue_step(last)
+                self._enqueue_step(last, self._parity)
+            if p2p:
+                self._parity ^= 1
+        if p2p:
+            stream = torch.cuda.current_stream(self.system.pos.device).cuda_stream
+            _lib.check(L.tmd_dd_store(self.ctx, self._parity, self.system.pos.data_ptr(), stream))
         tot = torch.cat([self.ene.sum(dim=1), self.ke])  # this rank's shares
         dist.all_reduce(tot, group=self.group)
         self.forces.stats()  # raises on neighbour-row overflow / far positions
@@ -192,7 +258,7 @@ def bench_decomposed(args, world, rank, local, config):
     launches_per_step = None
     if integ.use_graph:  # kernels of one captured step (the capture itself went through the counting path)
         st_b = forces.stats()
-        launches_per_step = (st_b["kernel_launches"] - st_a["kernel_launches"]) // 2  # two graphs captured
+        launches_per_step = (st_b["kernel_launches"] - st_a["kernel_launches"]) // max(1, len(integ._graphs))  # one step per captured graph
 
     L = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
@@ -306,7 +372,8 @@ def bench_decomposed(args, world, rank, local, config):
             "epot": float(pot[0]),
             "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
             "cuda_graph": bool(integ.use_graph),
-            "collective": "one all-gather of positions per step (NCCL)",
+            "collective": "one all-gather of positions per step (NCCL)" if integ.exchange == "allgather"
+            else "none: positions stored into every rank's buffer by the integration kernel (NVLink peer memory) + flag wait",
         },
     }
     print(json.dumps(line), flush=True)
