@@ -196,6 +196,25 @@ int tmd_dd_wait(tmd_ctx* ctx, tmd_stream stream);
 /* tmd_forces on position buffer `which`. */
 int tmd_dd_forces(tmd_ctx* ctx, int which, float* forces_dev, double* energies_dev, tmd_stream stream);
 
+/* ---- Wrapper.wrap (wrapper.py:8-30): molecules back into the box -----------------------
+ *
+ * Groups are the connected components of the bond graph (calculate_molecule_groups,
+ * wrapper.py:33-55) as a CSR over atom indices: group g holds
+ * group_atoms[group_ptr[g] .. group_ptr[g+1]); an atom without bonds is a group of one atom
+ * (the reference's "nongrouped" branch is the same arithmetic).  tmd_wrapper_wrap moves every
+ * group by  -floor(com / box) * box  per dimension, com being the plain mean of the group's
+ * coordinates, in place on pos_dev (R,N,3), for every replica; box_dev is the (R,3,3) box
+ * tensor (diagonal used).  If every box length is zero nothing happens (wrapper.py:14-15).
+ * The optional re-centring on a wrap-index group (wrapper.py:17-21) rebinds a local name in
+ * the reference and never reaches the caller's tensor; it is not part of this entry point.
+ * Independent of tmd_ctx; only enqueues. */
+typedef struct tmd_wrapper tmd_wrapper;
+int tmd_wrapper_create(tmd_wrapper** out, int device, int natoms, int ngroups,
+                       const int32_t* group_ptr_host, const int32_t* group_atoms_host);
+int tmd_wrapper_wrap(tmd_wrapper* w, float* pos_dev, const float* box_dev, int nreplicas,
+                     tmd_stream stream);
+int tmd_wrapper_destroy(tmd_wrapper* w);
+
 /* ---- inspection ------------------------------------------------------------ */
 
 /* The reference's neighbour list for one replica: every non-excluded pair

@@ -430,3 +430,52 @@ class OracleIntegrator:
             self.vel += 0.5 * dt * (self.f / m)
         ekin = kinetic_energy(m, self.vel).flatten().numpy()
         return ekin, pot, kinetic_to_temperature(ekin, len(m))
+
+
+# ---- Wrapper (wrapper.py) ------------------------------------------------------------------
+def molecule_groups(natoms, bonds):
+    """wrapper.py:33-55 -- connected components of the bond graph: (groups of >= 2 atoms,
+    atoms without any bond).  Breadth-first search instead of networkx; groups hold their
+    atoms in ascending order, ordered by smallest atom."""
+    if bonds is None or len(bonds) == 0:
+        return [], list(range(natoms))
+    adj = [[] for _ in range(natoms)]
+    for i, j in np.asarray(bonds).astype(np.int64):
+        adj[i].append(int(j))
+        adj[j].append(int(i))
+    seen = [False] * natoms
+    groups, single = [], []
+    for s in range(natoms):
+        if seen[s]:
+            continue
+        comp, stack = [], [s]
+        seen[s] = True
+        while stack:
+            a = stack.pop()
+            comp.append(a)
+            for b in adj[a]:
+                if not seen[b]:
+                    seen[b] = True
+                    stack.append(b)
+        if len(comp) == 1:
+            single.append(s)
+        else:
+            groups.append(sorted(comp))
+    return groups, single
+
+
+def wrap_positions(pos, box, groups, nongrouped):
+    """wrapper.py:8-30 without the wrap-index branch (which rebinds a local and has no effect on
+    the caller's tensor): in place on ``pos`` (R,N,3); ``box`` (R,3,3)."""
+    diag = box[:, torch.eye(3).bool()]  # :11
+    if torch.all(diag == 0):  # :12-13
+        return
+    for group in groups:  # :23-27
+        g = torch.as_tensor(group, dtype=torch.int64)
+        com = torch.sum(pos[:, g], dim=1) / len(group)
+        offset = torch.floor(com / diag) * diag
+        pos[:, g] -= offset.unsqueeze(1)
+    if len(nongrouped):  # :29-31
+        n = torch.as_tensor(nongrouped, dtype=torch.int64)
+        offset = torch.floor(pos[:, n] / diag.unsqueeze(1)) * diag.unsqueeze(1)
+        pos[:, n] -= offset

@@ -166,4 +166,51 @@ void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const
   }
 }
 
+// ---- Wrapper.wrap: the arithmetic of csrc/wrap.cuh k_wrap, lane for lane -----------------
+void hc_wrap(int natoms, int ngroups, const int* group_ptr, const int* group_atoms, int nrep, float* pos,
+             const float* box /* (R,3,3) */) {
+  bool allzero = true;
+  for (int r = 0; r < nrep; ++r)
+    for (int d = 0; d < 3; ++d) allzero &= (box[r * 9 + d * 4] == 0.f);
+  if (allzero) return;
+  for (int r = 0; r < nrep; ++r) {
+    float* p = pos + (size_t)r * natoms * 3;
+    for (int g = 0; g < ngroups; ++g) {
+      const int b = group_ptr[g], n = group_ptr[g + 1] - b;
+      if (n <= 0) continue;
+      float sum[3] = {0.f, 0.f, 0.f};
+      if (n <= 32) {
+        for (int m = 0; m < n; ++m)
+          for (int d = 0; d < 3; ++d) {
+            const float t = p[(size_t)group_atoms[b + m] * 3 + d];
+            sum[d] = (m == 0) ? t : add_rn(sum[d], t);
+          }
+      } else {
+        float lane[32][3];
+        for (int l = 0; l < 32; ++l)
+          for (int d = 0; d < 3; ++d) {
+            float acc = 0.f;
+            for (int e = l; e < n; e += 32) acc = add_rn(acc, p[(size_t)group_atoms[b + e] * 3 + d]);
+            lane[l][d] = acc;
+          }
+        for (int o = 16; o; o >>= 1) {
+          float nxt[32][3];
+          for (int l = 0; l < 32; ++l)
+            for (int d = 0; d < 3; ++d) nxt[l][d] = add_rn(lane[l][d], lane[l ^ o][d]);
+          for (int l = 0; l < 32; ++l)
+            for (int d = 0; d < 3; ++d) lane[l][d] = nxt[l][d];
+        }
+        for (int d = 0; d < 3; ++d) sum[d] = lane[0][d];
+      }
+      for (int d = 0; d < 3; ++d) {
+        const float off = wrap_offset(sum[d], n, box[r * 9 + d * 4]);
+        for (int e = 0; e < n; ++e) {
+          float& x = p[(size_t)group_atoms[b + e] * 3 + d];
+          x = sub_rn(x, off);
+        }
+      }
+    }
+  }
+}
+
 }  // extern "C"

@@ -1,0 +1,95 @@
+"""Wrapper.wrap (reference torchmd/wrapper.py): the oracle restatement and the arithmetic of
+the CUDA kernel (csrc/wrap.cuh, compiled for the host by the hostcheck shim) against golden
+vectors produced by the unmodified reference (tests/golden/make_golden_wrap.py); the GPU
+kernel itself in the gpu-marked test below.
+
+Tolerance: bit-exact.  (The image a group is moved by depends on floor(com / box); a
+different summation order could only change it for a centre within an ulp of a box face --
+none of the fixtures has one, and the test would say so.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import refmd
+
+CASES = ["water", "mixed", "nobonds", "zerobox"]
+
+
+def case(g, name):
+    bonds = g[name + "_bonds"]
+    return int(g[name + "_natoms"]), (bonds if len(bonds) else None), g[name + "_pos"], g[name + "_box"], g[name + "_after"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_wrap_matches_reference_golden(name):
+    g = load_golden("wrap_cases")
+    natoms, bonds, pos, box, after = case(g, name)
+    groups, single = refmd.molecule_groups(natoms, bonds)
+    assert len(groups) == int(g[name + "_ngroups"]) and len(single) == int(g[name + "_nsingle"])
+    p = torch.tensor(pos)
+    refmd.wrap_positions(p, torch.tensor(box), groups, single)
+    assert np.array_equal(p.numpy(), after)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_molecule_groups_match_oracle(name):
+    from torchmd_b200.wrapper import Wrapper, calculate_molecule_groups
+
+    g = load_golden("wrap_cases")
+    natoms, bonds, pos, box, after = case(g, name)
+    groups, single = refmd.molecule_groups(natoms, bonds)
+    mg, ng = calculate_molecule_groups(natoms, bonds)
+    assert [t.tolist() for t in mg] == groups and ng.tolist() == single
+    w = Wrapper(natoms, bonds, "cpu")  # construction is host-only; wrap() needs CUDA
+    assert [t.tolist() for t in w.groups] == groups and w.nongrouped.tolist() == single
+    # CSR handed to the kernel: every atom exactly once
+    assert sorted(w._atoms.tolist()) == list(range(natoms)) and w._ptr[-1] == natoms
+    with pytest.raises(RuntimeError):
+        w.wrap(torch.tensor(pos), torch.tensor(box))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_arithmetic_on_host_matches_reference_golden(name):
+    from torchmd_b200.wrapper import Wrapper
+
+    hc = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so"))
+    g = load_golden("wrap_cases")
+    natoms, bonds, pos, box, after = case(g, name)
+    w = Wrapper(natoms, bonds, "cpu")
+    p = np.ascontiguousarray(pos, np.float32).copy()
+    b = np.ascontiguousarray(box, np.float32)
+    hc.hc_wrap(natoms, len(w._ptr) - 1, w._ptr.ctypes.data_as(C.c_void_p), w._atoms.ctypes.data_as(C.c_void_p),
+               p.shape[0], p.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(p, after)
+
+
+def test_wrap_index_branch_leaves_caller_tensor_alone():
+    """wrapper.py:17-21 rebinds the local `pos`: with wrapidx the caller's tensor is unchanged."""
+    from torchmd_b200.wrapper import Wrapper
+
+    g = load_golden("wrap_cases")
+    natoms, bonds, pos, box, after = case(g, "mixed")
+    w = Wrapper(natoms, bonds, "cpu")
+    p = torch.tensor(pos)
+    w.wrap(p, torch.tensor(box), wrapidx=[0, 1, 2])
+    assert np.array_equal(p.numpy(), pos)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
+                    reason="wrap kernel: host-checked, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_wrap_matches_reference_golden(name):
+    from torchmd_b200.wrapper import Wrapper
+
+    g = load_golden("wrap_cases")
+    natoms, bonds, pos, box, after = case(g, name)
+    w = Wrapper(natoms, bonds, "cuda:0")
+    p = torch.tensor(pos, device="cuda:0")
+    w.wrap(p, torch.tensor(box, device="cuda:0"))
+    assert np.array_equal(p.cpu().numpy(), after)

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "tmd_dd_vv_first_push": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_double, _P]),
     "tmd_dd_wait": (C.c_int, [_P, _P]),
     "tmd_dd_forces": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "tmd_wrapper_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P, _P]),
+    "tmd_wrapper_wrap": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "tmd_wrapper_destroy": (C.c_int, [_P]),
     "tmd_profile_begin": (C.c_int, [_P, C.c_int]),
     "tmd_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), _P]),
 }

@@ -168,6 +168,12 @@ TMD_HD bool ref_inside(float xi, float yi, float zi, float xj, float yj, float z
   return norm2_ref(wx, wy, wz) <= s_max;
 }
 
+// ---- Wrapper.wrap (wrapper.py:24-27): image offset of a group from its coordinate sum ----
+//   com = sum / len ;  offset = floor(com / box) * box        (three rounded fp32 operations)
+TMD_HD float wrap_offset(float coord_sum, int len, float box) {
+  return mul_rn(floorf(div_rn(div_rn(coord_sum, (float)len), box)), box);
+}
+
 // ---- fixed-point periodic coordinates ---------------------------------------------------
 // For the pair kernel of a periodic box a coordinate x along a dimension of length L is
 // also kept as the 32-bit integer  X = round(x * 2^32 / L) mod 2^32  (computed in fp64 from

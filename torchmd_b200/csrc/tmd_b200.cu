@@ -14,6 +14,7 @@
 #include "bonded.cuh"
 #include "context.cuh"
 #include "integrate.cuh"
+#include "wrap.cuh"
 #include "neighbor.cuh"
 #include "pair.cuh"
 
@@ -863,6 +864,63 @@ int tmd_dd_forces(tmd_ctx* ctx, int which, float* forces, double* energies, tmd_
   TMD_DD_READY("tmd_dd_forces")
   if (which != 0 && which != 1) return fail(TMD_ERR_ARG, "tmd_dd_forces: bad arguments");
   return tmd_forces(ctx, dd_pos_of(ctx, ctx->dd_rank, which), forces, energies, stream);
+}
+
+// ---- Wrapper.wrap ---------------------------------------------------------------------------
+int tmd_wrapper_create(tmd_wrapper** out, int device, int natoms, int ngroups, const int32_t* group_ptr,
+                       const int32_t* group_atoms) {
+  if (!out || natoms <= 0 || ngroups < 0 || !group_ptr || (ngroups > 0 && !group_atoms))
+    return fail(TMD_ERR_ARG, "tmd_wrapper_create: bad arguments");
+  if (group_ptr[0] != 0) return fail(TMD_ERR_ARG, "tmd_wrapper_create: group_ptr[0] must be 0");
+  for (int g = 0; g < ngroups; ++g)
+    if (group_ptr[g + 1] < group_ptr[g]) return fail(TMD_ERR_ARG, "tmd_wrapper_create: group_ptr must not decrease");
+  const int total = group_ptr[ngroups];
+  if (total > natoms) return fail(TMD_ERR_ARG, "tmd_wrapper_create: more group members than atoms");
+  std::vector<char> seen((size_t)natoms, 0);
+  for (int e = 0; e < total; ++e) {
+    const int a = group_atoms[e];
+    if (a < 0 || a >= natoms || seen[a]) return fail(TMD_ERR_ARG, "tmd_wrapper_create: atom index out of range or in two groups");
+    seen[a] = 1;
+  }
+  int ndev = 0;
+  TMD_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(TMD_ERR_ARG, "tmd_wrapper_create: no such CUDA device");
+  DeviceGuard guard(device);
+  tmd_wrapper* w = new tmd_wrapper();
+  w->device = device;
+  w->natoms = natoms;
+  w->ngroups = ngroups;
+  int rc;
+  if ((rc = upload(&w->group_ptr, group_ptr, (size_t)ngroups + 1)) || (rc = upload(&w->group_atoms, group_atoms, (size_t)total)) ||
+      (rc = device_alloc(&w->flag, (size_t)1))) {
+    tmd_wrapper_destroy(w);
+    return rc;
+  }
+  *out = w;
+  return TMD_OK;
+}
+
+int tmd_wrapper_wrap(tmd_wrapper* w, float* pos, const float* box, int nrep, tmd_stream stream) {
+  if (!w || !pos || !box || nrep <= 0 || nrep > 65535) return fail(TMD_ERR_ARG, "tmd_wrapper_wrap: bad arguments");
+  if (w->ngroups == 0) return TMD_OK;
+  DeviceGuard guard(w->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_wrap_boxflag<<<1, 256, 0, st>>>(box, nrep, w->flag);
+  k_wrap<<<dim3((unsigned)((w->ngroups + WRAP_WARPS - 1) / WRAP_WARPS), (unsigned)nrep), WRAP_WARPS * 32, 0, st>>>(
+      w->natoms, w->ngroups, w->group_ptr, w->group_atoms, pos, box, w->flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("launch k_wrap: ") + cudaGetErrorString(e));
+  return TMD_OK;
+}
+
+int tmd_wrapper_destroy(tmd_wrapper* w) {
+  if (!w) return TMD_OK;
+  DeviceGuard guard(w->device);
+  if (w->group_ptr) cudaFree(w->group_ptr);
+  if (w->group_atoms) cudaFree(w->group_atoms);
+  if (w->flag) cudaFree(w->flag);
+  delete w;
+  return TMD_OK;
 }
 
 int tmd_profile_begin(tmd_ctx* ctx, int max_samples) {
