@@ -240,6 +240,34 @@ class Forces:
         self._box_key = key
 
     # ------------------------------------------------------------------ compute
+    def _evaluate(self, pos, box, forces, sync=True):
+        """One pass of the kernels: forces (R,N,3) overwritten, returns the (R, NUM_ENERGIES) fp64
+        device energies.  ``sync``: check the neighbour rows now (synchronises; a row overflow
+        grows the capacity and recomputes) instead of at the next ``stats()``."""
+        self._check_tensor(pos, "pos")
+        nrep = pos.shape[0]
+        self._check_tensor(forces, "forces", pos.shape)
+        if not torch.is_tensor(box) or tuple(box.shape) != (nrep, 3, 3):
+            raise RuntimeError("box must be a (nreplicas, 3, 3) tensor")
+        ctx = self._ensure_ctx(pos)
+        self._ensure_box(box)
+        L = _lib.lib()
+        stream = torch.cuda.current_stream(pos.device).cuda_stream
+        ene = torch.empty((nrep, NUM_ENERGIES), dtype=torch.float64, device=pos.device)
+        for _attempt in range(4):
+            _lib.check(L.tmd_forces(ctx, pos.data_ptr(), forces.data_ptr(), ene.data_ptr(), stream))
+            if not sync:
+                break
+            try:
+                self.stats()  # synchronises; grows the neighbour rows if one overflowed
+                break
+            except _lib.TmdError as err:
+                if err.code != _lib.ERR_OVERFLOW:
+                    raise
+        else:
+            raise RuntimeError("neighbour rows kept overflowing")
+        return ene
+
     def compute(
         self,
         pos,
@@ -250,58 +278,64 @@ class Forces:
         toNumpy=True,
         calculateForces=True,
     ):
+        """forces.py:83-346.  ``explicit_forces=False`` (forces as -dE/dpos by autograd in the
+        reference) runs the same kernels: they evaluate exactly that derivative analytically.
+        With ``toNumpy=False`` and positions that require grad the returned energies carry a
+        grad_fn whose backward is -F of the same kernel pass, so ``Epot.sum().backward()`` and
+        ``torch.vmap`` over a batch of systems work as with the reference (the batch is folded
+        into the replica dimension).  Gradients w.r.t. force-field parameters are not provided."""
         if calculateForces:
             if not explicit_forces and not pos.requires_grad:
                 raise RuntimeError(
                     "The positions passed don't require gradients. Please use pos.detach().requires_grad_(True) before passing."
                 )
-            if not explicit_forces:
-                raise NotImplementedError(
-                    "explicit_forces=False (forces by autograd through the energy) is not built yet; "
-                    "the kernels compute the same explicit forces the reference's default path does"
-                )
-        self._check_tensor(pos, "pos")
-        nrep = pos.shape[0]
-        if forces is None:
-            if calculateForces:
+            if forces is None:
                 raise RuntimeError("forces tensor required when calculateForces=True")
-            if self._scratch_forces is None or self._scratch_forces.shape != pos.shape:
-                self._scratch_forces = torch.empty_like(pos)
-            forces = self._scratch_forces
-        self._check_tensor(forces, "forces", pos.shape)
-        if not torch.is_tensor(box) or tuple(box.shape) != (nrep, 3, 3):
-            raise RuntimeError("box must be a (nreplicas, 3, 3) tensor")
-
-        ctx = self._ensure_ctx(pos)
-        self._ensure_box(box)
-        L = _lib.lib()
-        stream = torch.cuda.current_stream(pos.device).cuda_stream
-        ene = torch.empty((nrep, NUM_ENERGIES), dtype=torch.float64, device=pos.device)
-        for _attempt in range(4):
-            _lib.check(L.tmd_forces(ctx, pos.data_ptr(), forces.data_ptr(), ene.data_ptr(), stream))
-            if not toNumpy:
-                break
-            try:
-                self.stats()  # synchronises; grows the neighbour rows if one overflowed
-                break
-            except _lib.TmdError as err:
-                if err.code != _lib.ERR_OVERFLOW:
-                    raise
         else:
-            raise RuntimeError("neighbour rows kept overflowing")
+            explicit_forces = False
+
+        if (not toNumpy) and torch.is_tensor(pos) and ((pos.requires_grad and torch.is_grad_enabled()) or _is_batched(pos)):
+            sel, F = _EnergyFunction.apply(pos, box, self)
+            if forces is not None:
+                forces.copy_(F)
+            ext = None
+            if self.external:
+                ext, ext_force = self.external.calculate(pos, box)
+                if forces is not None:
+                    if explicit_forces:
+                        forces += ext_force
+                    elif calculateForces and torch.is_tensor(ext) and ext.requires_grad:
+                        forces -= torch.autograd.grad(ext.sum(), pos, retain_graph=True)[0]
+            return self._format_tensors(sel, ext, returnDetails)
+
+        pos_in = pos.detach() if torch.is_tensor(pos) and pos.requires_grad else pos
+        if forces is None:
+            if self._scratch_forces is None or self._scratch_forces.shape != pos_in.shape:
+                self._scratch_forces = torch.empty_like(pos_in)
+            forces = self._scratch_forces
+        ene = self._evaluate(pos_in, box, forces, sync=toNumpy)
 
         ext = None
         if self.external:
-            ext_ene, ext_force = self.external.calculate(pos, box)
-            forces += ext_force
-            ext = ext_ene
-        return self._format(ene, ext, pos.dtype, returnDetails, toNumpy)
+            ext, ext_force = self.external.calculate(pos, box)
+            if explicit_forces:
+                forces += ext_force
+            elif calculateForces and torch.is_tensor(ext) and ext.requires_grad:  # forces.py:328-336
+                forces -= torch.autograd.grad(ext.sum(), pos, retain_graph=True)[0]
+            if torch.is_tensor(ext):
+                ext = ext.detach()
+        if toNumpy:
+            return self._format(ene, ext, pos_in.dtype, returnDetails, True)
+        return self._format_tensors(ene[:, self._energy_columns()].to(pos_in.dtype), ext, returnDetails)
+
+    def _energy_columns(self):
+        return [ENERGY_SLOTS.index(t) for t in self.energies]
 
     def _format(self, ene, ext, dtype, returnDetails, toNumpy):
         """Marshal (R, NUM_ENERGIES) fp64 device sums into the reference's return formats
         (forces.py:338-346)."""
         nrep = ene.shape[0]
-        cols = [ENERGY_SLOTS.index(t) for t in self.energies]
+        cols = self._energy_columns()
         if toNumpy:
             host = ene.cpu().numpy()
             exth = [float(ext[r]) for r in range(nrep)] if ext is not None else [0.0] * nrep
@@ -313,8 +347,12 @@ class Forces:
                     out.append(d)
                 return out
             return [float(host[r, cols].sum()) + exth[r] for r in range(nrep)]
-        sel = ene[:, cols].to(dtype)
-        extt = ext.to(dtype).reshape(nrep) if ext is not None else torch.zeros(nrep, dtype=dtype, device=ene.device)
+        return self._format_tensors(ene[:, cols].to(dtype), ext, returnDetails)
+
+    def _format_tensors(self, sel, ext, returnDetails):
+        """``toNumpy=False`` formats from the (R, nterms) per-term energies (forces.py:338-346)."""
+        nrep = sel.shape[0]
+        extt = ext.to(sel.dtype).reshape(nrep) if ext is not None else torch.zeros(nrep, dtype=sel.dtype, device=sel.device)
         if returnDetails:
             out = []
             for r in range(nrep):
@@ -363,3 +401,53 @@ class Forces:
         p = out[:n].to(torch.int64)
         order = torch.argsort(p[:, 0] * self.natoms + p[:, 1])
         return out[:n][order]
+
+
+
+def _is_batched(t):
+    """Inside torch.vmap the positions are a BatchedTensor (which does not report requires_grad)."""
+    fn = getattr(getattr(torch._C, "_functorch", None), "is_batchedtensor", None)
+    return bool(fn(t)) if fn is not None else False
+
+
+class _EnergyFunction(torch.autograd.Function):
+    """Per-term energies (R, nterms) of ``Forces`` as a differentiable function of the
+    positions: the backward pass is -F from the same kernel pass that produced the energies
+    (forces.py:328-336 obtains F the other way round, as -dE/dpos by autograd).  The kernels
+    give the gradient of the SUM of the terms, so the incoming gradient must be the same for
+    every term of a replica (``Epot.sum()``, the reference's own use); anything else raises."""
+
+    @staticmethod
+    def forward(pos, box, owner):
+        F = torch.empty_like(pos, memory_format=torch.contiguous_format)
+        p = pos.detach().contiguous()
+        ene = owner._evaluate(p, box.detach().contiguous(), F, sync=False)
+        return ene[:, owner._energy_columns()].to(pos.dtype), F
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.mark_non_differentiable(output[1])
+        ctx.save_for_backward(output[1])
+
+    @staticmethod
+    def backward(ctx, grad_e, grad_f):
+        (F,) = ctx.saved_tensors
+        g = grad_e[:, 0]
+        if grad_e.shape[1] > 1 and not bool((grad_e == g[:, None]).all()):
+            raise NotImplementedError(
+                "gradients that differ between energy terms need one force pass per term; "
+                "differentiate the summed energy (returnDetails=False or sum the terms with equal weights)"
+            )
+        return -F * g.to(F.dtype)[:, None, None], None, None
+
+    @staticmethod
+    def vmap(info, in_dims, pos, box, owner):
+        """``torch.vmap`` over a batch of systems: the batch is folded into the replica dimension
+        (the kernels run one grid slice per replica)."""
+        pd, bd, _ = in_dims
+        nb = info.batch_size
+        pb = pos.movedim(pd, 0) if pd is not None else pos.unsqueeze(0).expand(nb, *pos.shape)
+        bb = box.movedim(bd, 0) if bd is not None else box.unsqueeze(0).expand(nb, *box.shape)
+        nrep, natoms = pb.shape[1], pb.shape[2]
+        e, F = _EnergyFunction.apply(pb.reshape(nb * nrep, natoms, 3), bb.reshape(nb * nrep, 3, 3), owner)
+        return (e.reshape(nb, nrep, -1), F.reshape(nb, nrep, natoms, 3)), (0, 0)
