@@ -148,6 +148,13 @@ int tmd_md_steps_host(tmd_ctx* ctx, int niter, float* pos_host, float* vel_host,
                       uint64_t first_step_index, double* energies_host, double* ke_host,
                       tmd_stream stream);
 
+/* Which force the switched LJ term returns.  0 (default): the reference's explicit formula
+ * s*dE/dr + E*s'/r with its extra 1/r (forces.py:410-412), what Forces.compute returns with
+ * explicit_forces=True.  1: the exact derivative d(E*s)/dr = s*dE/dr + E*s', what the
+ * reference obtains by autograd with explicit_forces=False (forces.py:328-336).  Every other
+ * term's explicit force already is its exact gradient.  Takes effect at the next call. */
+int tmd_set_force_convention(tmd_ctx* ctx, int exact_gradient);
+
 /* ---- decomposed runs (one context per rank, every rank holds all positions) --------- */
 
 /* Restrict the FORCE and INTEGRATION work of this context to the atoms

@@ -89,11 +89,13 @@ def pair_geometry(xyz, pairs, box_diag):
 # ----------------------------------------------------------------------------
 # pair potentials  (forces.py:381-491)
 # ----------------------------------------------------------------------------
-def lj_pair(dist, A, B, scale, switch_dist, cutoff):
+def lj_pair(dist, A, B, scale, switch_dist, cutoff, true_gradient=False):
     """12-6 energy and dE/dr, optional quintic switch (forces.py:389-415).
 
     With switching the 'force' is s*dE/dr + E*s'/r  -- the extra 1/r is the
-    reference's (forces.py:410-412) and is reproduced on purpose.
+    reference's (forces.py:410-412) and is reproduced on purpose.  ``true_gradient``: the
+    derivative autograd takes of the same energy, s*dE/dr + E*s' (the reference's
+    explicit_forces=False path, forces.py:328-336).
     """
     rinv = 1 / dist
     r6 = rinv**6
@@ -105,7 +107,7 @@ def lj_pair(dist, A, B, scale, switch_dist, cutoff):
         t = (dist[outer] - switch_dist) / (cutoff - switch_dist)
         sw = 1 + t * t * t * (-10 + t * (15 - t * 6))
         dsw = t * t * (-30 + t * (60 - t * 30)) / (cutoff - switch_dist)
-        dedr[outer] = sw * dedr[outer] + ene[outer] * dsw / dist[outer]
+        dedr[outer] = sw * dedr[outer] + (ene[outer] * dsw if true_gradient else ene[outer] * dsw / dist[outer])
         ene[outer] = ene[outer] * sw
     return ene, dedr
 
@@ -235,12 +237,17 @@ class OracleForces:
         switch_dist=None,
         exclusions=("bonds", "angles", "1-4"),
         decision_dtype=None,
+        true_gradient=False,
     ):
-        """``decision_dtype``: evaluate the ``dist <= cutoff`` masks in this dtype (e.g. the
+        """``true_gradient``: forces as the exact gradient of the energy -- what the reference returns
+        with ``explicit_forces=False`` (autograd, forces.py:328-336); only the switched LJ differs
+        from the explicit formulas.
+        ``decision_dtype``: evaluate the ``dist <= cutoff`` masks in this dtype (e.g. the
         reference's fp32 decisions) while the energies/forces use the dtype of ``pos`` --
         the yardstick for an fp32 kernel: same pair set, exact values.  ``None`` = the
         reference's behaviour (decisions in the dtype of ``pos``)."""
         self.decision_dtype = decision_dtype
+        self.true_gradient = bool(true_gradient)
         self.par = par
         self.terms = [t.lower() for t in terms]
         for t in self.terms:
@@ -361,7 +368,8 @@ class OracleForces:
                             dist, par.charges[pairs[:, 0]], par.charges[pairs[:, 1]], 1, self.cutoff, self.rfa, self.eps_solvent
                         )
                     elif t == "lj":
-                        ene, dedr = lj_pair(dist, par.A[ti[:, 0], ti[:, 1]], par.B[ti[:, 0], ti[:, 1]], 1, self.switch_dist, self.cutoff)
+                        ene, dedr = lj_pair(dist, par.A[ti[:, 0], ti[:, 1]], par.B[ti[:, 0], ti[:, 1]], 1, self.switch_dist, self.cutoff,
+                                            self.true_gradient)
                     elif t == "repulsion":
                         ene, dedr = repulsion_pair(dist, par.A[ti[:, 0], ti[:, 1]])
                     elif t == "repulsioncg":

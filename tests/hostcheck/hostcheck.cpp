@@ -10,6 +10,9 @@ extern "C" {
 
 float hc_squared_threshold(float rc) { return squared_threshold(rc); }
 
+static int g_true_gradient = 0;  // PairParams::true_gradient for hc_pair_terms (forces the run-time term path)
+void hc_set_true_gradient(int on) { g_true_gradient = on; }
+
 // minimum image + squared distance + cutoff decision for n pairs
 void hc_decide(int n, const float* pi, const float* pj, const float* box, int periodic, float s_max,
                float* w_out, float* s_out, int* in_out) {
@@ -39,9 +42,10 @@ void hc_pair_terms(int n, const float* s, const float* qq, const float* A, const
   pp.krf = krf;
   pp.crf = crf;
   pp.two_krf = 2.0f * krf;
+  pp.true_gradient = g_true_gradient;
   for (int k = 0; k < n; ++k) {
     float a = 0, b = 0, c = 0, d = 0, rinv;
-    dedr[k] = (terms == (T_LJ | T_ELEC) && has_switch && rfa) ? pair_terms<1>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv) : pair_terms<0>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv);
+    dedr[k] = (terms == (T_LJ | T_ELEC) && has_switch && rfa && !g_true_gradient) ? pair_terms<1>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv) : pair_terms<0>(pp, s[k], qq[k], A[k], B[k], a, b, c, d, rinv);
     e_el[k] = a; e_lj[k] = b; e_rep[k] = c; e_cg[k] = d;
   }
 }

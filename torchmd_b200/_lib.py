@@ -72,6 +72,7 @@ _SIGNATURES = {
     "tmd_export_pairs": (C.c_int, [_P, _P, C.c_int, _P, C.c_int64, _P, _P]),
     "tmd_get_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "tmd_set_owned_atoms": (C.c_int, [_P, C.c_int, C.c_int]),
+    "tmd_set_force_convention": (C.c_int, [_P, C.c_int]),
     "tmd_dd_create": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "tmd_dd_connect": (C.c_int, [_P, _P]),
     "tmd_dd_load": (C.c_int, [_P, C.c_int, _P, _P]),

@@ -199,7 +199,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
   __shared__ float2 ab_s[SMALLT ? FX_SMALLT_MAX * FX_SMALLT_MAX : 1];
   if (SMALLT) {
     static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX <= PAIR_WARPS * 32, "one table entry per thread");
-    if ((int)threadIdx.x < S.ntypes * S.ntypes) ab_s[threadIdx.x] = S.AB[threadIdx.x];
+    if (S.AB && (int)threadIdx.x < S.ntypes * S.ntypes) ab_s[threadIdx.x] = S.AB[threadIdx.x];  // no table without an LJ-type term
     __syncthreads();
   }
 

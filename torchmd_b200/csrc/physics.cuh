@@ -229,6 +229,8 @@ struct PairParams {
   float inv_sw_width; // 1 / (cutoff - switch_dist)
   float krf, crf;     // reaction-field constants (forces.py:466-468)
   float two_krf;
+  int true_gradient;  // 1: switched-LJ force is the exact d(E*s)/dr (the reference's autograd path, forces.py:328-336);
+                      // 0: the reference's explicit formula with its extra 1/r (forces.py:410-412)
 };
 
 enum : uint32_t {
@@ -272,7 +274,9 @@ TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float 
       float t = fmaxf((r - pp.switch_dist) * pp.inv_sw_width, 0.0f);
       float sw = 1.0f + t * t * t * (-10.0f + t * (15.0f - t * 6.0f));
       float dsw = t * t * (-30.0f + t * (60.0f - t * 30.0f)) * pp.inv_sw_width;
-      f = sw * f + e * dsw * rinv;
+      // explicit path: s*dE/dr + E*s'/r (sic, forces.py:410-412); autograd path: the true derivative
+      const bool exact = MODE == 1 ? false : pp.true_gradient != 0;
+      f = sw * f + e * dsw * (exact ? 1.0f : rinv);
       e = e * sw;
     }
     e_lj += e;

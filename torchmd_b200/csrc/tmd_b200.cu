@@ -394,7 +394,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     ctx->safe_image = (ctx->cutoff + 2.0 * ctx->skin + 2.0 * margin) < 0.45 * (double)lmin;
   }
   d.check_far = ctx->safe_image ? 1 : 0;
-  ctx->pair_mode = (ctx->pair_mask == (T_LJ | T_ELEC) && d.pp.has_switch && d.pp.rfa) ? 1 : 0;
+  d.pp.true_gradient = ctx->exact_gradient;
+  ctx->pair_mode = (ctx->pair_mask == (T_LJ | T_ELEC) && d.pp.has_switch && d.pp.rfa && !ctx->exact_gradient) ? 1 : 0;
 
   // Fixed-point separations in the pair kernel (k_pair_fx): periodic box with the guard-free
   // image condition.  Opt-in (TMD_B200_FX=1) until it has been through the B200 parity suite.
@@ -758,6 +759,14 @@ int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs
   k_export_pairs<<<(ctx->natoms + 3) / 4, 128, 0, st>>>(ctx->d, replica, pairs, (long long)capacity,
                                                        reinterpret_cast<unsigned long long*>(count));
   TMD_LAUNCHED(ctx, "k_export_pairs");
+  return TMD_OK;
+}
+
+int tmd_set_force_convention(tmd_ctx* ctx, int exact_gradient) {
+  if (!ctx) return fail(TMD_ERR_ARG, "tmd_set_force_convention: null context");
+  ctx->exact_gradient = exact_gradient ? 1 : 0;
+  ctx->d.pp.true_gradient = ctx->exact_gradient;  // uniform kernel parameter: takes effect at the next launch
+  ctx->pair_mode = (ctx->pair_mask == (T_LJ | T_ELEC) && ctx->d.pp.has_switch && ctx->d.pp.rfa && !ctx->exact_gradient) ? 1 : 0;
   return TMD_OK;
 }
 

@@ -110,6 +110,7 @@ class Forces:
         self._ctx_key = None
         self._box_key = None
         self._scratch_forces = None
+        self._exact_gradient = False  # force convention currently set in the context
 
     # ------------------------------------------------------------------ context
     def __del__(self):
@@ -228,6 +229,7 @@ class Forces:
             _lib.check(L.tmd_set_pairs14(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
 
         self._ctx, self._ctx_key, self._box_key = ctx, key, None
+        self._exact_gradient = False
         return ctx
 
     def _ensure_box(self, box):
@@ -240,10 +242,12 @@ class Forces:
         self._box_key = key
 
     # ------------------------------------------------------------------ compute
-    def _evaluate(self, pos, box, forces, sync=True):
+    def _evaluate(self, pos, box, forces, sync=True, exact_gradient=False):
         """One pass of the kernels: forces (R,N,3) overwritten, returns the (R, NUM_ENERGIES) fp64
         device energies.  ``sync``: check the neighbour rows now (synchronises; a row overflow
-        grows the capacity and recomputes) instead of at the next ``stats()``."""
+        grows the capacity and recomputes) instead of at the next ``stats()``.
+        ``exact_gradient``: the switched-LJ force as the true derivative of the energy (what the
+        reference's autograd path yields) instead of its explicit formula (forces.py:410-412)."""
         self._check_tensor(pos, "pos")
         nrep = pos.shape[0]
         self._check_tensor(forces, "forces", pos.shape)
@@ -252,6 +256,9 @@ class Forces:
         ctx = self._ensure_ctx(pos)
         self._ensure_box(box)
         L = _lib.lib()
+        if bool(exact_gradient) != self._exact_gradient:
+            _lib.check(L.tmd_set_force_convention(ctx, int(bool(exact_gradient))))
+            self._exact_gradient = bool(exact_gradient)
         stream = torch.cuda.current_stream(pos.device).cuda_stream
         ene = torch.empty((nrep, NUM_ENERGIES), dtype=torch.float64, device=pos.device)
         for _attempt in range(4):
@@ -279,11 +286,14 @@ class Forces:
         calculateForces=True,
     ):
         """forces.py:83-346.  ``explicit_forces=False`` (forces as -dE/dpos by autograd in the
-        reference) runs the same kernels: they evaluate exactly that derivative analytically.
-        With ``toNumpy=False`` and positions that require grad the returned energies carry a
-        grad_fn whose backward is -F of the same kernel pass, so ``Epot.sum().backward()`` and
-        ``torch.vmap`` over a batch of systems work as with the reference (the batch is folded
-        into the replica dimension).  Gradients w.r.t. force-field parameters are not provided."""
+        reference) runs the same kernels with the switched-LJ term in its exact-gradient form:
+        every other term's explicit force already is the derivative of its energy, the
+        reference's explicit switched LJ is not (forces.py:410-412), and autograd returns the
+        true one.  With ``toNumpy=False`` and positions that require grad the returned energies
+        carry a grad_fn whose backward is -F of that exact-gradient pass, so
+        ``Epot.sum().backward()`` and ``torch.vmap`` over a batch of systems work as with the
+        reference (the batch is folded into the replica dimension).  Gradients w.r.t.
+        force-field parameters are not provided."""
         if calculateForces:
             if not explicit_forces and not pos.requires_grad:
                 raise RuntimeError(
@@ -297,7 +307,10 @@ class Forces:
         if (not toNumpy) and torch.is_tensor(pos) and ((pos.requires_grad and torch.is_grad_enabled()) or _is_batched(pos)):
             sel, F = _EnergyFunction.apply(pos, box, self)
             if forces is not None:
-                forces.copy_(F)
+                if explicit_forces:  # the buffer gets the explicit-formula forces, the graph the true gradient
+                    self._evaluate(pos.detach(), box, forces, sync=False, exact_gradient=False)
+                else:
+                    forces.copy_(F)
             ext = None
             if self.external:
                 ext, ext_force = self.external.calculate(pos, box)
@@ -313,7 +326,7 @@ class Forces:
             if self._scratch_forces is None or self._scratch_forces.shape != pos_in.shape:
                 self._scratch_forces = torch.empty_like(pos_in)
             forces = self._scratch_forces
-        ene = self._evaluate(pos_in, box, forces, sync=toNumpy)
+        ene = self._evaluate(pos_in, box, forces, sync=toNumpy, exact_gradient=calculateForces and not explicit_forces)
 
         ext = None
         if self.external:
@@ -421,7 +434,7 @@ class _EnergyFunction(torch.autograd.Function):
     def forward(pos, box, owner):
         F = torch.empty_like(pos, memory_format=torch.contiguous_format)
         p = pos.detach().contiguous()
-        ene = owner._evaluate(p, box.detach().contiguous(), F, sync=False)
+        ene = owner._evaluate(p, box.detach().contiguous(), F, sync=False, exact_gradient=True)
         return ene[:, owner._energy_columns()].to(pos.dtype), F
 
     @staticmethod
