@@ -9,6 +9,8 @@ timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_su
 tail -3 gpurun_out/validate_suite.log
 TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_gpu_zzz_fixedpoint.py -q -s > gpurun_out/validate_fx.log 2>&1; echo "fx rc=$?"
 grep -E "max\|dF\||NVE|passed|failed|Error|error" gpurun_out/validate_fx.log | tail -30
+TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_gpu_zzz_p2p.py -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap/autograd/p2p-world1 rc=$?"
+grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
 for fx in 0 1; do
   TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx$fx.json 2> gpurun_out/validate_bench_fx$fx.err
   python - <<PY
@@ -17,13 +19,16 @@ d=json.load(open("gpurun_out/validate_bench_fx$fx.json"))
 print("FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f frac %.4f T %.0f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["roofline"]["frac"], d["state"]["temperature_K"]))
 PY
 done
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DPAIR_FX_MINBLOCKS=5 -o /tmp/var/lib_fx5.so torchmd_b200/csrc/tmd_b200.cu
-TMD_B200_LIB=/tmp/var/lib_fx5.so TMD_B200_FX=1 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx5.json 2> gpurun_out/validate_bench_fx5.err
-python - <<PY
+for cfg in "5 2" "6 4" "5 4"; do
+  set -- $cfg; mb=$1; un=$2
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DPAIR_FX_MINBLOCKS=$mb -DPAIR_FX_UNROLL=$un -o /tmp/var/lib_fx_${mb}_$un.so torchmd_b200/csrc/tmd_b200.cu
+  TMD_B200_LIB=/tmp/var/lib_fx_${mb}_$un.so TMD_B200_FX=1 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx_${mb}_$un.json 2> gpurun_out/validate_bench_fx_${mb}_$un.err
+  python - <<PY
 import json
-d=json.load(open("gpurun_out/validate_bench_fx5.json"))
-print("FX=1, 5 CTAs/SM (48 regs): steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
+d=json.load(open("gpurun_out/validate_bench_fx_${mb}_$un.json"))
+print("FX=1, $mb CTAs/SM, $un entries/lane/iteration: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
 PY
+done
 # 4. list build with chunk culling (-DBT_CULL=1): whole GPU suite + bench against the variant library
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
 TMD_B200_LIB=/tmp/var/lib_cull.so timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_cull_suite.log 2>&1; echo "cull suite rc=$?"

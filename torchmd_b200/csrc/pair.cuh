@@ -174,6 +174,9 @@ constexpr int FX_SMALLT_MAX = 16;
 #ifndef PAIR_FX_MINBLOCKS
 #define PAIR_FX_MINBLOCKS PAIR_MINBLOCKS
 #endif
+#ifndef PAIR_FX_UNROLL
+#define PAIR_FX_UNROLL 2  // list entries per lane and loop iteration (2 or 4)
+#endif
 
 // Partner record of a replica's fixed-point array at byte offset `off` from `base` (an
 // integer the compiler cannot see through, so the replica's base stays in a register pair
@@ -246,6 +249,30 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
       if (s < s_lo) accumulate(entry, wx, wy, wz, s, __int_as_float(pj.w));
       else s_skipped = fminf(s_skipped, s);
     };
+#if PAIR_FX_UNROLL == 4
+    {  // four entries per lane and iteration (tuning variant: two more registers, half the loop overhead)
+      int e = lane;
+      int j0 = (e < n) ? __ldcs(row + e) : -1;
+      int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+      int j2 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+      int j3 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+      while (e < n) {
+        const int jn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
+        const int jn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
+        const int jn2 = (e + 192 < n) ? __ldcs(row + e + 192) : -1;
+        const int jn3 = (e + 224 < n) ? __ldcs(row + e + 224) : -1;
+        if (j0 >= 0) interact(j0, fx_record(xf_base, ((unsigned)j0 << 4) & 0x0ffffff0u));
+        if (j1 >= 0) interact(j1, fx_record(xf_base, ((unsigned)j1 << 4) & 0x0ffffff0u));
+        if (j2 >= 0) interact(j2, fx_record(xf_base, ((unsigned)j2 << 4) & 0x0ffffff0u));
+        if (j3 >= 0) interact(j3, fx_record(xf_base, ((unsigned)j3 << 4) & 0x0ffffff0u));
+        j0 = jn0;
+        j1 = jn1;
+        j2 = jn2;
+        j3 = jn3;
+        e += 128;
+      }
+    }
+#else
     {
       int e = lane;
       int j0 = (e < n) ? __ldcs(row + e) : -1;
@@ -260,6 +287,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
         e += 64;
       }
     }
+#endif
     if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
       // rare (a few percent of the rows): re-scan the row and give the pairs inside the band
       // the reference's own decision on the original positions
