@@ -41,3 +41,16 @@ d=json.load(open("gpurun_out/validate_bench_cull_fx$fx.json"))
 print("CULL=1 FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
 PY
 done
+# 5. bonded kernel overlapped with the pair kernel on a second stream (TMD_B200_OVERLAP=1): suite + bench
+TMD_B200_OVERLAP=1 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_overlap_suite.log 2>&1; echo "overlap suite rc=$?"
+tail -3 gpurun_out/validate_overlap_suite.log
+for cfg in "0 0" "1 0" "1 1"; do
+  set -- $cfg; fx=$1; cull=$2
+  lib=torchmd_b200/libtmd_b200.so; [ "$cull" = 1 ] && lib=/tmp/var/lib_cull.so
+  TMD_B200_LIB=$lib TMD_B200_FX=$fx TMD_B200_OVERLAP=1 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_ov_${fx}_$cull.json 2> gpurun_out/validate_bench_ov_${fx}_$cull.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/validate_bench_ov_${fx}_$cull.json"))
+print("OVERLAP=1 FX=$fx CULL=$cull: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
+PY
+done

@@ -46,7 +46,7 @@ __device__ __forceinline__ Vec3 load3(const float* p, size_t atom) {
 
 __global__ void __launch_bounds__(BONDED_THREADS)
 k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, const float* __restrict__ pos,
-         float* __restrict__ forces, double* __restrict__ energies) {
+         float* __restrict__ forces, double* __restrict__ energies, double* __restrict__ scratch) {
   const int r = blockIdx.y;
   const int a = S.own_lo + blockIdx.x * blockDim.x + threadIdx.x;  // owned atoms only
   const size_t base = (size_t)r * S.natoms;
@@ -120,7 +120,14 @@ k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, cons
         f = slot == 0 ? f - fv : f + fv;
       }
     }
-    if (T.atom_ptr[a + 1] > T.atom_ptr[a]) {
+    if (scratch) {
+      // overlapped with the pair kernel on another stream: the fp64 sums go to a scratch
+      // buffer, k_add_bonded folds them into the forces afterwards (same single rounding)
+      double* o = scratch + (base + a) * 3;
+      o[0] = f.x;
+      o[1] = f.y;
+      o[2] = f.z;
+    } else if (T.atom_ptr[a + 1] > T.atom_ptr[a]) {
       float* out = forces + (base + a) * 3;
       out[0] = (float)((double)out[0] + f.x);
       out[1] = (float)((double)out[1] + f.y);
@@ -138,6 +145,19 @@ k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, cons
       if (S.pp.terms & T_LJ) block_accumulate<BONDED_THREADS / 32>(e_lj, E + TMD_E_LJ, red);
       if (S.pp.terms & T_ELEC) block_accumulate<BONDED_THREADS / 32>(e_el, E + TMD_E_ELECTROSTATICS, red);
     }
+  }
+}
+
+// forces += bonded sums of k_bonded's scratch mode (owned atoms), rounded once like the in-place path
+__global__ void __launch_bounds__(BONDED_THREADS)
+k_add_bonded(int natoms, int lo, int cnt, float* __restrict__ forces, const double* __restrict__ scratch) {
+  const int a = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= lo + cnt) return;
+  const size_t e = ((size_t)blockIdx.y * natoms + a) * 3;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double s = scratch[e + d];
+    if (s != 0.0) forces[e + d] = (float)((double)forces[e + d] + s);
   }
 }
 

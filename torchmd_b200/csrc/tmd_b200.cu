@@ -81,6 +81,10 @@ int device_alloc(T** dst, size_t n) {
 
 
 struct CtxPriv {
+  // TMD_B200_OVERLAP=1: bonded kernel on a second stream, concurrent with the pair kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double* bonded_scratch = nullptr;  // (R,N,3) fp64
   bool dirty = true;
   size_t nbr_entries = 0;
   std::vector<cudaEvent_t> ev;  // pair-kernel timing samples (begin,end interleaved)
@@ -177,6 +181,10 @@ int tmd_destroy(tmd_ctx* ctx) {
     if (b) cudaFree(b);
   dd_release(ctx);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
+  if (priv(ctx).side) cudaStreamDestroy(priv(ctx).side);
+  if (priv(ctx).ev_fork) cudaEventDestroy(priv(ctx).ev_fork);
+  if (priv(ctx).ev_join) cudaEventDestroy(priv(ctx).ev_join);
+  if (priv(ctx).bonded_scratch) cudaFree(priv(ctx).bonded_scratch);
   delete static_cast<tmd_ctx_full*>(ctx);
   return TMD_OK;
 }
@@ -516,6 +524,23 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       if (total >= R) ctx->coop_blocks = std::max(1, total / R);
     }
   }
+  // bonded kernel concurrent with the pair kernel (opt-in until validated on a B200)
+  {
+    CtxPriv& pv = priv(ctx);
+    const char* env = getenv("TMD_B200_OVERLAP");
+    const bool want = env && env[0] == '1' && ctx->bonded_nentries > 0 && ctx->pair_mask;
+    if (want && !pv.side) {
+      TMD_CUDA(cudaStreamCreateWithFlags(&pv.side, cudaStreamNonBlocking));
+      TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_fork, cudaEventDisableTiming));
+      TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_join, cudaEventDisableTiming));
+      if ((rc = device_alloc(&pv.bonded_scratch, (size_t)R * N * 3))) return rc;
+      TMD_CUDA(cudaMemset(pv.bonded_scratch, 0, (size_t)R * N * 3 * sizeof(double)));
+    }
+    if (!want && pv.side) {
+      cudaStreamDestroy(pv.side);
+      pv.side = nullptr;
+    }
+  }
   priv(ctx).dirty = false;
   return TMD_OK;
 }
@@ -567,6 +592,35 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   ctx->force_calls++;
   if (energies) TMD_CUDA(cudaMemsetAsync(energies, 0, (size_t)R * TMD_NUM_ENERGIES * sizeof(double), st));
 
+  BondedTables T;
+  const bool have_bonded = ctx->bonded_nentries > 0;
+  if (have_bonded) {
+    const uint32_t bm = ctx->bonded_mask;
+    T.atom_ptr = ctx->bonded_atom_ptr;
+    T.entries = ctx->bonded_entries;
+    T.bonds = ctx->bonds;
+    T.angles = ctx->angles;
+    T.torsions[0] = ctx->torsions[0];
+    T.torsions[1] = ctx->torsions[1];
+    T.pairs14 = ctx->pairs14;
+    if (!(bm & TMD_TERM(TMD_E_BONDS))) T.bonds.n = 0;
+    if (!(bm & TMD_TERM(TMD_E_ANGLES))) T.angles.n = 0;
+    if (!(bm & TMD_TERM(TMD_E_DIHEDRALS))) T.torsions[0].n = 0;
+    if (!(bm & TMD_TERM(TMD_E_IMPROPERS))) T.torsions[1].n = 0;
+    if (!(bm & TMD_TERM(TMD_E_14))) T.pairs14.n = 0;
+  }
+  // fork: the bonded terms need only the positions, so they run on a second stream while the
+  // list check and the pair kernel run here; joined by k_add_bonded below
+  const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr;
+  if (overlap) {
+    CtxPriv& pv = priv(ctx);
+    TMD_CUDA(cudaEventRecord(pv.ev_fork, st));
+    TMD_CUDA(cudaStreamWaitEvent(pv.side, pv.ev_fork, 0));
+    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, pv.side>>>(d, T, ctx->q, pos, forces, energies, pv.bonded_scratch);
+    TMD_LAUNCHED(ctx, "k_bonded");
+    TMD_CUDA(cudaEventRecord(pv.ev_join, pv.side));
+  }
+
   if (ctx->pair_mask) {
     k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
     TMD_LAUNCHED(ctx, "k_prepare");
@@ -615,22 +669,13 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     TMD_CUDA(cudaMemsetAsync(forces, 0, (size_t)R * N * 3 * sizeof(float), st));
   }
 
-  if (ctx->bonded_nentries > 0) {
-    const uint32_t bm = ctx->bonded_mask;
-    BondedTables T;
-    T.atom_ptr = ctx->bonded_atom_ptr;
-    T.entries = ctx->bonded_entries;
-    T.bonds = ctx->bonds;
-    T.angles = ctx->angles;
-    T.torsions[0] = ctx->torsions[0];
-    T.torsions[1] = ctx->torsions[1];
-    T.pairs14 = ctx->pairs14;
-    if (!(bm & TMD_TERM(TMD_E_BONDS))) T.bonds.n = 0;
-    if (!(bm & TMD_TERM(TMD_E_ANGLES))) T.angles.n = 0;
-    if (!(bm & TMD_TERM(TMD_E_DIHEDRALS))) T.torsions[0].n = 0;
-    if (!(bm & TMD_TERM(TMD_E_IMPROPERS))) T.torsions[1].n = 0;
-    if (!(bm & TMD_TERM(TMD_E_14))) T.pairs14.n = 0;
-    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies);
+  if (overlap) {
+    CtxPriv& pv = priv(ctx);
+    TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_join, 0));
+    k_add_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
+    TMD_LAUNCHED(ctx, "k_add_bonded");
+  } else if (have_bonded) {
+    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies, nullptr);
     TMD_LAUNCHED(ctx, "k_bonded");
   }
   return TMD_OK;
