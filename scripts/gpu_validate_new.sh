@@ -54,3 +54,14 @@ d=json.load(open("gpurun_out/validate_bench_ov_${fx}_$cull.json"))
 print("OVERLAP=1 FX=$fx CULL=$cull: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
 PY
 done
+# 6. single-GPU step as a replayed CUDA graph with the rebuild in a conditional node (TMD_B200_GRAPH=1)
+TMD_B200_GRAPH=1 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_graph_suite.log 2>&1; echo "graph suite rc=$?"
+tail -3 gpurun_out/validate_graph_suite.log
+for fx in 0 1; do
+  TMD_B200_GRAPH=1 TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_graph_fx$fx.json 2> gpurun_out/validate_bench_graph_fx$fx.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/validate_bench_graph_fx$fx.json"))
+print("GRAPH=1 FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f launches %d"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["gpu_launches"]))
+PY
+done

@@ -49,6 +49,7 @@ struct DeviceState {
   int nsub;         // cells per list radius
   int own_lo, own_n, own_all;  // atoms (original indices) whose forces this context computes; all by default
   unsigned long long* counters;  // [0] force calls (parity of the rebuild flag), [1] vv_first calls (Philox position)
+  unsigned long long cond;       // cudaGraphConditionalHandle of the rebuild body when this launch is a graph node; 0 otherwise
   int check_far;    // flag positions beyond 2000 box lengths (guard-free minimum image in use)
   // per-atom static data (original order)
   const float* q;        // charge * sqrt(coulomb constant)

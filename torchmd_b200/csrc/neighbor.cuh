@@ -72,7 +72,11 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
   const float dx = x - ref.x, dy = y - ref.y, dz = z - ref.z;
   const float d2 = dx * dx + dy * dy + dz * dz;
   if (!(d2 <= S.trigger2)) {  // also true for NaN (= no list yet)
-    if (fl[F_REBUILD0 + parity] == 0) fl[F_REBUILD0 + parity] = 1;
+    if (fl[F_REBUILD0 + parity] == 0) {
+      fl[F_REBUILD0 + parity] = 1;
+      // inside a CUDA graph the rebuild kernels sit in the body of a conditional node: switch it on
+      if (S.cond) cudaGraphSetConditional((cudaGraphConditionalHandle)S.cond, 1u);
+    }
   }
   if (S.check_far) {
     const Grid* g = S.grid + r;

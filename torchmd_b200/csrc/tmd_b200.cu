@@ -85,6 +85,27 @@ struct CtxPriv {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double* bonded_scratch = nullptr;  // (R,N,3) fp64
+  // TMD_B200_COND=1: when a force call is being captured into a CUDA graph, the rebuild kernels go
+  // into the body of a conditional node that k_prepare switches on (nothing is launched on the
+  // steps that keep their list) instead of five kernels that return at once
+  bool use_cond = false;
+  cudaStream_t helper = nullptr;     // captures the body of the conditional node
+  // TMD_B200_GRAPH=1: tmd_md_steps replays one captured step (two variants: with / without energies)
+  bool use_graph = false;
+  cudaStream_t gstream = nullptr;    // capture + replay stream (the caller's may be the legacy default stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  struct StepKey {
+    float *pos, *vel, *forces;
+    const float *masses, *vcoeff;
+    double dt, gamma;
+    uint64_t seed, first_step;
+    double *energies, *ke;
+  } step_key{};
+  DeviceState step_state{};          // the kernel arguments baked into the captured steps
+  bool steps_valid = false;
+  int64_t step_launches[2] = {0, 0};  // kernels of one captured step (rebuild body included)
   bool dirty = true;
   size_t nbr_entries = 0;
   std::vector<cudaEvent_t> ev;  // pair-kernel timing samples (begin,end interleaved)
@@ -181,6 +202,14 @@ int tmd_destroy(tmd_ctx* ctx) {
     if (b) cudaFree(b);
   dd_release(ctx);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
+  for (int k = 0; k < 2; ++k) {
+    if (priv(ctx).exec[k]) cudaGraphExecDestroy(priv(ctx).exec[k]);
+    if (priv(ctx).graph[k]) cudaGraphDestroy(priv(ctx).graph[k]);
+  }
+  if (priv(ctx).helper) cudaStreamDestroy(priv(ctx).helper);
+  if (priv(ctx).gstream) cudaStreamDestroy(priv(ctx).gstream);
+  if (priv(ctx).ev_in) cudaEventDestroy(priv(ctx).ev_in);
+  if (priv(ctx).ev_out) cudaEventDestroy(priv(ctx).ev_out);
   if (priv(ctx).side) cudaStreamDestroy(priv(ctx).side);
   if (priv(ctx).ev_fork) cudaEventDestroy(priv(ctx).ev_fork);
   if (priv(ctx).ev_join) cudaEventDestroy(priv(ctx).ev_join);
@@ -541,6 +570,20 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       pv.side = nullptr;
     }
   }
+  {
+    CtxPriv& pv = priv(ctx);
+    const char* ec = getenv("TMD_B200_COND");
+    const char* eg = getenv("TMD_B200_GRAPH");
+    pv.use_graph = eg && eg[0] == '1';
+    pv.use_cond = (ec && ec[0] == '1') || pv.use_graph;
+    if (pv.use_cond && !pv.helper) TMD_CUDA(cudaStreamCreateWithFlags(&pv.helper, cudaStreamNonBlocking));
+    if (pv.use_graph && !pv.gstream) {
+      TMD_CUDA(cudaStreamCreateWithFlags(&pv.gstream, cudaStreamNonBlocking));
+      TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_in, cudaEventDisableTiming));
+      TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_out, cudaEventDisableTiming));
+    }
+    pv.steps_valid = false;  // buffers may have moved: captured steps are rebuilt
+  }
   priv(ctx).dirty = false;
   return TMD_OK;
 }
@@ -622,10 +665,43 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   }
 
   if (ctx->pair_mask) {
-    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
+    // Being captured into a CUDA graph?  Then the rebuild becomes the body of a conditional node.
+    cudaGraph_t cap_graph = nullptr;
+    bool in_body = false;
+    if (priv(ctx).use_cond) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamGetCaptureInfo(st, &cs, nullptr, &cap_graph, nullptr, nullptr) != cudaSuccess ||
+          cs != cudaStreamCaptureStatusActive)
+        cap_graph = nullptr;
+    }
+    DeviceState dp = d;  // k_prepare's copy carries the handle it switches on
+    cudaGraphConditionalHandle handle = 0;
+    if (cap_graph) {
+      TMD_CUDA(cudaGraphConditionalHandleCreate(&handle, cap_graph, 0, cudaGraphCondAssignDefault));
+      dp.cond = (unsigned long long)handle;
+    }
+    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(dp, pos);
     TMD_LAUNCHED(ctx, "k_prepare");
     const int need_bounds = (!ctx->periodic && ctx->cutoff >= 0) ? 1 : 0;
-    if (ctx->coop_blocks > 0) {
+    cudaStream_t rs = st;  // stream the rebuild kernels are enqueued on
+    cudaGraphNode_t cond_node = nullptr;
+    if (cap_graph) {
+      cudaStreamCaptureStatus cs;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t ndeps = 0;
+      TMD_CUDA(cudaStreamGetCaptureInfo(st, &cs, nullptr, &cap_graph, &deps, &ndeps));
+      cudaGraphNodeParams np = {};  // (anonymous union member: no default constructor)
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = handle;
+      np.conditional.type = cudaGraphCondTypeIf;
+      np.conditional.size = 1;
+      TMD_CUDA(cudaGraphAddNode(&cond_node, cap_graph, deps, ndeps, &np));
+      TMD_CUDA(cudaStreamBeginCaptureToGraph(priv(ctx).helper, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                             cudaStreamCaptureModeRelaxed));
+      rs = priv(ctx).helper;
+      in_body = true;
+    }
+    if (ctx->coop_blocks > 0 && !in_body) {
       // the whole (gated) rebuild in one cooperative launch
       const float* pos_arg = pos;
       int nb_arg = need_bounds;
@@ -635,24 +711,29 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_rebuild");
     } else {
       if (need_bounds) {
-        k_bounds<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
+        k_bounds<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d, pos);
         TMD_LAUNCHED(ctx, "k_bounds");
-        k_grid<<<(R + 63) / 64, 64, 0, st>>>(d);
+        k_grid<<<(R + 63) / 64, 64, 0, rs>>>(d);
         TMD_LAUNCHED(ctx, "k_grid");
       }
-      k_bin<<<atoms_grid(ctx, 256), 256, 0, st>>>(d, pos);
+      k_bin<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d, pos);
       TMD_LAUNCHED(ctx, "k_bin");
-      k_scan<<<R, 1024, 0, st>>>(d);
+      k_scan<<<R, 1024, 0, rs>>>(d);
       TMD_LAUNCHED(ctx, "k_scan");
-      k_place<<<atoms_grid(ctx, 256), 256, 0, st>>>(d);
+      k_place<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d);
       TMD_LAUNCHED(ctx, "k_place");
       {
         const int blocks = std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8));
-        k_sort_pack<<<dim3(blocks, R), 256, 0, st>>>(d);
+        k_sort_pack<<<dim3(blocks, R), 256, 0, rs>>>(d);
         TMD_LAUNCHED(ctx, "k_sort_pack");
       }
-      k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, st>>>(d);
+      k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, rs>>>(d);
       TMD_LAUNCHED(ctx, "k_build_list");
+    }
+    if (in_body) {
+      cudaGraph_t body = nullptr;
+      TMD_CUDA(cudaStreamEndCapture(priv(ctx).helper, &body));
+      TMD_CUDA(cudaStreamUpdateCaptureDependencies(st, &cond_node, 1, cudaStreamSetCaptureDependencies));
     }
 
     const dim3 pg((std::max(d.own_n, 1) + PAIR_WARPS - 1) / PAIR_WARPS, R);
@@ -755,6 +836,52 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
   int rc;
   if (priv(ctx).dirty && (rc = finalize(ctx, st))) return rc;
   const size_t per_step = (size_t)ctx->nrep * ctx->natoms * 3;
+  CtxPriv& pv = priv(ctx);
+  if (pv.use_graph && !noise && !pv.profiling && niter > 0) {
+    // One MD step captured once (with and without the energy outputs) and replayed: one graph
+    // launch per step, the rebuild kernels inside a conditional node.  Everything that changes
+    // between steps lives on the device, so the captured step is valid until an argument or a
+    // context buffer changes.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      const CtxPriv::StepKey key{pos, vel, forces, masses, vcoeff, dt, gamma, seed, first_step, energies, ke};
+      if (!pv.steps_valid || memcmp(&key, &pv.step_key, sizeof(key)) != 0 || memcmp(&ctx->d, &pv.step_state, sizeof(DeviceState)) != 0) {
+        for (int k = 0; k < 2; ++k) {
+          if (pv.exec[k]) cudaGraphExecDestroy(pv.exec[k]);
+          if (pv.graph[k]) cudaGraphDestroy(pv.graph[k]);
+          pv.exec[k] = nullptr;
+          pv.graph[k] = nullptr;
+          const bool with_e = (k == 1);
+          const int64_t l0 = ctx->launches, f0 = ctx->force_calls;
+          TMD_CUDA(cudaStreamBeginCapture(pv.gstream, cudaStreamCaptureModeRelaxed));
+          rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, pv.gstream);
+          if (!rc) rc = enqueue_forces(ctx, pos, forces, with_e ? energies : nullptr, pv.gstream);
+          if (!rc) rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, nullptr, seed, first_step,
+                                          with_e ? ke : nullptr, pv.gstream);
+          cudaError_t ce = cudaStreamEndCapture(pv.gstream, &pv.graph[k]);
+          if (rc) return rc;
+          if (ce != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+          TMD_CUDA(cudaGraphInstantiate(&pv.exec[k], pv.graph[k], 0));
+          pv.step_launches[k] = ctx->launches - l0;
+          ctx->launches = l0;  // the capture launched nothing; replays are counted below
+          ctx->force_calls = f0;
+        }
+        memset(&pv.step_key, 0, sizeof(pv.step_key));
+        pv.step_key = key;
+        pv.step_state = ctx->d;
+        pv.steps_valid = true;
+      }
+      TMD_CUDA(cudaEventRecord(pv.ev_in, st));
+      TMD_CUDA(cudaStreamWaitEvent(pv.gstream, pv.ev_in, 0));
+      for (int it = 0; it < niter; ++it) TMD_CUDA(cudaGraphLaunch(pv.exec[it == niter - 1 ? 1 : 0], pv.gstream));
+      TMD_CUDA(cudaEventRecord(pv.ev_out, pv.gstream));
+      TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_out, 0));
+      ctx->force_calls += niter;
+      ctx->launches += (int64_t)(niter - 1) * pv.step_launches[0] + pv.step_launches[1];
+      return TMD_OK;
+    }
+  }
   for (int it = 0; it < niter; ++it) {
     const bool last = (it == niter - 1);
     if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st))) return rc;
