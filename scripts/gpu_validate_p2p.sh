@@ -17,3 +17,15 @@ except Exception as e:
     print("$ex N=$N: no result", e)
 PY
 done
+# conditional-node rebuild inside the captured multi-GPU step
+for ex in allgather p2p; do
+  TMD_B200_COND=1 TMD_B200_EXCHANGE=$ex timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29583 bench.py --gpus $N --steps 3000 --warmup 100 > gpurun_out/p2p_bench_cond_${ex}_$N.json 2> gpurun_out/p2p_bench_cond_${ex}_$N.err
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/p2p_bench_cond_${ex}_$N.json") if l.startswith("{")][-1])
+    print("COND=1 $ex N=$N: steps/s %.0f  ms/step %.4f"%(d["value"], d["ms_per_step"]))
+except Exception as e:
+    print("COND=1 $ex N=$N: no result", e)
+PY
+done

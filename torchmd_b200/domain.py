@@ -179,7 +179,10 @@ class DecomposedIntegrator:
             try:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # TMD_B200_COND=1: the library edits the graph under capture (conditional node for the
+                # rebuild kernels, body captured from a helper stream) -- relaxed mode permits that
+                mode = "relaxed" if os.environ.get("TMD_B200_COND", "")[:1] == "1" else "global"
+                with torch.cuda.graph(g, capture_error_mode=mode):
                     self._enqueue_step(with_energy, parity)
                 # the capture only records; state was not advanced
             except Exception as err:  # pragma: no cover - depends on the NCCL build
