@@ -203,6 +203,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
   if (SMALLT) {
     static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX <= PAIR_WARPS * 32, "one table entry per thread");
     if (S.AB && (int)threadIdx.x < S.ntypes * S.ntypes) ab_s[threadIdx.x] = S.AB[threadIdx.x];  // no table without an LJ-type term
+    asm volatile("" ::: "memory");  // the table is read back through inline PTX below: keep the stores
     __syncthreads();
   }
 
