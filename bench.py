@@ -159,7 +159,8 @@ def workload_config(ngpus):
         "workload": "synthetic TIP3P water box, 33333 waters = 99999 atoms, L=99.93 A, LJ(switch 7.5)+RF electrostatics cutoff 9 A, "
         "flexible bonds+angles, Langevin 300 K gamma 0.1/ps, dt 1 fs, 1 replica",
         "natoms": 3 * N_WATERS,
-        "pair_kernel": "fixed-point separations (TMD_B200_FX=1)" if os.environ.get("TMD_B200_FX", "")[:1] == "1" else "float separations (default)",
+        "pair_kernel": {"1": "fixed-point separations (TMD_B200_FX=1)", "2": "fixed-point separations + packed fp32x2 arithmetic (TMD_B200_FX=2)"}.get(
+            os.environ.get("TMD_B200_FX", "")[:1], "float separations (default)"),
         "parallelism": "single GPU" if ngpus == 1 else (f"spatial slabs over {ngpus} GPUs, " + ("positions pushed to all ranks over NVLink peer memory by the integration kernel"
                                                    if os.environ.get("TMD_B200_EXCHANGE", "").lower() == "p2p" else "position all-gather")),
         "l2": "no flush between steps: consecutive MD steps are data-dependent; the neighbour list streamed by the "

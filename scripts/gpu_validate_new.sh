@@ -5,13 +5,15 @@
 # 3. A/B bench of the pair kernels, register budgets 6 and 5 CTAs/SM.
 mkdir -p gpurun_out /tmp/var
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/validate_build.log 2>&1
+# 0. do packed fp32x2 operations save issue slots on this GPU? (decides whether k_pair_fx2 can win)
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_f32x2 scripts/ubench_f32x2.cu && /tmp/ubench_f32x2 | tee gpurun_out/ubench_f32x2.txt
 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_suite.log 2>&1; echo "suite rc=$?"
 tail -3 gpurun_out/validate_suite.log
 TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_gpu_zzz_fixedpoint.py -q -s > gpurun_out/validate_fx.log 2>&1; echo "fx rc=$?"
 grep -E "max\|dF\||NVE|passed|failed|Error|error" gpurun_out/validate_fx.log | tail -30
 TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_trajectory.py tests/test_gpu_zzz_p2p.py -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap/autograd/p2p-world1 rc=$?"
 grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
-for fx in 0 1; do
+for fx in 0 1 2; do
   TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx$fx.json 2> gpurun_out/validate_bench_fx$fx.err
   python - <<PY
 import json

@@ -137,6 +137,32 @@ void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const
     iL[k] = 1.0f / box[k];
   }
   for (int e = 0; e < natoms * 3; ++e) forces[e] = 0.f;
+  if (variant == 2) {  // k_pair_fx2: fixed-point separations, two pairs per packed evaluation
+    const SwitchConsts sc = make_switch_consts(pp);
+    for (int q = 0; q < npairs; q += 2) {
+      const int q1 = (q + 1 < npairs) ? q + 1 : q;
+      const int ia[2] = {pairs[2 * q], pairs[2 * q1]}, ja[2] = {pairs[2 * q + 1], pairs[2 * q1 + 1]};
+      F2 w[3];
+      for (int k = 0; k < 3; ++k)
+        w[k] = f2_mul(f2((float)(int32_t)((uint32_t)fx_encode(pos[3 * ia[0] + k], inv[k]) - (uint32_t)fx_encode(pos[3 * ja[0] + k], inv[k])),
+                         (float)(int32_t)((uint32_t)fx_encode(pos[3 * ia[1] + k], inv[k]) - (uint32_t)fx_encode(pos[3 * ja[1] + k], inv[k]))),
+                      f2(unit[k]));
+      const F2 s = f2_fma(w[2], w[2], f2_fma(w[1], w[1], f2_mul(w[0], w[0])));
+      const float* ab0 = AB + 2 * (type[ia[0]] * ntypes + type[ja[0]]);
+      const float* ab1 = AB + 2 * (type[ia[1]] * ntypes + type[ja[1]]);
+      const F2 nqq = f2(-(qs[ia[0]] * qs[ja[0]]), -(qs[ia[1]] * qs[ja[1]]));
+      const F2 nc = pair_coef2(sc, s, nqq, f2(ab0[0], ab1[0]), f2(ab0[1], ab1[1]), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+                               f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)));
+      const float ncs[2] = {nc.x, (q1 == q) ? 0.f : nc.y};
+      for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 3; ++k) {
+          const float wk = h == 0 ? w[k].x : w[k].y;
+          forces[3 * ia[h] + k] += wk * ncs[h];
+          forces[3 * ja[h] + k] -= wk * ncs[h];
+        }
+    }
+    return;
+  }
   for (int q = 0; q < npairs; ++q) {
     const int i = pairs[2 * q], j = pairs[2 * q + 1];
     float w[3], s;
@@ -167,6 +193,25 @@ void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const
       forces[3 * i + k] -= w[k] * cf;
       forces[3 * j + k] += w[k] * cf;
     }
+  }
+}
+
+// packed two-partner coefficient of k_pair_fx2: returns c = (dE/dr)/r for n pairs (n even)
+void hc_pair_coef2(int n, const float* s, const float* qq, const float* A, const float* B, float cutoff,
+                   float switch_dist, float krf, float* c_out) {
+  PairParams pp{};
+  pp.cutoff = cutoff;
+  pp.has_switch = 1;
+  pp.switch_dist = switch_dist;
+  pp.inv_sw_width = 1.0f / (cutoff - switch_dist);
+  pp.two_krf = 2.0f * krf;
+  const SwitchConsts sc = make_switch_consts(pp);
+  for (int k = 0; k + 1 < n; k += 2) {
+    const F2 ss = f2(s[k], s[k + 1]);
+    const F2 nc = pair_coef2(sc, ss, f2(-qq[k], -qq[k + 1]), f2(A[k], A[k + 1]), f2(B[k], B[k + 1]),
+                             f2(rsqrt_seed(ss.x), rsqrt_seed(ss.y)), f2(neg_rcp_seed(ss.x), neg_rcp_seed(ss.y)));
+    c_out[k] = -nc.x;
+    c_out[k + 1] = -nc.y;
   }
 }
 

@@ -28,10 +28,12 @@ PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water
 
 
 def make_forces(g, fx, **kw):
+    """fx: 0 float kernel, 1 fixed-point kernel, 2 fixed-point + packed fp32x2 arithmetic (k_pair_fx2,
+    used for force-only passes of the LJ+switch+RF term set; other passes take the fixed-point kernel)."""
     from torchmd_b200 import Forces
 
     old = os.environ.get("TMD_B200_FX")
-    os.environ["TMD_B200_FX"] = "1" if fx else "0"
+    os.environ["TMD_B200_FX"] = str(int(fx))
     try:
         par = params_from_golden(g, precision=torch.float32, device=DEV)
         f = Forces(par, terms=[str(t) for t in g["terms"]], **golden_cfg(g), **kw)
@@ -46,11 +48,21 @@ def make_forces(g, fx, **kw):
     return f, pos, box, F, E
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", PERIODIC_CASES)
-def test_fixed_point_kernel_matches_golden(name):
+def test_fixed_point_kernel_matches_golden(name, mode):
     g = load_golden(name)
-    f, pos, box, F, E = make_forces(g, True)
-    f0, _, _, F0, E0 = make_forces(g, False)
+    f, pos, box, F, E = make_forces(g, mode)
+    f0, _, _, F0, E0 = make_forces(g, 0)
+    if mode == 2:  # the packed kernel runs when no energies are requested: a force-only pass
+        os.environ["TMD_B200_FX"] = "2"
+        try:
+            from torchmd_b200 import _lib
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().tmd_forces(f._ctx, pos.data_ptr(), F.data_ptr(), None, stream))
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("TMD_B200_FX", None)
     ref = g["forces_f64"]
     scale = max(1.0, float(np.abs(ref).max()) / 100.0)
     err = np.abs(F.cpu().numpy().astype(np.float64) - ref).max()
@@ -67,9 +79,10 @@ def test_fixed_point_kernel_matches_golden(name):
     if "pairs_f32" in g:
         assert np.array_equal(f.neighbour_pairs(pos, box).cpu().numpy(), g["pairs_f32"])
     # deterministic
-    F1 = F.clone()
-    f.compute(pos, box, F)
-    assert torch.equal(F, F1)
+    if mode == 1:
+        F1 = F.clone()
+        f.compute(pos, box, F)
+        assert torch.equal(F, F1)
 
 
 def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
@@ -93,17 +106,22 @@ def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
     of32 = refmd.OracleForces(params_from_golden(g, precision=torch.float32), terms, **cfg)
     pairs_ref = of32.neighbour_pairs(pos_c[0], torch.tensor(g["box"])).numpy().astype(np.int32)
 
-    os.environ["TMD_B200_FX"] = "1"
-    try:
-        f = Forces(params_from_golden(g, precision=torch.float32, device=DEV), terms=terms, **cfg)
-        pos, bx = pos_c.to(DEV), box_c.to(DEV)
-        F = torch.zeros_like(pos)
-        f.compute(pos, bx, F)
-    finally:
-        os.environ.pop("TMD_B200_FX", None)
-    err = (F.cpu().double() - f64).abs().max().item()
-    print(f"drifted molecules: max|dF| vs fp64 oracle {err:.3e}")
-    assert err < 1e-4
+    for mode in ("1", "2"):
+        os.environ["TMD_B200_FX"] = mode
+        try:
+            f = Forces(params_from_golden(g, precision=torch.float32, device=DEV), terms=terms, **cfg)
+            pos, bx = pos_c.to(DEV), box_c.to(DEV)
+            F = torch.zeros_like(pos)
+            f.compute(pos, bx, F)
+            if mode == "2":  # force-only pass -> packed kernel
+                from torchmd_b200 import _lib
+                _lib.check(_lib.lib().tmd_forces(f._ctx, pos.data_ptr(), F.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+                torch.cuda.synchronize()
+        finally:
+            os.environ.pop("TMD_B200_FX", None)
+        err = (F.cpu().double() - f64).abs().max().item()
+        print(f"drifted molecules, TMD_B200_FX={mode}: max|dF| vs fp64 oracle {err:.3e}")
+        assert err < 1e-4
     assert np.array_equal(f.neighbour_pairs(pos, bx).cpu().numpy(), pairs_ref)
 
 
@@ -115,8 +133,8 @@ def test_fixed_point_trajectory_tracks_float_kernel():
     g = load_golden("water999_eq")
     cfg = golden_cfg(g)
     out = []
-    for fx in (False, True):
-        os.environ["TMD_B200_FX"] = "1" if fx else "0"
+    for fx in (0, 1, 2):
+        os.environ["TMD_B200_FX"] = str(fx)
         try:
             par = params_from_golden(g, precision=torch.float32, device=DEV)
             s = System(len(g["coords"]), 1, torch.float32, DEV)
@@ -129,7 +147,8 @@ def test_fixed_point_trajectory_tracks_float_kernel():
             out.append((s.pos.cpu().clone(), float(ek[0]), float(ep[0])))
         finally:
             os.environ.pop("TMD_B200_FX", None)
-    dp = (out[0][0] - out[1][0]).abs().max().item()
-    print(f"NVE 100 steps: max |dpos| fixed-point vs float kernel {dp:.3e}; Epot {out[0][2]:.4f} / {out[1][2]:.4f}")
-    assert dp < 5e-3
-    assert abs(out[0][2] - out[1][2]) < 0.05
+    for k in (1, 2):
+        dp = (out[0][0] - out[k][0]).abs().max().item()
+        print(f"NVE 100 steps: max |dpos| TMD_B200_FX={k} vs float kernel {dp:.3e}; Epot {out[0][2]:.4f} / {out[k][2]:.4f}")
+        assert dp < 5e-3
+        assert abs(out[0][2] - out[k][2]) < 0.05

@@ -275,12 +275,41 @@ def test_fx_pair_forces_meet_the_tolerance(hc, drift):
     krf = (1 / rc**3) * (eps - 1) / (2 * eps + 1)
     crf = (1 / rc) * (3 * eps) / (2 * eps + 1)
     errs = []
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         out = np.zeros((len(pos), 3), F32)
         hc.hc_pair_forces(variant, len(pos), len(pairs), p(np.ascontiguousarray(pairs)), p(pos), p(qs), p(types), nt,
                           p(np.ascontiguousarray(AB)), p(box), (1 << 5) | (1 << 6), C.c_float(rc), 1,
                           C.c_float(cfg["switch_dist"]), 1, C.c_float(krf), C.c_float(crf), p(out))
         errs.append(np.abs(out.astype(np.float64) - f64[0].numpy()).max())
-    print(f"max |dF| vs fp64 oracle: float path {errs[0]:.2e}, fixed-point path {errs[1]:.2e} (drift={drift})")
-    assert errs[1] < 1e-4
+    print(f"max |dF| vs fp64 oracle: float path {errs[0]:.2e}, fixed-point path {errs[1]:.2e}, "
+          f"fixed-point + packed arithmetic {errs[2]:.2e} (drift={drift})")
+    assert errs[1] < 1e-4 and errs[2] < 1e-4
     assert errs[1] <= errs[0] * 1.25 + 5e-6
+    assert errs[2] <= errs[1] * 1.25 + 5e-6
+
+
+def test_packed_two_partner_coefficient_matches_oracle(hc):
+    """physics.cuh pair_coef2 (k_pair_fx2): LJ with switch + reaction field, explicit-force
+    convention, two partners per packed evaluation."""
+    rng = np.random.default_rng(8)
+    n, cutoff, switch, eps = 40000, 9.0, 7.5, 78.5
+    r = rng.uniform(1.6, cutoff, n)
+    s = (r * r).astype(F32)
+    qq = (refmd.COULOMB * rng.uniform(-1, 1, n) * rng.uniform(-1, 1, n)).astype(F32)
+    A = rng.uniform(1e4, 6e5, n).astype(F32)
+    B = rng.uniform(10, 600, n).astype(F32)
+    krf = (1 / cutoff**3) * (eps - 1) / (2 * eps + 1)
+    out = np.zeros(n, F32)
+    hc.hc_pair_coef2(n, p(s), p(qq), p(A), p(B), C.c_float(cutoff), C.c_float(switch), C.c_float(krf), p(out))
+    dist = torch.tensor(np.sqrt(s.astype(np.float64)))
+    _, lj_f = refmd.lj_pair(dist, torch.tensor(A.astype(np.float64)), torch.tensor(B.astype(np.float64)), 1, switch, cutoff)
+    _, el_f = refmd.coulomb_pair(dist, torch.tensor(qq.astype(np.float64) / refmd.COULOMB), torch.ones(n, dtype=torch.float64), 1, cutoff, True, eps)
+    want = ((lj_f + el_f) / dist).numpy()
+    assert np.abs(out - want).max() <= 4e-6 * max(1.0, np.abs(want).max())
+    # and agrees with the scalar kernel arithmetic (pair_terms<1>) to rounding
+    o5 = [np.zeros(n, F32) for _ in range(5)]
+    crf = (1 / cutoff) * (3 * eps) / (2 * eps + 1)
+    hc.hc_pair_terms(n, p(s), p(qq), p(A), p(B), (1 << 5) | (1 << 6), 1, C.c_float(cutoff), 1, C.c_float(switch), 1,
+                     C.c_float(krf), C.c_float(crf), *[p(o) for o in o5])
+    scalar = o5[4].astype(np.float64) / np.sqrt(s.astype(np.float64))
+    assert np.abs(out - scalar).max() <= 4e-6 * max(1.0, np.abs(scalar).max())

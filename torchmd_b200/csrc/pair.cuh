@@ -328,4 +328,131 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
   }
 }
 
+// ---- fixed-point separations + packed fp32x2 arithmetic ------------------------------------
+// k_pair_fx for the production term set (LJ with switch + reaction-field Coulomb, forces only,
+// <= 16 atom types) with the two list entries a lane handles per iteration evaluated TOGETHER
+// in packed fp32x2 operations (physics.cuh, pair_coef2): the kernel is issue-bound, a packed
+// operation costs one issue slot for two results.  Decisions, band handling and list layout are
+// those of k_pair_fx; a partner that is not taken contributes through a zeroed coefficient.
+static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in the shared-memory loads of k_pair_fx2");
+#ifndef PAIR_FX2_MINBLOCKS
+#define PAIR_FX2_MINBLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
+k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
+  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int kk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  const int N = S.natoms;
+  const size_t base = (size_t)r * N;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
+
+  // LJ table staged as two planes (A, B): the packed operands (A_0, A_1), (B_0, B_1) of the two
+  // partners are then loaded straight into register pairs
+  __shared__ float ab_s[2 * FX_SMALLT_MAX * FX_SMALLT_MAX];
+  if ((int)threadIdx.x < S.ntypes * S.ntypes) {
+    const float2 v = S.AB[threadIdx.x];
+    ab_s[threadIdx.x] = v.x;
+    ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
+  }
+  asm volatile("" ::: "memory");
+  __syncthreads();
+  if (kk >= S.own_n) return;
+
+  const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
+  const int4* __restrict__ xf = S.xf_s + (size_t)r * (N + 1);
+  unsigned long long xf_base = reinterpret_cast<unsigned long long>(xf);
+  asm volatile("" : "+l"(xf_base));
+  const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+  const int n = S.nnbr[base + k];
+  const int4 pi = xf[k];
+  const float nqi = -__int_as_float(pi.w);
+  const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)(S.type_s[base + k] * S.ntypes) * 4u;
+  const Grid* g = S.grid + r;
+  const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
+  const float margin = fmaf(g->fx_c1, __int_as_float(S.flags[r * F_COUNT + F_PMAX]), g->fx_c0);
+  const float s_hi = S.pp.s_max + margin, s_lo = S.pp.s_max - margin;
+  F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);  // the two halves are added at the end
+  float s_skipped = INFINITY;
+
+  int e = lane;
+  int j0 = (e < n) ? __ldcs(row + e) : -1;
+  int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+  while (e < n) {
+    const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+    const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    const bool v0 = j0 >= 0, v1 = j1 >= 0;
+    const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;  // an empty slot reads record 0 and is masked
+    const int4 p0 = fx_record(xf_base, (en0 << 4) & 0x0ffffff0u);
+    const int4 p1 = fx_record(xf_base, (en1 << 4) & 0x0ffffff0u);
+    const F2 wx = f2_mul(f2((float)(int)((unsigned)pi.x - (unsigned)p0.x), (float)(int)((unsigned)pi.x - (unsigned)p1.x)), ux);
+    const F2 wy = f2_mul(f2((float)(int)((unsigned)pi.y - (unsigned)p0.y), (float)(int)((unsigned)pi.y - (unsigned)p1.y)), uy);
+    const F2 wz = f2_mul(f2((float)(int)((unsigned)pi.z - (unsigned)p0.z), (float)(int)((unsigned)pi.z - (unsigned)p1.z)), uz);
+    const F2 s = f2_fma(wz, wz, f2_fma(wy, wy, f2_mul(wx, wx)));
+    const bool in0 = v0 && s.x < s_lo, in1 = v1 && s.y < s_lo;
+    if (v0 && !in0) s_skipped = fminf(s_skipped, s.x);
+    if (v1 && !in1) s_skipped = fminf(s_skipped, s.y);
+    if (in0 || in1) {
+      float2 ab0, ab1;  // (A,B) of partner 0 / partner 1
+      {
+        const unsigned a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
+        asm("ld.shared.f32 %0, [%1];" : "=f"(ab0.x) : "r"(a0));
+        asm("ld.shared.f32 %0, [%1];" : "=f"(ab1.x) : "r"(a1));
+        asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab0.y) : "r"(a0));
+        asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab1.y) : "r"(a1));
+      }
+      const F2 nqq = f2_mul(f2(nqi), f2(__int_as_float(p0.w), __int_as_float(p1.w)));
+      F2 nc = pair_coef2(sc, s, nqq, f2(ab0.x, ab1.x), f2(ab0.y, ab1.y), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+                         f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)));
+      nc = f2(in0 ? nc.x : 0.f, in1 ? nc.y : 0.f);  // a select, not a product: the other half may hold inf/NaN
+      FX = f2_fma(wx, nc, FX);
+      FY = f2_fma(wy, nc, FY);
+      FZ = f2_fma(wz, nc, FZ);
+    }
+    j0 = jn0;
+    j1 = jn1;
+    e += 64;
+  }
+  float fx = FX.x + FX.y, fy = FY.x + FY.y, fz = FZ.x + FZ.y;
+  if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
+    // pairs inside the decision band: the reference's own decision, scalar arithmetic
+    const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
+    const PairParams pp = S.pp;
+    const float qi = -nqi;
+    float e_el = 0.f, e_lj = 0.f, e_rep = 0.f, e_cg = 0.f;
+    for (int eb = lane; eb < n; eb += 32) {
+      const int entry = row[eb];
+      const int j = entry & 0xffffff;
+      const int4 pj = xf[j];
+      const float wx = fx_delta(pi.x, pj.x, ux.x), wy = fx_delta(pi.y, pj.y, uy.x), wz = fx_delta(pi.z, pj.z, uz.x);
+      const float s = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+      if (!(s < s_lo) && s <= s_hi) {
+        const float4 a = xq[k], b = xq[j];
+        if (ref_inside(a.x, a.y, a.z, b.x, b.y, b.z, g->L[0], g->L[1], g->L[2], g->invL[0], g->invL[1], g->invL[2],
+                       pp.s_max)) {
+          float2 ab;
+          asm("ld.shared.f32 %0, [%1];" : "=f"(ab.x) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
+          asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab.y) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
+          float rinv;
+          const float dedr = pair_terms<1>(pp, s, qi * __int_as_float(pj.w), ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
+          const float c = dedr * rinv;
+          fx -= wx * c;
+          fy -= wy * c;
+          fz -= wz * c;
+        }
+      }
+    }
+  }
+  fx = warp_sum(fx);
+  fy = warp_sum(fy);
+  fz = warp_sum(fz);
+  if (lane == 0) {
+    float* f = forces + (base + S.perm[base + k]) * 3;
+    f[0] = fx;
+    f[1] = fy;
+    f[2] = fz;
+  }
+}
+
 }  // namespace tmd

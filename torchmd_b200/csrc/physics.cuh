@@ -305,6 +305,106 @@ TMD_HD float pair_terms(const PairParams& pp, float s, float qq, float A, float 
   return dedr;
 }
 
+// ---- two partners at once: packed fp32x2 arithmetic ---------------------------------------
+// Blackwell (sm_100) has packed single-precision instructions (FFMA2 / FMUL2 / FADD2: two
+// IEEE fp32 operations per lane and instruction, PTX fma.rn.f32x2 ...).  The pair kernel is
+// bound by instruction issue, not by the FP32 datapath, so evaluating the partners a lane
+// handles two at a time halves the issue slots of the arithmetic.  Each half of a packed
+// operation is the ordinary correctly rounded operation, so the host build (fmaf per half)
+// reproduces the device results exactly apart from the two hardware approximations that seed
+// the Newton steps.
+struct F2 {
+  float x, y;
+};
+TMD_HD F2 f2(float a, float b) { return F2{a, b}; }
+TMD_HD F2 f2(float a) { return F2{a, a}; }
+TMD_HD F2 f2_fma(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return F2{r.x, r.y};
+#else
+  return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+}
+TMD_HD F2 f2_mul(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return F2{r.x, r.y};
+#else
+  return F2{mul_rn(a.x, b.x), mul_rn(a.y, b.y)};
+#endif
+}
+TMD_HD F2 f2_add(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return F2{r.x, r.y};
+#else
+  return F2{add_rn(a.x, b.x), add_rn(a.y, b.y)};
+#endif
+}
+// hardware seeds of the Newton steps: 1/sqrt(s) and -1/s (the sign saves every negation below)
+TMD_HD float rsqrt_seed(float s) { return rsqrt_fast(s); }
+TMD_HD float neg_rcp_seed(float s) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-s));
+  return y;
+#else
+  return -1.0f / s;
+#endif
+}
+
+// Uniform constants of pair_coef2 (host-built once per PairParams).
+struct SwitchConsts {
+  float neg_switch_dist, inv_sw_width;
+  float d1, d2, d3;  // -ds/dr polynomial: t^2 (d3 + t (d2 + t d1)),  d = (30, -60, 30) / (cutoff - switch_dist)
+  float two_krf;
+};
+inline SwitchConsts make_switch_consts(const PairParams& pp) {
+  SwitchConsts c;
+  c.neg_switch_dist = -pp.switch_dist;
+  c.inv_sw_width = pp.inv_sw_width;
+  c.d1 = 30.0f * pp.inv_sw_width;
+  c.d2 = -60.0f * pp.inv_sw_width;
+  c.d3 = 30.0f * pp.inv_sw_width;
+  c.two_krf = pp.two_krf;
+  return c;
+}
+
+// MINUS the force coefficient (dE/dr)/r of two partners for LJ with switch + reaction-field
+// Coulomb in the explicit-force convention (pair_terms<1> restated with packed operations and
+// signs arranged so that no negation is ever needed):
+//   s    squared distances          nqq  -(k_e q_i q_j)             A, B  LJ table entries
+//   y    rsqrt_seed(s)              nz   neg_rcp_seed(s)
+// The force on atom i is then  F_i += w * result.
+TMD_HD F2 pair_coef2(const SwitchConsts& c, F2 s, F2 nqq, F2 A, F2 B, F2 y, F2 nz) {
+  // 1/r to ~1 ulp and r
+  const F2 t = f2_mul(s, y);
+  const F2 u = f2_fma(f2_mul(t, f2(-0.5f)), y, f2(0.5f));
+  const F2 rinv = f2_fma(y, u, y);
+  const F2 r = f2_mul(s, rinv);
+  // -1/r^2 to ~0.5 ulp:  nz (1 + (1 + s nz))
+  const F2 e1 = f2_fma(s, nz, f2(1.0f));
+  const F2 nr2 = f2_fma(nz, e1, nz);
+  const F2 nr6 = f2_mul(f2_mul(nr2, nr2), nr2);  // -1/r^6
+  const F2 a12 = f2_mul(f2_mul(A, nr6), nr6);    //  A/r^12
+  const F2 nb6 = f2_mul(B, nr6);                 // -B/r^6
+  const F2 e = f2_add(a12, nb6);                 //  E_lj
+  // -(dE/dr) of the unswitched LJ: (12 a12 - 6 b6) / r
+  const F2 nf = f2_mul(f2_fma(nb6, f2(6.0f), f2_mul(a12, f2(12.0f))), rinv);
+  // switch: t = max((r - r_s) / (r_c - r_s), 0), sw = 1 + t^3 (-10 + t (15 - 6 t)), -ds/dr
+  F2 tt = f2_mul(f2_add(r, f2(c.neg_switch_dist)), f2(c.inv_sw_width));
+  tt = f2(fmaxf(tt.x, 0.0f), fmaxf(tt.y, 0.0f));
+  const F2 t2 = f2_mul(tt, tt);
+  const F2 sw = f2_fma(f2_mul(t2, tt), f2_fma(tt, f2_fma(tt, f2(-6.0f), f2(15.0f)), f2(-10.0f)), f2(1.0f));
+  const F2 ndsw = f2_mul(t2, f2_fma(tt, f2_fma(tt, f2(c.d1), f2(c.d2)), f2(c.d3)));
+  // -(s dE/dr + E s'/r)   (the reference's explicit formula, forces.py:410-412)
+  const F2 nfsw = f2_fma(sw, nf, f2_mul(f2_mul(e, ndsw), rinv));
+  // reaction field: dE/dr = qq (2 k_rf r - 1/r^2)
+  const F2 ndedr = f2_fma(nqq, f2_fma(f2(c.two_krf), r, nr2), nfsw);
+  return f2_mul(ndedr, rinv);
+}
+
 // ---- bonded terms --------------------------------------------------------------------
 // Templated on the real type: the bonded kernel evaluates them in fp64 (they are O(N),
 // a few percent of the pair work, and a stiff bond turns the 6e-8 A rounding of an fp32

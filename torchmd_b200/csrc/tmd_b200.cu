@@ -439,7 +439,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   d.xf_s = nullptr;
   {
     const char* env = getenv("TMD_B200_FX");
-    if (env && env[0] == '1' && ctx->safe_image && ctx->pair_mask) {
+    ctx->fx_packed = env && env[0] == '2';
+    if (env && (env[0] == '1' || env[0] == '2') && ctx->safe_image && ctx->pair_mask) {
       const size_t n = (size_t)R * N + R;
       if ((rc = device_alloc(&ctx->xf_buf, n))) return rc;
       TMD_CUDA(cudaMemset(ctx->xf_buf, 0, n * sizeof(int4)));
@@ -597,6 +598,10 @@ template <bool E>
 static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
   const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
   const int th = PAIR_WARPS * 32;
+  if (!E && ctx->fx_packed && ctx->pair_mode == 1 && small) {  // TMD_B200_FX=2: packed fp32x2 arithmetic
+    k_pair_fx2<<<pg, th, 0, st>>>(ctx->d, make_switch_consts(ctx->d.pp), forces);
+    return;
+  }
   if (ctx->pair_mode == 1) {
     if (small) k_pair_fx<E, 1, true><<<pg, th, 0, st>>>(ctx->d, forces, energies);
     else k_pair_fx<E, 1, false><<<pg, th, 0, st>>>(ctx->d, forces, energies);
