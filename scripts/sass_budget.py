@@ -62,11 +62,12 @@ def summarise(name, ins, res):
     body = [t for _, t in ins[loop[0] : loop[1] + 1]]
     npairs = sum("LDG.E.128" in t for t in body)
     mufu = sum(t.startswith("MUFU") for t in body)
+    packed = sum(any(p in t for p in ("FFMA2", "FMUL2", "FADD2")) for t in body)
     spill = sum(("STL" in t or "LDL" in t) for t in body)
     total = len(body)
     r = res.get(name, (0, 0, 0))
     print(f"{name}\n  registers {r[0]}, stack {r[1]} B, static smem {r[2]} B; main loop {total} instructions for {npairs} list entries per lane"
-          f" = {total / npairs:.1f} per entry (MUFU {mufu // npairs} per entry, local-memory ops in the loop: {spill})")
+          f" = {total / npairs:.1f} per entry (MUFU {mufu // npairs} per entry, packed fp32x2 instructions {packed}, local-memory ops in the loop: {spill})")
 
 
 def main():
@@ -74,10 +75,10 @@ def main():
     print("Static SASS budget of the pair kernels (cuobjdump of torchmd_b200/libtmd_b200.so, sm_100a; no GPU involved).")
     print("Every lane executes the whole loop body when any lane of its warp has an in-cutoff partner, so the per-entry count is")
     print("the warp-level issue cost per list slot.  k_pair = float separations (default, measured 160 us at 99,999 atoms);")
-    print("k_pair_fx = fixed-point separations (opt-in, not yet measured).  Template args: <ENERGY, PERIODIC, SAFE, MODE> and")
+    print("k_pair_fx = fixed-point separations, k_pair_fx2 = the same with packed fp32x2 arithmetic (both opt-in, not yet measured).  Template args: <ENERGY, PERIODIC, SAFE, MODE> and")
     print("<ENERGY, MODE, SMALLT>.\n")
     for name in sorted(table):
-        if "k_pair" in name and ("ILb0E" in name):
+        if "k_pair" in name and ("ILb0E" in name or "k_pair_fx2" in name):
             summarise(name, table[name], res)
 
 
