@@ -32,6 +32,17 @@ print("FX=1, $mb CTAs/SM, $un entries/lane/iteration: steps/s %.0f  ms/step %.4f
 PY
 done
 # 4. list build with chunk culling (-DBT_CULL=1): whole GPU suite + bench against the variant library
+# 3b. packed kernel: register budget / unroll variants
+for cfg in "5 1" "4 2" "3 2"; do
+  set -- $cfg; mb=$1; un=$2
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DPAIR_FX2_MINBLOCKS=$mb -DPAIR_FX2_UNROLL=$un -o /tmp/var/lib_fx2_${mb}_$un.so torchmd_b200/csrc/tmd_b200.cu
+  TMD_B200_LIB=/tmp/var/lib_fx2_${mb}_$un.so TMD_B200_FX=2 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx2_${mb}_$un.json 2> gpurun_out/validate_bench_fx2_${mb}_$un.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/validate_bench_fx2_${mb}_$un.json"))
+print("FX=2, $mb CTAs/SM, $un packed evaluations/iteration: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
+PY
+done
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
 TMD_B200_LIB=/tmp/var/lib_cull.so timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_cull_suite.log 2>&1; echo "cull suite rc=$?"
 tail -3 gpurun_out/validate_cull_suite.log

@@ -338,6 +338,9 @@ static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in t
 #ifndef PAIR_FX2_MINBLOCKS
 #define PAIR_FX2_MINBLOCKS 4
 #endif
+#ifndef PAIR_FX2_UNROLL
+#define PAIR_FX2_UNROLL 1  // packed evaluations (pairs of list entries) per lane and loop iteration: 1 or 2
+#endif
 
 __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
 k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
@@ -376,12 +379,8 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
   F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);  // the two halves are added at the end
   float s_skipped = INFINITY;
 
-  int e = lane;
-  int j0 = (e < n) ? __ldcs(row + e) : -1;
-  int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
-  while (e < n) {
-    const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-    const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+  // two list entries evaluated together
+  auto pair2 = [&](int j0, int j1) {
     const bool v0 = j0 >= 0, v1 = j1 >= 0;
     const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;  // an empty slot reads record 0 and is masked
     const int4 p0 = fx_record(xf_base, (en0 << 4) & 0x0ffffff0u);
@@ -410,10 +409,43 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
       FY = f2_fma(wy, nc, FY);
       FZ = f2_fma(wz, nc, FZ);
     }
-    j0 = jn0;
-    j1 = jn1;
-    e += 64;
+  };
+#if PAIR_FX2_UNROLL == 2
+  {  // tuning variant: two packed evaluations (four list entries) per iteration
+    int e = lane;
+    int j0 = (e < n) ? __ldcs(row + e) : -1;
+    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    int j2 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+    int j3 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    while (e < n) {
+      const int jn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
+      const int jn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
+      const int jn2 = (e + 192 < n) ? __ldcs(row + e + 192) : -1;
+      const int jn3 = (e + 224 < n) ? __ldcs(row + e + 224) : -1;
+      pair2(j0, j1);
+      pair2(j2, j3);
+      j0 = jn0;
+      j1 = jn1;
+      j2 = jn2;
+      j3 = jn3;
+      e += 128;
+    }
   }
+#else
+  {
+    int e = lane;
+    int j0 = (e < n) ? __ldcs(row + e) : -1;
+    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    while (e < n) {
+      const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+      const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+      pair2(j0, j1);
+      j0 = jn0;
+      j1 = jn1;
+      e += 64;
+    }
+  }
+#endif
   float fx = FX.x + FX.y, fy = FY.x + FY.y, fz = FZ.x + FZ.y;
   if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
     // pairs inside the decision band: the reference's own decision, scalar arithmetic
