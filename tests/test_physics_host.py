@@ -313,3 +313,21 @@ def test_packed_two_partner_coefficient_matches_oracle(hc):
                      C.c_float(krf), C.c_float(crf), *[p(o) for o in o5])
     scalar = o5[4].astype(np.float64) / np.sqrt(s.astype(np.float64))
     assert np.abs(out - scalar).max() <= 4e-6 * max(1.0, np.abs(scalar).max())
+
+
+@pytest.mark.parametrize("scale", [1, 50, 1900])
+def test_fx_decision_bound_holds_far_from_the_origin(hc, scale):
+    """The margin grows with the largest |coordinate| (the reference's own rounding of p_i - p_j and
+    L*n does): the bound must hold and the classification stay sound up to the 2000-box limit."""
+    rng = np.random.default_rng(1)
+    box = np.array([99.93, 87.41, 120.07], F32)
+    n = 100000
+    pi = (rng.uniform(-scale, scale, (n, 3)) * box).astype(F32)
+    d = rng.normal(size=(n, 3))
+    d *= (rng.uniform(8.95, 9.05, n) / np.linalg.norm(d, axis=1))[:, None]
+    pj = (pi.astype(np.float64) - d + rng.integers(-3, 4, (n, 3)) * box.astype(np.float64)).astype(F32)
+    pmax = float(max(np.abs(pi).max(), np.abs(pj).max()))
+    _, s, cls, margin = fx_decide(hc, pi, pj, box, 9.0, 11.0, pmax)
+    _, sref, inside = decide(hc, pi, pj, box, 9.0)
+    assert np.abs(s - sref).max() <= margin
+    assert ((cls == 2) | ((cls == 1) == inside)).all()
