@@ -1,80 +1,79 @@
 #!/bin/bash
-# Round-2 opener: run everything that was written after round 1's GPU budget was spent.
-#   gpurun --timeout 900 -- 'bash scripts/gpu_validate_new.sh'
-# 1. the standing GPU suite (must stay green), 2. the gated tests of the new code paths,
-# 3. A/B bench of the pair kernels, register budgets 6 and 5 CTAs/SM.
+# Round-2 opener: run everything that was written after round 1's GPU budget was spent (DESIGN.md 4b).
+#   gpurun --timeout 1700 -- 'bash scripts/gpu_validate_new.sh'            all sections (~25-30 min of box time)
+#   gpurun --timeout 700  -- 'bash scripts/gpu_validate_new.sh 0 1 2'      only the named sections
+# Sections:
+#   0  FFMA2 issue microbenchmark              1  standing GPU suite (default switches; must stay green)
+#   2  gated tests of the new code paths        3  pair kernels: A/B bench TMD_B200_FX=0/1/2 + register/unroll variants
+#   4  list build with chunk culling            5  bonded kernel overlapped on a second stream
+#   6  captured step + conditional-node rebuild on one GPU
 mkdir -p gpurun_out /tmp/var
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/validate_build.log 2>&1
-# 0. do packed fp32x2 operations save issue slots on this GPU? (decides whether k_pair_fx2 can win)
-nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_f32x2 scripts/ubench_f32x2.cu && /tmp/ubench_f32x2 | tee gpurun_out/ubench_f32x2.txt
-timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_suite.log 2>&1; echo "suite rc=$?"
-tail -3 gpurun_out/validate_suite.log
-TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_gpu_zzz_fixedpoint.py -q -s > gpurun_out/validate_fx.log 2>&1; echo "fx rc=$?"
-grep -E "max\|dF\||NVE|passed|failed|Error|error" gpurun_out/validate_fx.log | tail -30
-TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_trajectory.py tests/test_gpu_zzz_p2p.py -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap/autograd/p2p-world1 rc=$?"
-grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
-for fx in 0 1 2; do
-  TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx$fx.json 2> gpurun_out/validate_bench_fx$fx.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_fx$fx.json"))
-print("FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f frac %.4f T %.0f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["roofline"]["frac"], d["state"]["temperature_K"]))
+SECTIONS="${*:-0 1 2 3 4 5 6}"
+has() { [[ " $SECTIONS " == *" $1 "* ]]; }
+NVCC="nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
+BENCH="python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10"
+
+bench_line() {  # label, json file
+  python - "$1" "$2" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[2]))
+    print("%-46s steps/s %6.0f  ms/step %.4f  pair_ms %.4f  frac %.4f  launches %d  T %.0f" % (
+        sys.argv[1], d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["roofline"]["frac"], d["gpu_launches"], d["state"]["temperature_K"]))
+except Exception as e:
+    print("%-46s no result (%s) -- see %s" % (sys.argv[1], e, sys.argv[2].replace(".json", ".err")))
 PY
-done
-for cfg in "5 2" "6 4" "5 4"; do
-  set -- $cfg; mb=$1; un=$2
-  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DPAIR_FX_MINBLOCKS=$mb -DPAIR_FX_UNROLL=$un -o /tmp/var/lib_fx_${mb}_$un.so torchmd_b200/csrc/tmd_b200.cu
-  TMD_B200_LIB=/tmp/var/lib_fx_${mb}_$un.so TMD_B200_FX=1 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx_${mb}_$un.json 2> gpurun_out/validate_bench_fx_${mb}_$un.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_fx_${mb}_$un.json"))
-print("FX=1, $mb CTAs/SM, $un entries/lane/iteration: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
-PY
-done
-# 4. list build with chunk culling (-DBT_CULL=1): whole GPU suite + bench against the variant library
-# 3b. packed kernel: register budget / unroll variants
-for cfg in "5 1" "4 2" "3 2"; do
-  set -- $cfg; mb=$1; un=$2
-  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DPAIR_FX2_MINBLOCKS=$mb -DPAIR_FX2_UNROLL=$un -o /tmp/var/lib_fx2_${mb}_$un.so torchmd_b200/csrc/tmd_b200.cu
-  TMD_B200_LIB=/tmp/var/lib_fx2_${mb}_$un.so TMD_B200_FX=2 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_fx2_${mb}_$un.json 2> gpurun_out/validate_bench_fx2_${mb}_$un.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_fx2_${mb}_$un.json"))
-print("FX=2, $mb CTAs/SM, $un packed evaluations/iteration: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
-PY
-done
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
-TMD_B200_LIB=/tmp/var/lib_cull.so timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_cull_suite.log 2>&1; echo "cull suite rc=$?"
-tail -3 gpurun_out/validate_cull_suite.log
-for fx in 0 1; do
-  TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_cull_fx$fx.json 2> gpurun_out/validate_bench_cull_fx$fx.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_cull_fx$fx.json"))
-print("CULL=1 FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
-PY
-done
-# 5. bonded kernel overlapped with the pair kernel on a second stream (TMD_B200_OVERLAP=1): suite + bench
-TMD_B200_OVERLAP=1 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_overlap_suite.log 2>&1; echo "overlap suite rc=$?"
-tail -3 gpurun_out/validate_overlap_suite.log
-for cfg in "0 0" "1 0" "1 1"; do
-  set -- $cfg; fx=$1; cull=$2
-  lib=torchmd_b200/libtmd_b200.so; [ "$cull" = 1 ] && lib=/tmp/var/lib_cull.so
-  TMD_B200_LIB=$lib TMD_B200_FX=$fx TMD_B200_OVERLAP=1 timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_ov_${fx}_$cull.json 2> gpurun_out/validate_bench_ov_${fx}_$cull.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_ov_${fx}_$cull.json"))
-print("OVERLAP=1 FX=$fx CULL=$cull: steps/s %.0f  ms/step %.4f pair_ms %.4f"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"]))
-PY
-done
-# 6. single-GPU step as a replayed CUDA graph with the rebuild in a conditional node (TMD_B200_GRAPH=1)
-TMD_B200_GRAPH=1 timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_graph_suite.log 2>&1; echo "graph suite rc=$?"
-tail -3 gpurun_out/validate_graph_suite.log
-for fx in 0 1; do
-  TMD_B200_GRAPH=1 TMD_B200_FX=$fx timeout -s KILL 200 python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10 > gpurun_out/validate_bench_graph_fx$fx.json 2> gpurun_out/validate_bench_graph_fx$fx.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/validate_bench_graph_fx$fx.json"))
-print("GRAPH=1 FX=$fx: steps/s %.0f  ms/step %.4f pair_ms %.4f launches %d"%(d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["gpu_launches"]))
-PY
-done
+}
+run_bench() {  # label, tag, then environment assignments
+  local label="$1" tag="$2"; shift 2
+  env "$@" timeout -s KILL 240 $BENCH > gpurun_out/validate_bench_$tag.json 2> gpurun_out/validate_bench_$tag.err
+  bench_line "$label" gpurun_out/validate_bench_$tag.json
+}
+run_suite() {  # tag, then environment assignments
+  local tag="$1"; shift
+  env "$@" timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/validate_suite_$tag.log 2>&1
+  echo "suite [$tag] rc=$? : $(tail -1 gpurun_out/validate_suite_$tag.log)"
+}
+
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/validate_build.log 2>&1 || { echo "build failed"; tail -5 gpurun_out/validate_build.log; exit 1; }
+
+if has 0; then
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_f32x2 scripts/ubench_f32x2.cu && /tmp/ubench_f32x2 | tee gpurun_out/ubench_f32x2.txt
+fi
+if has 1; then
+  run_suite default TMD_B200_VALIDATE=0
+fi
+if has 2; then
+  TMD_B200_VALIDATE=1 timeout -s KILL 500 python -m pytest tests/test_gpu_zzz_fixedpoint.py -q -s > gpurun_out/validate_fx.log 2>&1; echo "fixed-point / packed kernels rc=$?"
+  grep -E "max\|dF\||NVE|drifted|passed|failed|Error|error" gpurun_out/validate_fx.log | tail -40
+  TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_trajectory.py tests/test_gpu_zzz_p2p.py -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap / autograd / trajectory / p2p-world1 rc=$?"
+  grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
+fi
+if has 3; then
+  for fx in 0 1 2; do run_bench "TMD_B200_FX=$fx" fx$fx TMD_B200_FX=$fx; done
+  for cfg in "5 2" "6 4" "5 4"; do
+    set -- $cfg
+    $NVCC -DPAIR_FX_MINBLOCKS=$1 -DPAIR_FX_UNROLL=$2 -o /tmp/var/lib_fx_$1_$2.so torchmd_b200/csrc/tmd_b200.cu
+    run_bench "FX=1, $1 CTAs/SM, $2 entries/lane/iteration" fx1_$1_$2 TMD_B200_LIB=/tmp/var/lib_fx_$1_$2.so TMD_B200_FX=1
+  done
+  for cfg in "5 1" "4 2" "3 2"; do
+    set -- $cfg
+    $NVCC -DPAIR_FX2_MINBLOCKS=$1 -DPAIR_FX2_UNROLL=$2 -o /tmp/var/lib_fx2_$1_$2.so torchmd_b200/csrc/tmd_b200.cu
+    run_bench "FX=2, $1 CTAs/SM, $2 packed evaluations/iteration" fx2_$1_$2 TMD_B200_LIB=/tmp/var/lib_fx2_$1_$2.so TMD_B200_FX=2
+  done
+fi
+if has 4; then
+  $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
+  run_suite cull TMD_B200_LIB=/tmp/var/lib_cull.so
+  for fx in 0 2; do run_bench "BT_CULL=1 FX=$fx" cull_fx$fx TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=$fx; done
+fi
+if has 5; then
+  run_suite overlap TMD_B200_OVERLAP=1
+  for fx in 0 2; do run_bench "OVERLAP=1 FX=$fx" ov_fx$fx TMD_B200_OVERLAP=1 TMD_B200_FX=$fx; done
+fi
+if has 6; then
+  run_suite graph TMD_B200_GRAPH=1
+  for fx in 0 2; do run_bench "GRAPH=1 FX=$fx" graph_fx$fx TMD_B200_GRAPH=1 TMD_B200_FX=$fx; done
+  [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
+  run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
+fi
