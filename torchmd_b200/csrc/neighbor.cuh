@@ -363,6 +363,7 @@ struct BuildShared {
   int counts[BT_MAXI];
 #if BT_CULL
   float bb[BT_CHUNKS][6];   // per chunk: min x,y,z, max x,y,z over its finite records
+  int jr[BT_CHUNKS][2];     // per chunk: smallest / largest sorted atom index among its records
 #endif
 };
 
@@ -384,6 +385,12 @@ __device__ __forceinline__ void build_chunk_boxes(BuildShared& sh, int fill) {
         sh.bb[c][d] = dec_float(lo);
         sh.bb[c][3 + d] = dec_float(hi);
       }
+    }
+    const int j = __float_as_int(p.w) & 0xffffff;  // (padding records carry 0xffffff: they only widen the range)
+    const int jlo = __reduce_min_sync(0xffffffffu, j), jhi = __reduce_max_sync(0xffffffffu, j);
+    if (lane == 0) {
+      sh.jr[c][0] = jlo;
+      sh.jr[c][1] = jhi;
     }
   }
 }
@@ -425,11 +432,14 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     int count = sh.counts[ii];
 #if BT_CULL
     // chunks whose bounding box is within the list radius of this atom (lane c tests chunks
-    // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling
-    unsigned long long visit;
+    // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling.  `special`:
+    // chunks whose index range can hold the atom itself or one of its exclusions -- only those
+    // pay for the per-candidate index tests.
+    exlo = min(exlo, k);
+    exhi = max(exhi, k);
+    unsigned mh[2], sp[2];  // chunks 0..31 and 32..63
     {
       const int nchunks = (fill + 31) >> 5;
-      unsigned mh[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h;
@@ -449,14 +459,20 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
           v = (dx * dx + dy * dy + dz * dz) * 0.99999f <= rl2;
         }
         mh[h] = __ballot_sync(0xffffffffu, v);
+        sp[h] = __ballot_sync(0xffffffffu, v && sh.jr[c][0] <= exhi && sh.jr[c][1] >= exlo);
       }
-      visit = (unsigned long long)mh[0] | ((unsigned long long)mh[1] << 32);
     }
 #pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+    unsigned visit = mh[h];
+    const unsigned special = sp[h];
+#pragma unroll 1
     while (visit) {
-      const int c0 = (__ffsll((long long)visit) - 1) << 5;
+      const int cbit = __ffs((int)visit) - 1;
+      const int c0 = (cbit + 32 * h) << 5;
       visit &= visit - 1;
       const float4 pj = sh.tile[c0 + lane];
+      const bool check_index = (special >> cbit) & 1u;  // warp-uniform
 #else
     const float4* __restrict__ tp = sh.tile + lane;
 #pragma unroll 1
@@ -472,10 +488,17 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
         if (w1) dy -= g.L[1] * rintf(dy * g.invL[1]);
         if (w2) dz -= g.L[2] * rintf(dz * g.invL[2]);
       }
+#if BT_CULL
+      const bool near = dx * dx + dy * dy + dz * dz <= rl2;
+      unsigned m = __ballot_sync(0xffffffffu, near);
+      if (check_index) {  // rare: the atom itself or an exclusion may be in this chunk
+        bool excl = (j == k);
+#else
       const bool near = (dx * dx + dy * dy + dz * dz <= rl2) && (j != k);
       unsigned m = __ballot_sync(0xffffffffu, near);
       if (__any_sync(0xffffffffu, near && j >= exlo && j <= exhi)) {  // rare: an exclusion may be in this chunk
         bool excl = false;
+#endif
         const int nfast = min(ne, 32);
 #pragma unroll 1
         for (int e = 0; e < nfast; ++e) excl |= (__shfl_sync(0xffffffffu, my_excl, e) == j);
@@ -487,6 +510,9 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
       if (((m >> lane) & 1u) && slot < cap) row[slot] = entry;
       count += __popc(m);
     }
+#if BT_CULL
+    }  // both halves of the chunk mask
+#endif
     // keep the row padded to a multiple of 32 entries with the sentinel (record natoms holds
     // NaN coordinates and fails every cutoff test).  Later tiles overwrite the padding as the
     // row grows.
