@@ -28,8 +28,8 @@ PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water
 
 
 def make_forces(g, fx, **kw):
-    """fx: 0 float kernel, 1 fixed-point kernel, 2 fixed-point + packed fp32x2 arithmetic (k_pair_fx2,
-    used for force-only passes of the LJ+switch+RF term set; other passes take the fixed-point kernel)."""
+    """fx: 0 float kernel, 1 fixed-point kernel, 2 fixed-point + packed fp32x2 arithmetic (k_pair_fx2, taken
+    for the LJ+switch+RF term set with <= 16 atom types; other systems fall back to the fixed-point kernel)."""
     from torchmd_b200 import Forces
 
     old = os.environ.get("TMD_B200_FX")
@@ -54,7 +54,7 @@ def test_fixed_point_kernel_matches_golden(name, mode):
     g = load_golden(name)
     f, pos, box, F, E = make_forces(g, mode)
     f0, _, _, F0, E0 = make_forces(g, 0)
-    if mode == 2:  # the packed kernel runs when no energies are requested: a force-only pass
+    if mode == 2:  # also the force-only instantiation of the packed kernel
         os.environ["TMD_B200_FX"] = "2"
         try:
             from torchmd_b200 import _lib
@@ -113,7 +113,7 @@ def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
             pos, bx = pos_c.to(DEV), box_c.to(DEV)
             F = torch.zeros_like(pos)
             f.compute(pos, bx, F)
-            if mode == "2":  # force-only pass -> packed kernel
+            if mode == "2":  # also the force-only instantiation
                 from torchmd_b200 import _lib
                 _lib.check(_lib.lib().tmd_forces(f._ctx, pos.data_ptr(), F.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
                 torch.cuda.synchronize()

@@ -313,6 +313,15 @@ def test_packed_two_partner_coefficient_matches_oracle(hc):
                      C.c_float(krf), C.c_float(crf), *[p(o) for o in o5])
     scalar = o5[4].astype(np.float64) / np.sqrt(s.astype(np.float64))
     assert np.abs(out - scalar).max() <= 4e-6 * max(1.0, np.abs(scalar).max())
+    # energies of the ENERGY instantiation
+    c2, elj, eel = (np.zeros(n, F32) for _ in range(3))
+    hc.hc_pair_coef2e(n, p(s), p(qq), p(A), p(B), C.c_float(cutoff), C.c_float(switch), C.c_float(krf), C.c_float(crf),
+                      p(c2), p(elj), p(eel))
+    assert np.array_equal(c2, out)
+    lj_e, _ = refmd.lj_pair(dist, torch.tensor(A.astype(np.float64)), torch.tensor(B.astype(np.float64)), 1, switch, cutoff)
+    el_e, _ = refmd.coulomb_pair(dist, torch.tensor(qq.astype(np.float64) / refmd.COULOMB), torch.ones(n, dtype=torch.float64), 1, cutoff, True, eps)
+    assert np.abs(elj - lj_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(lj_e.numpy()).max())
+    assert np.abs(eel - el_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(el_e.numpy()).max())
 
 
 @pytest.mark.parametrize("scale", [1, 50, 1900])

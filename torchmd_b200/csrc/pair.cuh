@@ -342,8 +342,9 @@ static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in t
 #define PAIR_FX2_UNROLL 1  // packed evaluations (pairs of list entries) per lane and loop iteration: 1 or 2
 #endif
 
+template <bool ENERGY>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
-k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
+k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int kk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
@@ -361,8 +362,8 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
   }
   asm volatile("" ::: "memory");
   __syncthreads();
-  if (kk >= S.own_n) return;
-
+  float e_el = 0.f, e_lj = 0.f;
+  if (kk < S.own_n) {
   const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
   const int4* __restrict__ xf = S.xf_s + (size_t)r * (N + 1);
   unsigned long long xf_base = reinterpret_cast<unsigned long long>(xf);
@@ -377,6 +378,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
   const float margin = fmaf(g->fx_c1, __int_as_float(S.flags[r * F_COUNT + F_PMAX]), g->fx_c0);
   const float s_hi = S.pp.s_max + margin, s_lo = S.pp.s_max - margin;
   F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);  // the two halves are added at the end
+  F2 ELJ = f2(0.f), NEEL = f2(0.f);             // switched LJ energy / minus the Coulomb energy
   float s_skipped = INFINITY;
 
   // two list entries evaluated together
@@ -402,12 +404,17 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
         asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab1.y) : "r"(a1));
       }
       const F2 nqq = f2_mul(f2(nqi), f2(__int_as_float(p0.w), __int_as_float(p1.w)));
-      F2 nc = pair_coef2(sc, s, nqq, f2(ab0.x, ab1.x), f2(ab0.y, ab1.y), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
-                         f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)));
+      F2 elj, neel;
+      F2 nc = pair_coef2<ENERGY>(sc, s, nqq, f2(ab0.x, ab1.x), f2(ab0.y, ab1.y), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+                                 f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)), elj, neel);
       nc = f2(in0 ? nc.x : 0.f, in1 ? nc.y : 0.f);  // a select, not a product: the other half may hold inf/NaN
       FX = f2_fma(wx, nc, FX);
       FY = f2_fma(wy, nc, FY);
       FZ = f2_fma(wz, nc, FZ);
+      if (ENERGY) {
+        ELJ = f2_add(ELJ, f2(in0 ? elj.x : 0.f, in1 ? elj.y : 0.f));
+        NEEL = f2_add(NEEL, f2(in0 ? neel.x : 0.f, in1 ? neel.y : 0.f));
+      }
     }
   };
 #if PAIR_FX2_UNROLL == 2
@@ -447,12 +454,16 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
   }
 #endif
   float fx = FX.x + FX.y, fy = FY.x + FY.y, fz = FZ.x + FZ.y;
+  if (ENERGY) {
+    e_lj = ELJ.x + ELJ.y;
+    e_el = -(NEEL.x + NEEL.y);
+  }
   if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
     // pairs inside the decision band: the reference's own decision, scalar arithmetic
     const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
     const PairParams pp = S.pp;
     const float qi = -nqi;
-    float e_el = 0.f, e_lj = 0.f, e_rep = 0.f, e_cg = 0.f;
+    float e_rep = 0.f, e_cg = 0.f;
     for (int eb = lane; eb < n; eb += 32) {
       const int entry = row[eb];
       const int j = entry & 0xffffff;
@@ -484,6 +495,13 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces) {
     f[0] = fx;
     f[1] = fy;
     f[2] = fz;
+  }
+  }  // kk < own_n
+  if (ENERGY) {
+    __shared__ double red[PAIR_WARPS];
+    double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
+    block_accumulate<PAIR_WARPS>(0.5 * (double)e_el, E + TMD_E_ELECTROSTATICS, red);  // every pair is seen from both atoms
+    block_accumulate<PAIR_WARPS>(0.5 * (double)e_lj, E + TMD_E_LJ, red);
   }
 }
 

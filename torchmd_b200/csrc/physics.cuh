@@ -358,7 +358,7 @@ TMD_HD float neg_rcp_seed(float s) {
 struct SwitchConsts {
   float neg_switch_dist, inv_sw_width;
   float d1, d2, d3;  // -ds/dr polynomial: t^2 (d3 + t (d2 + t d1)),  d = (30, -60, 30) / (cutoff - switch_dist)
-  float two_krf;
+  float two_krf, krf, neg_crf;
 };
 inline SwitchConsts make_switch_consts(const PairParams& pp) {
   SwitchConsts c;
@@ -368,6 +368,8 @@ inline SwitchConsts make_switch_consts(const PairParams& pp) {
   c.d2 = -60.0f * pp.inv_sw_width;
   c.d3 = 30.0f * pp.inv_sw_width;
   c.two_krf = pp.two_krf;
+  c.krf = pp.krf;
+  c.neg_crf = -pp.crf;
   return c;
 }
 
@@ -376,8 +378,10 @@ inline SwitchConsts make_switch_consts(const PairParams& pp) {
 // signs arranged so that no negation is ever needed):
 //   s    squared distances          nqq  -(k_e q_i q_j)             A, B  LJ table entries
 //   y    rsqrt_seed(s)              nz   neg_rcp_seed(s)
-// The force on atom i is then  F_i += w * result.
-TMD_HD F2 pair_coef2(const SwitchConsts& c, F2 s, F2 nqq, F2 A, F2 B, F2 y, F2 nz) {
+// The force on atom i is then  F_i += w * result.  ENERGY: also the switched LJ energy and MINUS the
+// reaction-field Coulomb energy of each partner (forces.py:389-415, 466-478).
+template <bool ENERGY>
+TMD_HD F2 pair_coef2(const SwitchConsts& c, F2 s, F2 nqq, F2 A, F2 B, F2 y, F2 nz, F2& e_lj, F2& ne_el) {
   // 1/r to ~1 ulp and r
   const F2 t = f2_mul(s, y);
   const F2 u = f2_fma(f2_mul(t, f2(-0.5f)), y, f2(0.5f));
@@ -402,7 +406,15 @@ TMD_HD F2 pair_coef2(const SwitchConsts& c, F2 s, F2 nqq, F2 A, F2 B, F2 y, F2 n
   const F2 nfsw = f2_fma(sw, nf, f2_mul(f2_mul(e, ndsw), rinv));
   // reaction field: dE/dr = qq (2 k_rf r - 1/r^2)
   const F2 ndedr = f2_fma(nqq, f2_fma(f2(c.two_krf), r, nr2), nfsw);
+  if (ENERGY) {
+    e_lj = f2_mul(e, sw);
+    ne_el = f2_mul(nqq, f2_add(f2_fma(f2(c.krf), s, rinv), f2(c.neg_crf)));  // -qq (1/r + k_rf r^2 - c_rf)
+  }
   return f2_mul(ndedr, rinv);
+}
+TMD_HD F2 pair_coef2(const SwitchConsts& c, F2 s, F2 nqq, F2 A, F2 B, F2 y, F2 nz) {
+  F2 a, b;
+  return pair_coef2<false>(c, s, nqq, A, B, y, nz, a, b);
 }
 
 // ---- bonded terms --------------------------------------------------------------------

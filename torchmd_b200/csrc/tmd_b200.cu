@@ -598,8 +598,8 @@ template <bool E>
 static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
   const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
   const int th = PAIR_WARPS * 32;
-  if (!E && ctx->fx_packed && ctx->pair_mode == 1 && small) {  // TMD_B200_FX=2: packed fp32x2 arithmetic
-    k_pair_fx2<<<pg, th, 0, st>>>(ctx->d, make_switch_consts(ctx->d.pp), forces);
+  if (ctx->fx_packed && ctx->pair_mode == 1 && small) {  // TMD_B200_FX=2: packed fp32x2 arithmetic
+    k_pair_fx2<E><<<pg, th, 0, st>>>(ctx->d, make_switch_consts(ctx->d.pp), forces, energies);
     return;
   }
   if (ctx->pair_mode == 1) {
