@@ -113,18 +113,39 @@ class DecomposedIntegrator:
         self.use_graph = use_graph
         self._graphs = {}
         self._parity = 0  # p2p: which of the two position buffers holds the current positions
-        if self.exchange == "p2p":
-            self._connect_peers()
+        if self.exchange == "p2p" and not self._connect_peers():
+            self.exchange = "allgather"
+
+    def _all_ok(self, err, what):
+        """Every rank must take the same path: True iff the local step ``what`` worked on all ranks."""
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.system.pos.device)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return True
+        if self.rank == 0 or err is not None:
+            import sys
+
+            print(f"[domain] rank {self.rank}: peer-to-peer exchange unavailable ({what}: {err if err else 'failed on another rank'}); "
+                  "using the NCCL all-gather exchange", file=sys.stderr)
+        return False
 
     def _connect_peers(self):
         """Allocate this rank's exchange buffers and map every peer's (CUDA IPC handles travel
-        through one all-gather at set-up; nothing else does)."""
+        through one all-gather at set-up; nothing else does).  Returns False -- on every rank --
+        if any rank could not (CUDA IPC not permitted, no peer access between two GPUs ...)."""
         L = _lib.lib()
         if self.world > _lib.MAX_PEERS:
             raise NotImplementedError(f"peer-to-peer exchange supports up to {_lib.MAX_PEERS} ranks")
         dev = self.system.pos.device
         handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
-        _lib.check(L.tmd_dd_create(self.ctx, self.rank, self.world, handle))
+        err = None
+        try:
+            _lib.check(L.tmd_dd_create(self.ctx, self.rank, self.world, handle))
+        except _lib.TmdError as e:
+            err = e
+        if not self._all_ok(err, "allocating the exchange buffers"):
+            return False
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         everyone = torch.empty(self.world * _lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
         if self.world > 1:
@@ -133,9 +154,12 @@ class DecomposedIntegrator:
             everyone.copy_(mine)
         raw = bytes(everyone.cpu().numpy().tobytes())
         table = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
-        _lib.check(L.tmd_dd_connect(self.ctx, table))
-        if self.world > 1:
-            dist.barrier(group=self.group)  # every rank has mapped every buffer before anyone stores into one
+        try:
+            _lib.check(L.tmd_dd_connect(self.ctx, table))
+        except _lib.TmdError as e:
+            err = e
+        # (also the barrier: every rank has mapped every buffer before anyone stores into one)
+        return self._all_ok(err, "mapping the peers' buffers")
 
     # one MD step on the current stream; with_energy: also this rank's energy / KE share
     def _enqueue_step_p2p(self, with_energy, parity):
