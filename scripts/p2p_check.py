@@ -42,6 +42,11 @@ def main():
     for use_graph in (False, True):
         sa, fa, ia = make("allgather", use_graph)
         sb, fb, ib = make("p2p", use_graph)
+        if ib.exchange != "p2p":
+            if rank == 0:
+                print("P2P_CHECK FAIL: the peer-to-peer exchange could not be set up (see stderr)", flush=True)
+            dist.destroy_process_group()
+            sys.exit(2)
         for niter in (1, 2, 61):
             ea = ia.step(niter=niter)
             eb = ib.step(niter=niter)

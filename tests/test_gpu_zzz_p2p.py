@@ -51,7 +51,7 @@ def test_p2p_world1_matches_integrator_bitwise(use_graph):
     sb, fb = _setup()
     torch.manual_seed(9)
     ib = DecomposedIntegrator(sb, fb, 1.0, DEV, gamma=0.1, T=300.0, use_graph=use_graph, exchange="p2p")
-    assert ib.integ.seed == ia.seed
+    assert ib.integ.seed == ia.seed and ib.exchange == "p2p"
     for niter in (1, 2, 37):  # odd and even counts: both buffer parities start and end a call
         ea = ia.step(niter=niter)
         eb = ib.step(niter=niter)
