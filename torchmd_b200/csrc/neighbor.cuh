@@ -402,8 +402,14 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
                                                    bool w1, bool w2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
+#if BT_CULL
+  float rl2 = S.rlist2;
+  int cap = S.row_cap;
+  asm volatile("" : "+f"(rl2), "+r"(cap));  // keep both in registers: the chunk loop otherwise re-reads them from the constant bank
+#else
   const float rl2 = S.rlist2;
   const int cap = S.row_cap;
+#endif
   for (int ii = warp; ii < nib; ii += BT_WARPS) {
     const int k = b0 + ii;
     if (!S.own_all) {  // decomposed run: rows only for the atoms this rank owns
@@ -431,6 +437,8 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     int* __restrict__ row = S.nbr + (base + k) * (size_t)cap;
     int count = sh.counts[ii];
 #if BT_CULL
+    unsigned long long row_addr = reinterpret_cast<unsigned long long>(row);
+    asm volatile("" : "+l"(row_addr));  // one 64-bit base; a store address is then base + 4*slot
     // chunks whose bounding box is within the list radius of this atom (lane c tests chunks
     // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling.  `special`:
     // chunks whose index range can hold the atom itself or one of its exclusions -- only those
@@ -507,7 +515,12 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
         m &= ~__ballot_sync(0xffffffffu, excl);
       }
       const int slot = count + __popc(m & lt);
+#if BT_CULL
+      if (((m >> lane) & 1u) && slot < cap)
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(row_addr + 4ull * (unsigned)slot), "r"(entry) : "memory");
+#else
       if (((m >> lane) & 1u) && slot < cap) row[slot] = entry;
+#endif
       count += __popc(m);
     }
 #if BT_CULL
