@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "torchmd_b200", "libtmd_b200.so")
+LIB = os.environ.get("TMD_B200_LIB") or os.path.join(ROOT, "torchmd_b200", "libtmd_b200.so")
 
 
 def functions():
@@ -83,4 +83,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        LIB = sys.argv[1]
     main()
