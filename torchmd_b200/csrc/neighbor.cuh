@@ -621,6 +621,21 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
       for (int t0 = 0; t0 < M; t0 += BT_TILE) {
         const int fill = min(BT_TILE, M - t0);
         __syncthreads();  // tile free, counts initialised
+#if BT_CULL
+        // one warp per run, lanes stride its records: the same tile layout as the search below
+        // (slot = run offset + position in the run) without a binary search per record
+        for (int q = tid >> 5; q < BT_MAXRUN; q += BT_WARPS) {
+          const Run rn = runs[q];
+          const int first = roff[q] - t0;  // tile position of the run's first record (the run may straddle tiles)
+          for (int u = (tid & 31); u < rn.len; u += 32) {
+            const int at = first + u;
+            if (at < 0 || at >= fill) continue;
+            const int j = rn.a0 + u;
+            const float4 p = xw[j];
+            tile[at] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j | (S.type_s[base + j] << 24)));
+          }
+        }
+#else
         for (int u = tid; u < fill; u += nthr) {
           const int slot = t0 + u;
           int q = 0;  // binary search: last run with roff[q] <= slot
@@ -633,6 +648,7 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
           // the list entry: sorted index (24 bits) + atom type (8 bits), see pair.cuh
           tile[u] = make_float4(p.x + rn.sx, p.y + rn.sy, p.z + rn.sz, __int_as_float(j | (S.type_s[base + j] << 24)));
         }
+#endif
         // pad the last 32-candidate chunk with records that pass no distance test
         for (int u = fill + tid; u < ((fill + 31) & ~31); u += nthr)
           tile[u] = make_float4(NAN, NAN, NAN, __int_as_float(0xffffff));  // NaN: fails `<= rlist2` even when that is +inf
