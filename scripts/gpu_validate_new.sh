@@ -61,6 +61,10 @@ if has 3; then
     $NVCC -DPAIR_FX2_MINBLOCKS=$1 -DPAIR_FX2_UNROLL=$2 -o /tmp/var/lib_fx2_$1_$2.so torchmd_b200/csrc/tmd_b200.cu
     run_bench "FX=2, $1 CTAs/SM, $2 packed evaluations/iteration" fx2_$1_$2 TMD_B200_LIB=/tmp/var/lib_fx2_$1_$2.so TMD_B200_FX=2
   done
+  for mb in 4 3; do
+    $NVCC -DPAIR_FX2_MINBLOCKS=$mb -DPAIR_FX2_PIPE=1 -o /tmp/var/lib_fx2_pipe_$mb.so torchmd_b200/csrc/tmd_b200.cu
+    run_bench "FX=2, $mb CTAs/SM, pipelined gathers" fx2_pipe_$mb TMD_B200_LIB=/tmp/var/lib_fx2_pipe_$mb.so TMD_B200_FX=2
+  done
 fi
 if has 4; then
   $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu

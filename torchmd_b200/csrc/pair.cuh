@@ -341,6 +341,10 @@ static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in t
 #ifndef PAIR_FX2_UNROLL
 #define PAIR_FX2_UNROLL 1  // packed evaluations (pairs of list entries) per lane and loop iteration: 1 or 2
 #endif
+#ifndef PAIR_FX2_PIPE
+#define PAIR_FX2_PIPE 0    // 1: software-pipelined gathers (the ncu source view of round 1 puts 24 % of the
+                           // stall samples on the first use of a gathered record)
+#endif
 
 template <bool ENERGY>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
@@ -382,11 +386,11 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   float s_skipped = INFINITY;
 
   // two list entries evaluated together
-  auto pair2 = [&](int j0, int j1) {
+  // an empty slot (entry -1) reads record 0 and is masked later
+  auto record_of = [&](int j) { return fx_record(xf_base, ((j >= 0 ? (unsigned)j : 0u) << 4) & 0x0ffffff0u); };
+  auto pair2r = [&](int j0, int j1, const int4 p0, const int4 p1) {
     const bool v0 = j0 >= 0, v1 = j1 >= 0;
-    const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;  // an empty slot reads record 0 and is masked
-    const int4 p0 = fx_record(xf_base, (en0 << 4) & 0x0ffffff0u);
-    const int4 p1 = fx_record(xf_base, (en1 << 4) & 0x0ffffff0u);
+    const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;
     const F2 wx = f2_mul(f2((float)(int)((unsigned)pi.x - (unsigned)p0.x), (float)(int)((unsigned)pi.x - (unsigned)p1.x)), ux);
     const F2 wy = f2_mul(f2((float)(int)((unsigned)pi.y - (unsigned)p0.y), (float)(int)((unsigned)pi.y - (unsigned)p1.y)), uy);
     const F2 wz = f2_mul(f2((float)(int)((unsigned)pi.z - (unsigned)p0.z), (float)(int)((unsigned)pi.z - (unsigned)p1.z)), uz);
@@ -417,7 +421,30 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
       }
     }
   };
-#if PAIR_FX2_UNROLL == 2
+  auto pair2 = [&](int j0, int j1) { pair2r(j0, j1, record_of(j0), record_of(j1)); };
+#if PAIR_FX2_PIPE
+  {  // tuning variant: list entries two iterations ahead, partner records one iteration ahead
+    int e = lane;
+    int j0 = (e < n) ? __ldcs(row + e) : -1;
+    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+    int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    int4 p0 = record_of(j0), p1 = record_of(j1);
+    while (e < n) {
+      const int jnn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
+      const int jnn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
+      const int4 pn0 = record_of(jn0), pn1 = record_of(jn1);
+      pair2r(j0, j1, p0, p1);
+      j0 = jn0;
+      j1 = jn1;
+      jn0 = jnn0;
+      jn1 = jnn1;
+      p0 = pn0;
+      p1 = pn1;
+      e += 64;
+    }
+  }
+#elif PAIR_FX2_UNROLL == 2
   {  // tuning variant: two packed evaluations (four list entries) per iteration
     int e = lane;
     int j0 = (e < n) ? __ldcs(row + e) : -1;
