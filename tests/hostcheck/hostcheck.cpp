@@ -204,6 +204,8 @@ void hc_pair_coef2(int n, const float* s, const float* qq, const float* A, const
   pp.has_switch = 1;
   pp.switch_dist = switch_dist;
   pp.inv_sw_width = 1.0f / (cutoff - switch_dist);
+  pp.rfa = 1;
+  pp.krf = krf;
   pp.two_krf = 2.0f * krf;
   const SwitchConsts sc = make_switch_consts(pp);
   for (int k = 0; k + 1 < n; k += 2) {
@@ -223,6 +225,34 @@ void hc_pair_coef2e(int n, const float* s, const float* qq, const float* A, cons
   pp.has_switch = 1;
   pp.switch_dist = switch_dist;
   pp.inv_sw_width = 1.0f / (cutoff - switch_dist);
+  pp.rfa = 1;
+  pp.krf = krf;
+  pp.crf = crf;
+  pp.two_krf = 2.0f * krf;
+  const SwitchConsts sc = make_switch_consts(pp);
+  for (int k = 0; k + 1 < n; k += 2) {
+    const F2 ss = f2(s[k], s[k + 1]);
+    F2 elj, neel;
+    const F2 nc = pair_coef2<true>(sc, ss, f2(-qq[k], -qq[k + 1]), f2(A[k], A[k + 1]), f2(B[k], B[k + 1]),
+                                   f2(rsqrt_seed(ss.x), rsqrt_seed(ss.y)), f2(neg_rcp_seed(ss.x), neg_rcp_seed(ss.y)), elj, neel);
+    c_out[k] = -nc.x;
+    c_out[k + 1] = -nc.y;
+    elj_out[k] = elj.x;
+    elj_out[k + 1] = elj.y;
+    eel_out[k] = -neel.x;
+    eel_out[k + 1] = -neel.y;
+  }
+}
+
+// general form: with / without switching and reaction field (make_switch_consts covers all four)
+void hc_pair_coef2g(int n, const float* s, const float* qq, const float* A, const float* B, float cutoff, int has_switch,
+                    float switch_dist, int rfa, float krf, float crf, float* c_out, float* elj_out, float* eel_out) {
+  PairParams pp{};
+  pp.cutoff = cutoff;
+  pp.has_switch = has_switch;
+  pp.switch_dist = has_switch ? switch_dist : 0.f;
+  pp.inv_sw_width = has_switch ? 1.0f / (cutoff - switch_dist) : 0.f;
+  pp.rfa = rfa;
   pp.krf = krf;
   pp.crf = crf;
   pp.two_krf = 2.0f * krf;

@@ -29,7 +29,7 @@ PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water
 
 def make_forces(g, fx, **kw):
     """fx: 0 float kernel, 1 fixed-point kernel, 2 fixed-point + packed fp32x2 arithmetic (k_pair_fx2, taken
-    for the LJ+switch+RF term set with <= 16 atom types; other systems fall back to the fixed-point kernel)."""
+    for every lj/electrostatics term set with <= 16 atom types; other systems fall back to the fixed-point kernel)."""
     from torchmd_b200 import Forces
 
     old = os.environ.get("TMD_B200_FX")

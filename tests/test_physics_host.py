@@ -340,3 +340,27 @@ def test_fx_decision_bound_holds_far_from_the_origin(hc, scale):
     _, sref, inside = decide(hc, pi, pj, box, 9.0)
     assert np.abs(s - sref).max() <= margin
     assert ((cls == 2) | ((cls == 1) == inside)).all()
+
+
+@pytest.mark.parametrize("rfa,switch", [(True, 7.5), (False, None), (True, None), (False, 6.0)])
+def test_packed_coefficient_covers_every_lj_electrostatics_combination(hc, rfa, switch):
+    """make_switch_consts turns switching / the reaction field off through its constants."""
+    rng = np.random.default_rng(9)
+    n, cutoff, eps = 20000, 9.0, 78.5
+    r = rng.uniform(1.6, cutoff, n)
+    s = (r * r).astype(F32)
+    qq = (refmd.COULOMB * rng.uniform(-1, 1, n) * rng.uniform(-1, 1, n)).astype(F32)
+    A = rng.uniform(1e4, 6e5, n).astype(F32)
+    B = rng.uniform(10, 600, n).astype(F32)
+    krf = (1 / cutoff**3) * (eps - 1) / (2 * eps + 1)
+    crf = (1 / cutoff) * (3 * eps) / (2 * eps + 1)
+    c, elj, eel = (np.zeros(n, F32) for _ in range(3))
+    hc.hc_pair_coef2g(n, p(s), p(qq), p(A), p(B), C.c_float(cutoff), int(switch is not None), C.c_float(switch or 0.0), int(rfa),
+                      C.c_float(krf), C.c_float(crf), p(c), p(elj), p(eel))
+    dist = torch.tensor(np.sqrt(s.astype(np.float64)))
+    lj_e, lj_f = refmd.lj_pair(dist, torch.tensor(A.astype(np.float64)), torch.tensor(B.astype(np.float64)), 1, switch, cutoff)
+    el_e, el_f = refmd.coulomb_pair(dist, torch.tensor(qq.astype(np.float64) / refmd.COULOMB), torch.ones(n, dtype=torch.float64), 1, cutoff, rfa, eps)
+    want = ((lj_f + el_f) / dist).numpy()
+    assert np.abs(c - want).max() <= 4e-6 * max(1.0, np.abs(want).max())
+    assert np.abs(elj - lj_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(lj_e.numpy()).max())
+    assert np.abs(eel - el_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(el_e.numpy()).max())

@@ -329,8 +329,9 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
 }
 
 // ---- fixed-point separations + packed fp32x2 arithmetic ------------------------------------
-// k_pair_fx for the production term set (LJ with switch + reaction-field Coulomb, forces only,
-// <= 16 atom types) with the two list entries a lane handles per iteration evaluated TOGETHER
+// k_pair_fx for every combination of the "lj" and "electrostatics" terms (with or without
+// switching / reaction field; <= 16 atom types; explicit-force convention) with the two list
+// entries a lane handles per iteration evaluated TOGETHER
 // in packed fp32x2 operations (physics.cuh, pair_coef2): the kernel is issue-bound, a packed
 // operation costs one issue slot for two results.  Decisions, band handling and list layout are
 // those of k_pair_fx; a partner that is not taken contributes through a zeroed coefficient.
@@ -360,7 +361,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   // partners are then loaded straight into register pairs
   __shared__ float ab_s[2 * FX_SMALLT_MAX * FX_SMALLT_MAX];
   if ((int)threadIdx.x < S.ntypes * S.ntypes) {
-    const float2 v = S.AB[threadIdx.x];
+    const float2 v = (S.pp.terms & T_LJ) ? S.AB[threadIdx.x] : make_float2(0.f, 0.f);  // term off: zero table
     ab_s[threadIdx.x] = v.x;
     ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
   }
@@ -375,7 +376,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
   const int n = S.nnbr[base + k];
   const int4 pi = xf[k];
-  const float nqi = -__int_as_float(pi.w);
+  const float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
   const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)(S.type_s[base + k] * S.ntypes) * 4u;
   const Grid* g = S.grid + r;
   const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
@@ -489,7 +490,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
     // pairs inside the decision band: the reference's own decision, scalar arithmetic
     const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
     const PairParams pp = S.pp;
-    const float qi = -nqi;
+    const float qi = __int_as_float(pi.w);
     float e_rep = 0.f, e_cg = 0.f;
     for (int eb = lane; eb < n; eb += 32) {
       const int entry = row[eb];
@@ -505,7 +506,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
           asm("ld.shared.f32 %0, [%1];" : "=f"(ab.x) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
           asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab.y) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
           float rinv;
-          const float dedr = pair_terms<1>(pp, s, qi * __int_as_float(pj.w), ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
+          const float dedr = pair_terms<0>(pp, s, qi * __int_as_float(pj.w), ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
           const float c = dedr * rinv;
           fx -= wx * c;
           fy -= wy * c;

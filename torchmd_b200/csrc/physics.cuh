@@ -360,16 +360,24 @@ struct SwitchConsts {
   float d1, d2, d3;  // -ds/dr polynomial: t^2 (d3 + t (d2 + t d1)),  d = (30, -60, 30) / (cutoff - switch_dist)
   float two_krf, krf, neg_crf;
 };
+// Also covers the term sets without switching (t stays 0: sw = 1, ds/dr = 0) and without a reaction field
+// (k_rf = c_rf = 0: plain Coulomb), so pair_coef2 serves every combination of "lj" and "electrostatics".
 inline SwitchConsts make_switch_consts(const PairParams& pp) {
   SwitchConsts c;
-  c.neg_switch_dist = -pp.switch_dist;
-  c.inv_sw_width = pp.inv_sw_width;
-  c.d1 = 30.0f * pp.inv_sw_width;
-  c.d2 = -60.0f * pp.inv_sw_width;
-  c.d3 = 30.0f * pp.inv_sw_width;
-  c.two_krf = pp.two_krf;
-  c.krf = pp.krf;
-  c.neg_crf = -pp.crf;
+  if (pp.has_switch) {
+    c.neg_switch_dist = -pp.switch_dist;
+    c.inv_sw_width = pp.inv_sw_width;
+    c.d1 = 30.0f * pp.inv_sw_width;
+    c.d2 = -60.0f * pp.inv_sw_width;
+    c.d3 = 30.0f * pp.inv_sw_width;
+  } else {
+    c.neg_switch_dist = -1.0e30f;  // (r - 1e30) * 1 < 0 for every r: t = 0
+    c.inv_sw_width = 1.0f;
+    c.d1 = c.d2 = c.d3 = 0.0f;
+  }
+  c.two_krf = pp.rfa ? pp.two_krf : 0.0f;
+  c.krf = pp.rfa ? pp.krf : 0.0f;
+  c.neg_crf = pp.rfa ? -pp.crf : 0.0f;
   return c;
 }
 

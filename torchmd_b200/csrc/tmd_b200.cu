@@ -598,7 +598,9 @@ template <bool E>
 static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
   const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
   const int th = PAIR_WARPS * 32;
-  if (ctx->fx_packed && ctx->pair_mode == 1 && small) {  // TMD_B200_FX=2: packed fp32x2 arithmetic
+  // TMD_B200_FX=2: packed fp32x2 arithmetic for the term sets made of "lj" and "electrostatics"
+  const bool lj_el_only = ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0;
+  if (ctx->fx_packed && lj_el_only && !ctx->exact_gradient && small) {
     k_pair_fx2<E><<<pg, th, 0, st>>>(ctx->d, make_switch_consts(ctx->d.pp), forces, energies);
     return;
   }
