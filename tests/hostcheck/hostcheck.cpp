@@ -137,6 +137,29 @@ void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const
     iL[k] = 1.0f / box[k];
   }
   for (int e = 0; e < natoms * 3; ++e) forces[e] = 0.f;
+  if (variant == 3) {  // k_pair2_open: no box, float records, two pairs per packed evaluation
+    const SwitchConsts sc = make_switch_consts(pp);
+    for (int q = 0; q < npairs; q += 2) {
+      const int q1 = (q + 1 < npairs) ? q + 1 : q;
+      const int ia[2] = {pairs[2 * q], pairs[2 * q1]}, ja[2] = {pairs[2 * q + 1], pairs[2 * q1 + 1]};
+      F2 w[3];
+      for (int k = 0; k < 3; ++k) w[k] = f2_add(f2(pos[3 * ia[0] + k], pos[3 * ia[1] + k]), f2(-pos[3 * ja[0] + k], -pos[3 * ja[1] + k]));
+      const F2 s = f2_fma(w[2], w[2], f2_fma(w[1], w[1], f2_mul(w[0], w[0])));
+      const float* ab0 = AB + 2 * (type[ia[0]] * ntypes + type[ja[0]]);
+      const float* ab1 = AB + 2 * (type[ia[1]] * ntypes + type[ja[1]]);
+      const F2 nqq = f2(-(qs[ia[0]] * qs[ja[0]]), -(qs[ia[1]] * qs[ja[1]]));
+      const F2 nc = pair_coef2(sc, s, nqq, f2(ab0[0], ab1[0]), f2(ab0[1], ab1[1]), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+                               f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)));
+      const float ncs[2] = {nc.x, (q1 == q) ? 0.f : nc.y};
+      for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 3; ++k) {
+          const float wk = h == 0 ? w[k].x : w[k].y;
+          forces[3 * ia[h] + k] += wk * ncs[h];
+          forces[3 * ja[h] + k] -= wk * ncs[h];
+        }
+    }
+    return;
+  }
   if (variant == 2) {  // k_pair_fx2: fixed-point separations, two pairs per packed evaluation
     const SwitchConsts sc = make_switch_consts(pp);
     for (int q = 0; q < npairs; q += 2) {

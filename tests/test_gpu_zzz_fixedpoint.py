@@ -85,6 +85,39 @@ def test_fixed_point_kernel_matches_golden(name, mode):
         assert torch.equal(F, F1)
 
 
+@pytest.mark.parametrize("name", ["ala2_nobox_rf", "thrombin_nobox_rf", "argon100_nocut", "chain_amber_vacuum"])
+def test_packed_kernel_without_a_box(name):
+    """TMD_B200_FX=2 on systems without a box: k_pair2_open (packed arithmetic on the float records; thrombin has
+    45 atom types and reads the LJ table from global memory).  Decisions are exact by construction: pairs bit-exact."""
+    g = load_golden(name)
+    f, pos, box, F, E = make_forces(g, 2)
+    f0, _, _, F0, E0 = make_forces(g, 0)
+    ref = g["forces_f64"]
+    scale = max(1.0, float(np.abs(ref).max()) / 100.0)
+    dev = np.abs(g["forces_f32"].astype(np.float64) - ref).max()
+    for tag, Fx in (("with energies", F.clone()), ("forces only", None)):
+        if Fx is None:
+            from torchmd_b200 import _lib
+            os.environ["TMD_B200_FX"] = "2"
+            try:
+                _lib.check(_lib.lib().tmd_forces(f._ctx, pos.data_ptr(), F.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("TMD_B200_FX", None)
+            Fx = F
+        err = np.abs(Fx.cpu().numpy().astype(np.float64) - ref).max()
+        err0 = np.abs(F0.cpu().numpy().astype(np.float64) - ref).max()
+        print(f"{name} ({tag}): max|dF| vs fp64 reference: packed {err:.3e}, float kernel {err0:.3e}")
+        assert err < max(1e-4 * scale, 1.2 * dev)
+    keys = [str(k) for k in g["energy_keys"]]
+    for r in range(len(E)):
+        for c, k in enumerate(keys):
+            e_ref = g["energies_f64"][r, c]
+            assert abs(E[r][k] - e_ref) <= 1e-5 * abs(e_ref) + 2e-3, (k, E[r][k], e_ref)
+    if "pairs_f32" in g:
+        assert np.array_equal(f.neighbour_pairs(pos, box).cpu().numpy(), g["pairs_f32"])
+
+
 def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
     """Molecules several boxes away from the primary cell: the float path loses ~1e-3 there
     (fl(L*n) for |n|>=3), the fixed-point path must stay below 1e-4."""

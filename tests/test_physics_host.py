@@ -364,3 +364,31 @@ def test_packed_coefficient_covers_every_lj_electrostatics_combination(hc, rfa, 
     assert np.abs(c - want).max() <= 4e-6 * max(1.0, np.abs(want).max())
     assert np.abs(elj - lj_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(lj_e.numpy()).max())
     assert np.abs(eel - el_e.numpy()).max() <= 3e-6 * max(1.0, np.abs(el_e.numpy()).max())
+
+
+def test_packed_arithmetic_without_a_box(hc):
+    """k_pair2_open's arithmetic (float records, reference differences, packed evaluation) on the alanine-dipeptide
+    fixture without a box: non-bonded forces against the fp64 oracle on the fp32 pair set."""
+    g = load_golden("ala2_nobox_rf")
+    cfg = golden_cfg(g)
+    par64 = __import__("conftest").params_from_golden(g, precision=torch.float64)
+    of = refmd.OracleForces(par64, ["lj", "electrostatics"], decision_dtype=torch.float32, **cfg)
+    pos = g["coords"].astype(F32).copy()
+    pos_t = torch.tensor(pos)[None]
+    f64 = torch.zeros(1, len(pos), 3, dtype=torch.float64)
+    of.compute(pos_t.double(), torch.zeros(1, 3, 3, dtype=torch.float64), f64)
+    pairs = of.neighbour_pairs(pos_t[0], torch.zeros(3)).numpy().astype(np.int32)
+    types = g["par_types"].astype(np.int32)
+    nt = int(types.max()) + 1
+    A, B = par64.get_AB()
+    AB = np.stack([A.numpy(), B.numpy()], -1).astype(F32).reshape(nt, nt, 2)
+    qs = (g["par_charges"] * math.sqrt(refmd.COULOMB)).astype(F32)
+    eps, rc = 78.5, cfg["cutoff"]
+    krf = (1 / rc**3) * (eps - 1) / (2 * eps + 1)
+    crf = (1 / rc) * (3 * eps) / (2 * eps + 1)
+    out = np.zeros((len(pos), 3), F32)
+    hc.hc_pair_forces(3, len(pos), len(pairs), p(np.ascontiguousarray(pairs)), p(pos), p(qs), p(types), nt, p(np.ascontiguousarray(AB)),
+                      p(np.ones(3, F32)), (1 << 5) | (1 << 6), C.c_float(rc), int(cfg["switch_dist"] is not None),
+                      C.c_float(cfg["switch_dist"] or 0.0), int(cfg["rfa"]), C.c_float(krf), C.c_float(crf), p(out))
+    err = np.abs(out.astype(np.float64) - f64[0].numpy()).max()
+    assert err < 1e-4, err

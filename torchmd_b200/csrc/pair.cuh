@@ -347,7 +347,24 @@ static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in t
                            // stall samples on the first use of a gathered record)
 #endif
 
-template <bool ENERGY>
+// (A_0, A_1), (B_0, B_1) of two partners: from the staged planes (<= 16 types) or from the table in global memory
+template <bool SMALLT>
+__device__ __forceinline__ void lj_pair_entries(unsigned ab_row, const float2* __restrict__ ab_global, bool lj_on, unsigned en0,
+                                                unsigned en1, F2& A, F2& B) {
+  if (SMALLT) {
+    const unsigned a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
+    asm("ld.shared.f32 %0, [%1];" : "=f"(A.x) : "r"(a0));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(A.y) : "r"(a1));
+    asm("ld.shared.f32 %0, [%1+1024];" : "=f"(B.x) : "r"(a0));
+    asm("ld.shared.f32 %0, [%1+1024];" : "=f"(B.y) : "r"(a1));
+  } else {
+    const float2 v0 = __ldg(ab_global + (en0 >> 24)), v1 = __ldg(ab_global + (en1 >> 24));
+    A = lj_on ? f2(v0.x, v1.x) : f2(0.f);  // (the staged planes are zeroed instead when the term is off)
+    B = lj_on ? f2(v0.y, v1.y) : f2(0.f);
+  }
+}
+
+template <bool ENERGY, bool SMALLT>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
 k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* __restrict__ energies) {
   const int r = blockIdx.y;
@@ -359,8 +376,8 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
 
   // LJ table staged as two planes (A, B): the packed operands (A_0, A_1), (B_0, B_1) of the two
   // partners are then loaded straight into register pairs
-  __shared__ float ab_s[2 * FX_SMALLT_MAX * FX_SMALLT_MAX];
-  if ((int)threadIdx.x < S.ntypes * S.ntypes) {
+  __shared__ float ab_s[SMALLT ? 2 * FX_SMALLT_MAX * FX_SMALLT_MAX : 1];
+  if (SMALLT && (int)threadIdx.x < S.ntypes * S.ntypes) {
     const float2 v = (S.pp.terms & T_LJ) ? S.AB[threadIdx.x] : make_float2(0.f, 0.f);  // term off: zero table
     ab_s[threadIdx.x] = v.x;
     ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
@@ -377,7 +394,9 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   const int n = S.nnbr[base + k];
   const int4 pi = xf[k];
   const float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
-  const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)(S.type_s[base + k] * S.ntypes) * 4u;
+  const int ti = S.type_s[base + k] * S.ntypes;
+  const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+  const float2* __restrict__ ab_global = S.AB + ti;  // used when the table is not staged
   const Grid* g = S.grid + r;
   const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
   const float margin = fmaf(g->fx_c1, __int_as_float(S.flags[r * F_COUNT + F_PMAX]), g->fx_c0);
@@ -400,17 +419,11 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
     if (v0 && !in0) s_skipped = fminf(s_skipped, s.x);
     if (v1 && !in1) s_skipped = fminf(s_skipped, s.y);
     if (in0 || in1) {
-      float2 ab0, ab1;  // (A,B) of partner 0 / partner 1
-      {
-        const unsigned a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
-        asm("ld.shared.f32 %0, [%1];" : "=f"(ab0.x) : "r"(a0));
-        asm("ld.shared.f32 %0, [%1];" : "=f"(ab1.x) : "r"(a1));
-        asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab0.y) : "r"(a0));
-        asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab1.y) : "r"(a1));
-      }
+      F2 A, B;
+      lj_pair_entries<SMALLT>(ab_row, ab_global, (S.pp.terms & T_LJ) != 0, en0, en1, A, B);
       const F2 nqq = f2_mul(f2(nqi), f2(__int_as_float(p0.w), __int_as_float(p1.w)));
       F2 elj, neel;
-      F2 nc = pair_coef2<ENERGY>(sc, s, nqq, f2(ab0.x, ab1.x), f2(ab0.y, ab1.y), f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+      F2 nc = pair_coef2<ENERGY>(sc, s, nqq, A, B, f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
                                  f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)), elj, neel);
       nc = f2(in0 ? nc.x : 0.f, in1 ? nc.y : 0.f);  // a select, not a product: the other half may hold inf/NaN
       FX = f2_fma(wx, nc, FX);
@@ -502,9 +515,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
         const float4 a = xq[k], b = xq[j];
         if (ref_inside(a.x, a.y, a.z, b.x, b.y, b.z, g->L[0], g->L[1], g->L[2], g->invL[0], g->invL[1], g->invL[2],
                        pp.s_max)) {
-          float2 ab;
-          asm("ld.shared.f32 %0, [%1];" : "=f"(ab.x) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
-          asm("ld.shared.f32 %0, [%1+1024];" : "=f"(ab.y) : "r"(ab_row + (((unsigned)entry >> 24) << 2)));
+          const float2 ab = __ldg(S.AB + ti + (entry >> 24));  // (pair_terms<0> ignores it when LJ is off)
           float rinv;
           const float dedr = pair_terms<0>(pp, s, qi * __int_as_float(pj.w), ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
           const float c = dedr * rinv;
@@ -530,6 +541,94 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
     double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
     block_accumulate<PAIR_WARPS>(0.5 * (double)e_el, E + TMD_E_ELECTROSTATICS, red);  // every pair is seen from both atoms
     block_accumulate<PAIR_WARPS>(0.5 * (double)e_lj, E + TMD_E_LJ, red);
+  }
+}
+
+// ---- systems without a box: packed fp32x2 arithmetic on the float records ------------------
+// Without periodicity the reference's separation is the plain rounded difference p_i - p_j and
+// its squared length fma(z,z,fma(y,y,x*x)) -- both exist as packed operations with identical
+// rounding per half, so the cutoff decision of two partners is taken exactly, together, with
+// no band and no second pass.  Same term coverage and table staging as k_pair_fx2.
+template <bool ENERGY, bool SMALLT>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX2_MINBLOCKS)
+k_pair2_open(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* __restrict__ energies) {
+  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int kk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  const int N = S.natoms;
+  const size_t base = (size_t)r * N;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
+
+  __shared__ float ab_s[SMALLT ? 2 * FX_SMALLT_MAX * FX_SMALLT_MAX : 1];
+  if (SMALLT && (int)threadIdx.x < S.ntypes * S.ntypes) {
+    const float2 v = (S.pp.terms & T_LJ) ? S.AB[threadIdx.x] : make_float2(0.f, 0.f);
+    ab_s[threadIdx.x] = v.x;
+    ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
+  }
+  asm volatile("" ::: "memory");
+  __syncthreads();
+  F2 ELJ = f2(0.f), NEEL = f2(0.f);
+  if (kk < S.own_n) {
+    const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
+    const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
+    const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
+    const int n = S.nnbr[base + k];
+    const float4 pi = xq[k];
+    const float nqi = (S.pp.terms & T_ELEC) ? -pi.w : 0.f;
+    const int ti = S.type_s[base + k] * S.ntypes;
+    const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+    const float2* __restrict__ ab_global = S.AB + ti;
+    const float s_max = S.pp.s_max;
+    F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);
+
+    int e = lane;
+    int j0 = (e < n) ? __ldcs(row + e) : -1;
+    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    while (e < n) {
+      const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
+      const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+      const bool v0 = j0 >= 0, v1 = j1 >= 0;
+      const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;  // an empty slot reads record 0 and is masked
+      const float4 p0 = xq[en0 & 0xffffffu], p1 = xq[en1 & 0xffffffu];
+      // the reference's rounded differences and squared length (forces.py:368-372), two partners per operation
+      const F2 wx = f2_add(f2(pi.x), f2(-p0.x, -p1.x));
+      const F2 wy = f2_add(f2(pi.y), f2(-p0.y, -p1.y));
+      const F2 wz = f2_add(f2(pi.z), f2(-p0.z, -p1.z));
+      const F2 s = f2_fma(wz, wz, f2_fma(wy, wy, f2_mul(wx, wx)));
+      const bool in0 = v0 && s.x <= s_max, in1 = v1 && s.y <= s_max;
+      if (in0 || in1) {
+        F2 A, B;
+        lj_pair_entries<SMALLT>(ab_row, ab_global, (S.pp.terms & T_LJ) != 0, en0, en1, A, B);
+        const F2 nqq = f2_mul(f2(nqi), f2(p0.w, p1.w));
+        F2 elj, neel;
+        F2 nc = pair_coef2<ENERGY>(sc, s, nqq, A, B, f2(rsqrt_seed(s.x), rsqrt_seed(s.y)),
+                                   f2(neg_rcp_seed(s.x), neg_rcp_seed(s.y)), elj, neel);
+        nc = f2(in0 ? nc.x : 0.f, in1 ? nc.y : 0.f);
+        FX = f2_fma(wx, nc, FX);
+        FY = f2_fma(wy, nc, FY);
+        FZ = f2_fma(wz, nc, FZ);
+        if (ENERGY) {
+          ELJ = f2_add(ELJ, f2(in0 ? elj.x : 0.f, in1 ? elj.y : 0.f));
+          NEEL = f2_add(NEEL, f2(in0 ? neel.x : 0.f, in1 ? neel.y : 0.f));
+        }
+      }
+      j0 = jn0;
+      j1 = jn1;
+      e += 64;
+    }
+    const float fx = warp_sum(FX.x + FX.y), fy = warp_sum(FY.x + FY.y), fz = warp_sum(FZ.x + FZ.y);
+    if (lane == 0) {
+      float* f = forces + (base + S.perm[base + k]) * 3;
+      f[0] = fx;
+      f[1] = fy;
+      f[2] = fz;
+    }
+  }
+  if (ENERGY) {
+    __shared__ double red[PAIR_WARPS];
+    double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
+    block_accumulate<PAIR_WARPS>(-0.5 * (double)(NEEL.x + NEEL.y), E + TMD_E_ELECTROSTATICS, red);  // every pair is seen from both atoms
+    block_accumulate<PAIR_WARPS>(0.5 * (double)(ELJ.x + ELJ.y), E + TMD_E_LJ, red);
   }
 }
 

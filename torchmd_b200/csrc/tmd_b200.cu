@@ -600,8 +600,10 @@ static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces
   const int th = PAIR_WARPS * 32;
   // TMD_B200_FX=2: packed fp32x2 arithmetic for the term sets made of "lj" and "electrostatics"
   const bool lj_el_only = ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0;
-  if (ctx->fx_packed && lj_el_only && !ctx->exact_gradient && small) {
-    k_pair_fx2<E><<<pg, th, 0, st>>>(ctx->d, make_switch_consts(ctx->d.pp), forces, energies);
+  if (ctx->fx_packed && lj_el_only && !ctx->exact_gradient && ctx->d.ntypes <= 128) {
+    const SwitchConsts sc = make_switch_consts(ctx->d.pp);
+    if (small) k_pair_fx2<E, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    else k_pair_fx2<E, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
     return;
   }
   if (ctx->pair_mode == 1) {
@@ -617,6 +619,16 @@ static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, d
   if (ctx->d.xf_s) {
     if (e) launch_pair_fx<true>(ctx, pg, st, forces, energies);
     else launch_pair_fx<false>(ctx, pg, st, forces, energies);
+  } else if (!ctx->periodic && ctx->fx_packed && ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0 &&
+             !ctx->exact_gradient) {
+    // TMD_B200_FX=2 without a box: packed fp32x2 arithmetic on the float records
+    const SwitchConsts sc = make_switch_consts(ctx->d.pp);
+    const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
+    const int th = PAIR_WARPS * 32;
+    if (e && small) k_pair2_open<true, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    else if (e) k_pair2_open<true, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    else if (small) k_pair2_open<false, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    else k_pair2_open<false, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
   } else if (!ctx->periodic) {
     if (e) launch_pair_mode<true, false, false>(ctx, pg, st, forces, energies);
     else launch_pair_mode<false, false, false>(ctx, pg, st, forces, energies);
