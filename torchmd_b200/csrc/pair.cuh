@@ -395,7 +395,8 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   const int4 pi = xf[k];
   const float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
   const int ti = S.type_s[base + k] * S.ntypes;
-  const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+  unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+  asm volatile("" : "+r"(ab_row));  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
   const float2* __restrict__ ab_global = S.AB + ti;  // used when the table is not staged
   const Grid* g = S.grid + r;
   const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
@@ -576,7 +577,8 @@ k_pair2_open(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double*
     const float4 pi = xq[k];
     const float nqi = (S.pp.terms & T_ELEC) ? -pi.w : 0.f;
     const int ti = S.type_s[base + k] * S.ntypes;
-    const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+    unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
+  asm volatile("" : "+r"(ab_row));  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
     const float2* __restrict__ ab_global = S.AB + ti;
     const float s_max = S.pp.s_max;
     F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);
