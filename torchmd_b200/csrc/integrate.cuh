@@ -8,6 +8,7 @@
 #pragma once
 #include "context.cuh"
 #include "pair.cuh"
+#include "ptx.cuh"
 
 namespace tmd {
 
@@ -40,15 +41,6 @@ struct PeerTable {
   unsigned* flags[TMD_MAX_PEERS];   // flag array of every rank: flags[p][q] = last step rank q finished pushing to p
   int world, rank;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // k_vv_first for the owned atoms, new positions stored into every rank's write buffer; the
 // last block to finish publishes this rank's step number in every rank's flag array.

@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include "context.cuh"
+#include "ptx.cuh"
 
 namespace tmd {
 
@@ -405,7 +406,8 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
 #if BT_CULL
   float rl2 = S.rlist2;
   int cap = S.row_cap;
-  asm volatile("" : "+f"(rl2), "+r"(cap));  // keep both in registers: the chunk loop otherwise re-reads them from the constant bank
+  TMD_PIN_F(rl2);  // keep both in registers: the chunk loop otherwise re-reads them from the constant bank
+  TMD_PIN_R(cap);
 #else
   const float rl2 = S.rlist2;
   const int cap = S.row_cap;
@@ -438,7 +440,7 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
     int count = sh.counts[ii];
 #if BT_CULL
     unsigned long long row_addr = reinterpret_cast<unsigned long long>(row);
-    asm volatile("" : "+l"(row_addr));  // one 64-bit base; a store address is then base + 4*slot
+    TMD_PIN_L(row_addr);  // one 64-bit base; a store address is then base + 4*slot
     // chunks whose bounding box is within the list radius of this atom (lane c tests chunks
     // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling.  `special`:
     // chunks whose index range can hold the atom itself or one of its exclusions -- only those
@@ -517,7 +519,7 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
       const int slot = count + __popc(m & lt);
 #if BT_CULL
       if (((m >> lane) & 1u) && slot < cap)
-        asm volatile("st.global.u32 [%0], %1;" ::"l"(row_addr + 4ull * (unsigned)slot), "r"(entry) : "memory");
+        stg_u32(row_addr + 4ull * (unsigned)slot, entry);
 #else
       if (((m >> lane) & 1u) && slot < cap) row[slot] = entry;
 #endif

@@ -12,6 +12,7 @@
 // cutoff decision uses the reference's exact fp32 predicate (physics.cuh).
 #pragma once
 #include "context.cuh"
+#include "ptx.cuh"
 
 namespace tmd {
 
@@ -181,11 +182,7 @@ constexpr int FX_SMALLT_MAX = 16;
 // Partner record of a replica's fixed-point array at byte offset `off` from `base` (an
 // integer the compiler cannot see through, so the replica's base stays in a register pair
 // instead of being re-derived per pair).
-__device__ __forceinline__ int4 fx_record(unsigned long long base, unsigned off) {
-  int4 v;
-  asm("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(base + off));
-  return v;
-}
+__device__ __forceinline__ int4 fx_record(unsigned long long base, unsigned off) { return ldg_s32x4(base + off); }
 
 template <bool ENERGY, int MODE, bool SMALLT>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_FX_MINBLOCKS)
@@ -203,7 +200,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
   if (SMALLT) {
     static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX <= PAIR_WARPS * 32, "one table entry per thread");
     if (S.AB && (int)threadIdx.x < S.ntypes * S.ntypes) ab_s[threadIdx.x] = S.AB[threadIdx.x];  // no table without an LJ-type term
-    asm volatile("" ::: "memory");  // the table is read back through inline PTX below: keep the stores
+    TMD_KEEP_STORES();  // the table is read back through lds_* below
     __syncthreads();
   }
 
@@ -211,13 +208,13 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
     const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
     const int4* __restrict__ xf = S.xf_s + (size_t)r * (N + 1);
     unsigned long long xf_base = reinterpret_cast<unsigned long long>(xf);
-    asm volatile("" : "+l"(xf_base));
+    TMD_PIN_L(xf_base);
     const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
     const int n = S.nnbr[base + k];
     const int4 pi = xf[k];
     const float qi = __int_as_float(pi.w);
     const int ti = S.type_s[base + k] * S.ntypes;
-    const unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 8u;  // this atom's row of the staged table
+    const smem_addr ab_row = smem_address(ab_s) + (unsigned)ti * 8u;  // this atom's row of the staged table
     const bool need_ab = MODE == 1 ? true : (pp.terms & (T_LJ | T_REP | T_REPCG)) != 0;
     const Grid* g = S.grid + r;
     const float ux = g->fx_unit[0], uy = g->fx_unit[1], uz = g->fx_unit[2];
@@ -232,7 +229,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
       float2 ab = make_float2(0.f, 0.f);
       if (need_ab) {
         if (SMALLT) {
-          asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ab.x), "=f"(ab.y) : "r"(ab_row + (((unsigned)entry >> 24) << 3)));
+          ab = lds_f32x2(ab_row + (((unsigned)entry >> 24) << 3));
         } else {
           ab = __ldg(S.AB + ti + (entry >> 24));
         }
@@ -349,14 +346,12 @@ static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in t
 
 // (A_0, A_1), (B_0, B_1) of two partners: from the staged planes (<= 16 types) or from the table in global memory
 template <bool SMALLT>
-__device__ __forceinline__ void lj_pair_entries(unsigned ab_row, const float2* __restrict__ ab_global, bool lj_on, unsigned en0,
+__device__ __forceinline__ void lj_pair_entries(smem_addr ab_row, const float2* __restrict__ ab_global, bool lj_on, unsigned en0,
                                                 unsigned en1, F2& A, F2& B) {
   if (SMALLT) {
-    const unsigned a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
-    asm("ld.shared.f32 %0, [%1];" : "=f"(A.x) : "r"(a0));
-    asm("ld.shared.f32 %0, [%1];" : "=f"(A.y) : "r"(a1));
-    asm("ld.shared.f32 %0, [%1+1024];" : "=f"(B.x) : "r"(a0));
-    asm("ld.shared.f32 %0, [%1+1024];" : "=f"(B.y) : "r"(a1));
+    const smem_addr a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
+    A = f2(lds_f32(a0), lds_f32(a1));
+    B = f2(lds_f32_plane1(a0), lds_f32_plane1(a1));
   } else {
     const float2 v0 = __ldg(ab_global + (en0 >> 24)), v1 = __ldg(ab_global + (en1 >> 24));
     A = lj_on ? f2(v0.x, v1.x) : f2(0.f);  // (the staged planes are zeroed instead when the term is off)
@@ -382,21 +377,21 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
     ab_s[threadIdx.x] = v.x;
     ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
   }
-  asm volatile("" ::: "memory");
+  TMD_KEEP_STORES();
   __syncthreads();
   float e_el = 0.f, e_lj = 0.f;
   if (kk < S.own_n) {
   const int k = S.own_all ? kk : S.inv[base + S.own_lo + kk];
   const int4* __restrict__ xf = S.xf_s + (size_t)r * (N + 1);
   unsigned long long xf_base = reinterpret_cast<unsigned long long>(xf);
-  asm volatile("" : "+l"(xf_base));
+  TMD_PIN_L(xf_base);
   const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
   const int n = S.nnbr[base + k];
   const int4 pi = xf[k];
   const float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
   const int ti = S.type_s[base + k] * S.ntypes;
-  unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
-  asm volatile("" : "+r"(ab_row));  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
+  smem_addr ab_row = smem_address(ab_s) + (unsigned)ti * 4u;
+  TMD_PIN_R(ab_row);  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
   const float2* __restrict__ ab_global = S.AB + ti;  // used when the table is not staged
   const Grid* g = S.grid + r;
   const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
@@ -566,7 +561,7 @@ k_pair2_open(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double*
     ab_s[threadIdx.x] = v.x;
     ab_s[FX_SMALLT_MAX * FX_SMALLT_MAX + threadIdx.x] = v.y;
   }
-  asm volatile("" ::: "memory");
+  TMD_KEEP_STORES();
   __syncthreads();
   F2 ELJ = f2(0.f), NEEL = f2(0.f);
   if (kk < S.own_n) {
@@ -577,8 +572,8 @@ k_pair2_open(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double*
     const float4 pi = xq[k];
     const float nqi = (S.pp.terms & T_ELEC) ? -pi.w : 0.f;
     const int ti = S.type_s[base + k] * S.ntypes;
-    unsigned ab_row = (unsigned)__cvta_generic_to_shared(ab_s) + (unsigned)ti * 4u;
-  asm volatile("" : "+r"(ab_row));  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
+    smem_addr ab_row = smem_address(ab_s) + (unsigned)ti * 4u;
+  TMD_PIN_R(ab_row);  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
     const float2* __restrict__ ab_global = S.AB + ti;
     const float s_max = S.pp.s_max;
     F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);

@@ -1,0 +1,69 @@
+// ptx.cuh -- the handful of inline-PTX idioms the kernels use, behind small wrappers.
+//
+// Device: exactly the instruction wanted (shared/global loads by explicit address, register
+// pinning against re-materialisation, system-scope release/acquire).  Host: plain C++ with the same
+// meaning -- used only when the kernels are compiled for the SIMT interpreter of tests/simt, which
+// runs the real kernel code on the CPU to check its logic without a GPU (test infrastructure; the
+// product never executes these alternatives).
+#pragma once
+#include <stdint.h>
+
+namespace tmd {
+
+#if defined(__CUDA_ARCH__)
+#define TMD_PIN_R(x) asm volatile("" : "+r"(x))  // keep a 32-bit integer / float / 64-bit value in a register:
+#define TMD_PIN_F(x) asm volatile("" : "+f"(x))  // the compiler can no longer re-derive it inside a loop
+#define TMD_PIN_L(x) asm volatile("" : "+l"(x))
+#define TMD_KEEP_STORES() asm volatile("" ::: "memory")  // shared-memory stores that are read back through lds_*
+
+typedef unsigned smem_addr;  // address in the CTA's shared window
+__device__ __forceinline__ smem_addr smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(smem_addr a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32_plane1(smem_addr a) {  // the same entry of the second 1 KiB plane
+  float v;
+  asm("ld.shared.f32 %0, [%1+1024];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(smem_addr a) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 ldg_s32x4(unsigned long long addr) {
+  int4 v;
+  asm("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
+  return v;
+}
+__device__ __forceinline__ void stg_u32(unsigned long long addr, int v) {
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#else
+#define TMD_PIN_R(x) ((void)0)
+#define TMD_PIN_F(x) ((void)0)
+#define TMD_PIN_L(x) ((void)0)
+#define TMD_KEEP_STORES() ((void)0)
+
+typedef const char* smem_addr;
+inline smem_addr smem_address(const void* p) { return static_cast<const char*>(p); }
+inline float lds_f32(smem_addr a) { return *reinterpret_cast<const float*>(a); }
+inline float lds_f32_plane1(smem_addr a) { return *reinterpret_cast<const float*>(a + 1024); }
+inline float2 lds_f32x2(smem_addr a) { return *reinterpret_cast<const float2*>(a); }
+inline int4 ldg_s32x4(unsigned long long addr) { return *reinterpret_cast<const int4*>(addr); }
+inline void stg_u32(unsigned long long addr, int v) { *reinterpret_cast<int*>(addr) = v; }
+inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#endif
+
+}  // namespace tmd

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "bonded.cuh"
@@ -43,6 +44,19 @@ int fail(int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                     \
       return fail(TMD_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
   } while (0)
+
+// Every kernel launch goes through here.  The product enqueues on the stream; the SIMT interpreter
+// build of tests/simt (TMD_SIMT_HOST: the same kernels compiled for the CPU to check their logic
+// without a GPU) runs the grid on the spot.
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+#if defined(TMD_SIMT_HOST)
+  (void)st;
+  simt::run_grid(grid, block, [&]() { kernel(args...); });
+#else
+  kernel<<<grid, block, 0, st>>>(std::forward<Args>(args)...);
+#endif
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -591,8 +605,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
 
 template <bool E, bool P, bool SAFE>
 static void launch_pair_mode(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
-  if (ctx->pair_mode == 1) k_pair<E, P, SAFE, 1><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
-  else k_pair<E, P, SAFE, 0><<<pg, PAIR_WARPS * 32, 0, st>>>(ctx->d, forces, energies);
+  if (ctx->pair_mode == 1) launch(k_pair<E, P, SAFE, 1>, pg, PAIR_WARPS * 32, st, ctx->d, forces, energies);
+  else launch(k_pair<E, P, SAFE, 0>, pg, PAIR_WARPS * 32, st, ctx->d, forces, energies);
 }
 template <bool E>
 static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
@@ -602,16 +616,16 @@ static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces
   const bool lj_el_only = ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0;
   if (ctx->fx_packed && lj_el_only && !ctx->exact_gradient && ctx->d.ntypes <= 128) {
     const SwitchConsts sc = make_switch_consts(ctx->d.pp);
-    if (small) k_pair_fx2<E, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
-    else k_pair_fx2<E, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    if (small) launch(k_pair_fx2<E, true>, pg, th, st, ctx->d, sc, forces, energies);
+    else launch(k_pair_fx2<E, false>, pg, th, st, ctx->d, sc, forces, energies);
     return;
   }
   if (ctx->pair_mode == 1) {
-    if (small) k_pair_fx<E, 1, true><<<pg, th, 0, st>>>(ctx->d, forces, energies);
-    else k_pair_fx<E, 1, false><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+    if (small) launch(k_pair_fx<E, 1, true>, pg, th, st, ctx->d, forces, energies);
+    else launch(k_pair_fx<E, 1, false>, pg, th, st, ctx->d, forces, energies);
   } else {
-    if (small) k_pair_fx<E, 0, true><<<pg, th, 0, st>>>(ctx->d, forces, energies);
-    else k_pair_fx<E, 0, false><<<pg, th, 0, st>>>(ctx->d, forces, energies);
+    if (small) launch(k_pair_fx<E, 0, true>, pg, th, st, ctx->d, forces, energies);
+    else launch(k_pair_fx<E, 0, false>, pg, th, st, ctx->d, forces, energies);
   }
 }
 static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
@@ -625,10 +639,10 @@ static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, d
     const SwitchConsts sc = make_switch_consts(ctx->d.pp);
     const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
     const int th = PAIR_WARPS * 32;
-    if (e && small) k_pair2_open<true, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
-    else if (e) k_pair2_open<true, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
-    else if (small) k_pair2_open<false, true><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
-    else k_pair2_open<false, false><<<pg, th, 0, st>>>(ctx->d, sc, forces, energies);
+    if (e && small) launch(k_pair2_open<true, true>, pg, th, st, ctx->d, sc, forces, energies);
+    else if (e) launch(k_pair2_open<true, false>, pg, th, st, ctx->d, sc, forces, energies);
+    else if (small) launch(k_pair2_open<false, true>, pg, th, st, ctx->d, sc, forces, energies);
+    else launch(k_pair2_open<false, false>, pg, th, st, ctx->d, sc, forces, energies);
   } else if (!ctx->periodic) {
     if (e) launch_pair_mode<true, false, false>(ctx, pg, st, forces, energies);
     else launch_pair_mode<false, false, false>(ctx, pg, st, forces, energies);
@@ -678,7 +692,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaEventRecord(pv.ev_fork, st));
     TMD_CUDA(cudaStreamWaitEvent(pv.side, pv.ev_fork, 0));
-    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, pv.side>>>(d, T, ctx->q, pos, forces, energies, pv.bonded_scratch);
+    launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, pv.side, d, T, ctx->q, pos, forces, energies, pv.bonded_scratch);
     TMD_LAUNCHED(ctx, "k_bonded");
     TMD_CUDA(cudaEventRecord(pv.ev_join, pv.side));
   }
@@ -699,7 +713,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_CUDA(cudaGraphConditionalHandleCreate(&handle, cap_graph, 0, cudaGraphCondAssignDefault));
       dp.cond = (unsigned long long)handle;
     }
-    k_prepare<<<atoms_grid(ctx, 256), 256, 0, st>>>(dp, pos);
+    launch(k_prepare, atoms_grid(ctx, 256), 256, st, dp, pos);
     TMD_LAUNCHED(ctx, "k_prepare");
     const int need_bounds = (!ctx->periodic && ctx->cutoff >= 0) ? 1 : 0;
     cudaStream_t rs = st;  // stream the rebuild kernels are enqueued on
@@ -730,23 +744,23 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_rebuild");
     } else {
       if (need_bounds) {
-        k_bounds<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d, pos);
+        launch(k_bounds, atoms_grid(ctx, 256), 256, rs, d, pos);
         TMD_LAUNCHED(ctx, "k_bounds");
-        k_grid<<<(R + 63) / 64, 64, 0, rs>>>(d);
+        launch(k_grid, (R + 63) / 64, 64, rs, d);
         TMD_LAUNCHED(ctx, "k_grid");
       }
-      k_bin<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d, pos);
+      launch(k_bin, atoms_grid(ctx, 256), 256, rs, d, pos);
       TMD_LAUNCHED(ctx, "k_bin");
-      k_scan<<<R, 1024, 0, rs>>>(d);
+      launch(k_scan, R, 1024, rs, d);
       TMD_LAUNCHED(ctx, "k_scan");
-      k_place<<<atoms_grid(ctx, 256), 256, 0, rs>>>(d);
+      launch(k_place, atoms_grid(ctx, 256), 256, rs, d);
       TMD_LAUNCHED(ctx, "k_place");
       {
         const int blocks = std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8));
-        k_sort_pack<<<dim3(blocks, R), 256, 0, rs>>>(d);
+        launch(k_sort_pack, dim3(blocks, R), 256, rs, d);
         TMD_LAUNCHED(ctx, "k_sort_pack");
       }
-      k_build_list<<<dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, 0, rs>>>(d);
+      launch(k_build_list, dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, rs, d);
       TMD_LAUNCHED(ctx, "k_build_list");
     }
     if (in_body) {
@@ -772,10 +786,10 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   if (overlap) {
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_join, 0));
-    k_add_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
+    launch(k_add_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
     TMD_LAUNCHED(ctx, "k_add_bonded");
   } else if (have_bonded) {
-    k_bonded<<<owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, 0, st>>>(d, T, ctx->q, pos, forces, energies, nullptr);
+    launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, d, T, ctx->q, pos, forces, energies, nullptr);
     TMD_LAUNCHED(ctx, "k_bonded");
   }
   return TMD_OK;
@@ -783,7 +797,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
 
 static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses,
                             double dt, cudaStream_t st) {
-  k_vv_first<<<owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(
+  launch(k_vv_first, owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, 
       ctx->natoms, ctx->d.own_lo, ctx->d.own_n, ctx->d.counters, pos, vel, forces, masses, (float)dt, (float)(0.5 * dt));
   TMD_LAUNCHED(ctx, "k_vv_first");
   return TMD_OK;
@@ -799,11 +813,11 @@ static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, cons
   const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-gamma);
   if (ke) TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
   if (thermo) {
-    if (ke) k_vv_second<true, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
-    else k_vv_second<true, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    if (ke) launch(k_vv_second<true, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else launch(k_vv_second<true, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
   } else {
-    if (ke) k_vv_second<false, true><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
-    else k_vv_second<false, false><<<g, INTEG_THREADS, 0, st>>>(ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    if (ke) launch(k_vv_second<false, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    else launch(k_vv_second<false, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
   }
   TMD_LAUNCHED(ctx, "k_vv_second");
   return TMD_OK;
@@ -841,7 +855,7 @@ int tmd_kinetic_energy(tmd_ctx* ctx, const float* vel, const float* masses, doub
   DeviceGuard guard(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
-  k_kinetic<<<owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, 0, st>>>(ctx->natoms, ctx->d.own_lo, ctx->d.own_n, vel, masses, ke);
+  launch(k_kinetic, owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, ctx->natoms, ctx->d.own_lo, ctx->d.own_n, vel, masses, ke);
   TMD_LAUNCHED(ctx, "k_kinetic");
   return TMD_OK;
 }
@@ -947,7 +961,7 @@ int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs
   DeviceGuard guard(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   TMD_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st));
-  k_export_pairs<<<(ctx->natoms + 3) / 4, 128, 0, st>>>(ctx->d, replica, pairs, (long long)capacity,
+  launch(k_export_pairs, (ctx->natoms + 3) / 4, 128, st, ctx->d, replica, pairs, (long long)capacity,
                                                        reinterpret_cast<unsigned long long*>(count));
   TMD_LAUNCHED(ctx, "k_export_pairs");
   return TMD_OK;
@@ -1045,7 +1059,7 @@ int tmd_dd_vv_first_push(tmd_ctx* ctx, int which_in, float* vel, const float* fo
     pt.flags[p] = dd_flags_of(ctx, p);
   }
   const unsigned blocks = (unsigned)((std::max(ctx->d.own_n, 1) + INTEG_THREADS - 1) / INTEG_THREADS);
-  k_vv_first_push<<<blocks, INTEG_THREADS, 0, (cudaStream_t)stream>>>(
+  launch(k_vv_first_push, blocks, INTEG_THREADS, (cudaStream_t)stream, 
       ctx->natoms, ctx->d.own_lo, ctx->d.own_n, ctx->d.counters, dd_pos_of(ctx, ctx->dd_rank, which_in), vel, forces,
       masses, (float)dt, (float)(0.5 * dt), pt, ctx->dd_sync);
   TMD_LAUNCHED(ctx, "k_vv_first_push");
@@ -1054,7 +1068,7 @@ int tmd_dd_vv_first_push(tmd_ctx* ctx, int which_in, float* vel, const float* fo
 
 int tmd_dd_wait(tmd_ctx* ctx, tmd_stream stream) {
   TMD_DD_READY("tmd_dd_wait")
-  k_wait_peers<<<1, 32, 0, (cudaStream_t)stream>>>(dd_flags_of(ctx, ctx->dd_rank), ctx->dd_sync, ctx->dd_world,
+  launch(k_wait_peers, 1, 32, (cudaStream_t)stream, dd_flags_of(ctx, ctx->dd_rank), ctx->dd_sync, ctx->dd_world,
                                                     ctx->d.flags + F_PEERWAIT);
   TMD_LAUNCHED(ctx, "k_wait_peers");
   return TMD_OK;
@@ -1105,8 +1119,8 @@ int tmd_wrapper_wrap(tmd_wrapper* w, float* pos, const float* box, int nrep, tmd
   if (w->ngroups == 0) return TMD_OK;
   DeviceGuard guard(w->device);
   cudaStream_t st = (cudaStream_t)stream;
-  k_wrap_boxflag<<<1, 256, 0, st>>>(box, nrep, w->flag);
-  k_wrap<<<dim3((unsigned)((w->ngroups + WRAP_WARPS - 1) / WRAP_WARPS), (unsigned)nrep), WRAP_WARPS * 32, 0, st>>>(
+  launch(k_wrap_boxflag, 1, 256, st, box, nrep, w->flag);
+  launch(k_wrap, dim3((unsigned)((w->ngroups + WRAP_WARPS - 1) / WRAP_WARPS), (unsigned)nrep), WRAP_WARPS * 32, st, 
       w->natoms, w->ngroups, w->group_ptr, w->group_atoms, pos, box, w->flag);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("launch k_wrap: ") + cudaGetErrorString(e));
