@@ -231,6 +231,11 @@ int tmd_wrapper_destroy(tmd_wrapper* w);
 int tmd_export_pairs(tmd_ctx* ctx, const float* pos_dev, int replica, int32_t* pairs_dev,
                      int64_t capacity, int64_t* count_dev, tmd_stream stream);
 
+/* Which pair kernel the last tmd_forces / tmd_md_steps launched: 0 k_pair (float separations, the
+ * default), 1 k_pair_fx (fixed-point separations), 2 k_pair_fx2 (fixed point + packed fp32x2
+ * arithmetic), 3 k_pair2_open (no box, packed arithmetic).  For tests and bench labels. */
+int tmd_pair_kernel(tmd_ctx* ctx);
+
 typedef struct {
   int64_t rebuilds;        /* neighbour-list rebuilds so far (all replicas) */
   int64_t force_calls;     /* tmd_forces invocations */

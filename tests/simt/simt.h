@@ -1,0 +1,282 @@
+// simt.h -- a small SIMT interpreter: runs a CUDA kernel's threads as cooperative fibers on ONE host
+// thread, with real warp and block collectives.  TEST INFRASTRUCTURE (tests/simt): it lets the unit
+// tests execute the actual kernel sources of torchmd_b200/csrc on the CPU to check their LOGIC
+// (indexing, masks, list building, band handling, double buffering ...) without a GPU.  It says
+// nothing about performance and is never part of the product.
+//
+// Model: blocks of a grid run one after the other; the threads of a block are ucontext fibers
+// scheduled round-robin; a fiber runs until it reaches a collective (__shfl*/__ballot/... or
+// __syncthreads) where it parks until every live participant has arrived.  Threads that have
+// returned do not take part (CUDA semantics).  __activemask() first lets every other fiber advance
+// to its next parking point, then reports the lanes of the warp that are still alive.
+#pragma once
+#include <ucontext.h>
+
+#include <functional>
+#include <memory>
+#include <vector>
+
+namespace simt {
+
+struct uint3_ { unsigned x, y, z; };
+
+enum Kind { K_NONE, K_BALLOT, K_ANY, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_RMIN, K_RMAX, K_SYNCWARP };
+
+struct Warp {
+  unsigned live = 0;       // lanes that have not returned
+  unsigned arrived = 0;    // lanes parked at the current collective
+  unsigned req_mask = 0;   // mask argument of the current collective
+  unsigned gen = 0;        // bumped when a collective completes
+  int kind = K_NONE;
+  unsigned long long in[32], aux[32], out[32];
+};
+
+struct Fiber {
+  ucontext_t ctx;
+  std::unique_ptr<char[]> stack;
+  bool done = false;
+};
+
+struct Block {
+  dim3 grid, block, bidx;
+  int nthreads = 0;
+  std::vector<Fiber> fibers;
+  std::vector<Warp> warps;
+  ucontext_t sched;
+  int cur = -1;           // running fiber
+  int live = 0;           // threads that have not returned
+  int bar_arrived = 0;    // __syncthreads
+  unsigned bar_gen = 0;
+  int bar_or = 0, bar_or_result = 0;
+  const std::function<void()>* body = nullptr;
+  long long clock = 0;
+};
+
+inline Block*& current() {
+  static Block* b = nullptr;
+  return b;
+}
+inline int tid() { return current()->cur; }
+inline int lane() { return current()->cur & 31; }
+inline Warp& warp() { return current()->warps[current()->cur >> 5]; }
+inline void yield() {
+  Block* b = current();
+  swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+}
+inline long long fake_clock() { return current()->clock += 1000; }
+
+inline void complete(Warp& w) {
+  const unsigned part = w.arrived;
+  switch (w.kind) {
+    case K_BALLOT: {
+      unsigned r = 0;
+      for (int l = 0; l < 32; ++l)
+        if ((part >> l & 1u) && w.in[l]) r |= 1u << l;
+      for (int l = 0; l < 32; ++l) w.out[l] = r;
+      break;
+    }
+    case K_ANY: {
+      unsigned long long r = 0;
+      for (int l = 0; l < 32; ++l)
+        if ((part >> l & 1u) && w.in[l]) r = 1;
+      for (int l = 0; l < 32; ++l) w.out[l] = r;
+      break;
+    }
+    case K_SHFL:
+      for (int l = 0; l < 32; ++l) w.out[l] = w.in[w.aux[l] & 31];
+      break;
+    case K_SHFL_XOR:
+      for (int l = 0; l < 32; ++l) w.out[l] = w.in[(l ^ (int)w.aux[l]) & 31];
+      break;
+    case K_SHFL_UP:
+      for (int l = 0; l < 32; ++l) w.out[l] = (l >= (int)w.aux[l]) ? w.in[l - (int)w.aux[l]] : w.in[l];
+      break;
+    case K_RMIN:
+    case K_RMAX: {
+      bool first = true;
+      long long r = 0;
+      for (int l = 0; l < 32; ++l)
+        if (part >> l & 1u) {
+          const long long v = (long long)w.in[l];
+          if (first || (w.kind == K_RMIN ? v < r : v > r)) r = v;
+          first = false;
+        }
+      for (int l = 0; l < 32; ++l) w.out[l] = (unsigned long long)r;
+      break;
+    }
+    default:
+      break;
+  }
+  w.arrived = 0;
+  w.kind = K_NONE;
+  w.gen++;
+}
+
+// One warp collective: every live lane of `mask` deposits (value, aux) and gets out[lane].
+inline unsigned long long collective(int kind, unsigned mask, unsigned long long value, unsigned long long aux) {
+  Warp& w = warp();
+  const int l = lane();
+  const unsigned mygen = w.gen;
+  w.kind = kind;
+  w.req_mask = mask;
+  w.in[l] = value;
+  w.aux[l] = aux;
+  w.arrived |= 1u << l;
+  if (w.arrived == (mask & w.live)) complete(w);
+  else
+    while (w.gen == mygen) yield();
+  return w.out[l];
+}
+
+inline void block_barrier(int pred) {
+  Block* b = current();
+  const unsigned mygen = b->bar_gen;
+  b->bar_or |= (pred != 0);
+  if (++b->bar_arrived == b->live) {
+    b->bar_or_result = b->bar_or;
+    b->bar_or = 0;
+    b->bar_arrived = 0;
+    b->bar_gen++;
+  } else {
+    while (b->bar_gen == mygen) yield();
+  }
+}
+
+inline void fiber_main() {
+  Block* b = current();
+  (*b->body)();
+  // the thread returns: it leaves its warp and the block; collectives the others wait in may complete now
+  const int t = b->cur;
+  Warp& w = b->warps[t >> 5];
+  w.live &= ~(1u << (t & 31));
+  b->live--;
+  b->fibers[t].done = true;
+  if (w.arrived && w.arrived == (w.req_mask & w.live)) complete(w);
+  if (b->live > 0 && b->bar_arrived == b->live) {
+    b->bar_or_result = b->bar_or;
+    b->bar_or = 0;
+    b->bar_arrived = 0;
+    b->bar_gen++;
+  }
+  swapcontext(&b->fibers[t].ctx, &b->sched);
+}
+
+inline void run_block(Block& b) {
+  constexpr size_t STACK = 192 * 1024;
+  b.nthreads = (int)(b.block.x * b.block.y * b.block.z);
+  b.fibers.clear();
+  b.fibers.resize(b.nthreads);
+  b.warps.assign((b.nthreads + 31) / 32, Warp());
+  b.live = b.nthreads;
+  b.bar_arrived = 0;
+  b.bar_or = 0;
+  for (int t = 0; t < b.nthreads; ++t) {
+    Fiber& f = b.fibers[t];
+    f.stack.reset(new char[STACK]);
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.get();
+    f.ctx.uc_stack.ss_size = STACK;
+    f.ctx.uc_link = &b.sched;
+    makecontext(&f.ctx, (void (*)())fiber_main, 0);
+    b.warps[t >> 5].live |= 1u << (t & 31);
+  }
+  Block* saved = current();
+  current() = &b;
+  int remaining = b.nthreads;
+  long long idle_rounds = 0;
+  while (remaining > 0) {
+    int progressed = 0;
+    for (int t = 0; t < b.nthreads; ++t) {
+      if (b.fibers[t].done) continue;
+      b.cur = t;
+      swapcontext(&b.sched, &b.fibers[t].ctx);
+      if (b.fibers[t].done) {
+        --remaining;
+        ++progressed;
+      }
+    }
+    // a full round in which nobody finished is normal (threads parked at collectives make progress
+    // without finishing); a very long streak means a deadlock in the kernel under test
+    idle_rounds = progressed ? 0 : idle_rounds + 1;
+    if (idle_rounds > 50000000) {
+      fprintf(stderr, "simt: no thread finished for 5e7 scheduler rounds -- deadlock in the kernel under test?\n");
+      abort();
+    }
+  }
+  current() = saved;
+}
+
+template <typename F>
+inline void run_grid(dim3 grid, dim3 block, F&& f) {
+  const std::function<void()> body(f);
+  for (unsigned z = 0; z < grid.z; ++z)
+    for (unsigned y = 0; y < grid.y; ++y)
+      for (unsigned x = 0; x < grid.x; ++x) {
+        Block b;
+        b.grid = grid;
+        b.block = block;
+        b.bidx = dim3(x, y, z);
+        b.body = &body;
+        run_block(b);
+      }
+}
+
+struct ThreadIdxProxy {
+  struct X { operator unsigned() const { return (unsigned)tid() % current()->block.x; } } x;
+  struct Y { operator unsigned() const { return ((unsigned)tid() / current()->block.x) % current()->block.y; } } y;
+  struct Z { operator unsigned() const { return (unsigned)tid() / (current()->block.x * current()->block.y); } } z;
+};
+struct BlockIdxProxy {
+  struct X { operator unsigned() const { return current()->bidx.x; } } x;
+  struct Y { operator unsigned() const { return current()->bidx.y; } } y;
+  struct Z { operator unsigned() const { return current()->bidx.z; } } z;
+};
+struct BlockDimProxy {
+  struct X { operator unsigned() const { return current()->block.x; } } x;
+  struct Y { operator unsigned() const { return current()->block.y; } } y;
+  struct Z { operator unsigned() const { return current()->block.z; } } z;
+};
+struct GridDimProxy {
+  struct X { operator unsigned() const { return current()->grid.x; } } x;
+  struct Y { operator unsigned() const { return current()->grid.y; } } y;
+  struct Z { operator unsigned() const { return current()->grid.z; } } z;
+};
+
+}  // namespace simt
+
+static simt::ThreadIdxProxy threadIdx;
+static simt::BlockIdxProxy blockIdx;
+static simt::BlockDimProxy blockDim;
+static simt::GridDimProxy gridDim;
+
+// ---- collectives in CUDA spelling -----------------------------------------------------------------
+inline void __syncthreads() { simt::block_barrier(0); }
+inline int __syncthreads_or(int p) {
+  simt::block_barrier(p);
+  return simt::current()->bar_or_result;
+}
+inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::collective(simt::K_SYNCWARP, mask, 0, 0); }
+inline unsigned __ballot_sync(unsigned mask, int p) { return (unsigned)simt::collective(simt::K_BALLOT, mask, p != 0, 0); }
+inline int __any_sync(unsigned mask, int p) { return (int)simt::collective(simt::K_ANY, mask, p != 0, 0); }
+inline unsigned __activemask() {
+  simt::yield();  // let every other thread reach its next parking point (or return) first
+  return simt::warp().live;
+}
+template <typename T>
+inline unsigned long long simt_bits(T v) {
+  unsigned long long b = 0;
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  memcpy(&b, &v, sizeof(T));
+  return b;
+}
+template <typename T>
+inline T simt_unbits(unsigned long long b) {
+  T v;
+  memcpy(&v, &b, sizeof(T));
+  return v;
+}
+template <typename T> inline T __shfl_sync(unsigned mask, T v, int src) { return simt_unbits<T>(simt::collective(simt::K_SHFL, mask, simt_bits(v), (unsigned)src)); }
+template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int m) { return simt_unbits<T>(simt::collective(simt::K_SHFL_XOR, mask, simt_bits(v), (unsigned)m)); }
+template <typename T> inline T __shfl_up_sync(unsigned mask, T v, unsigned d) { return simt_unbits<T>(simt::collective(simt::K_SHFL_UP, mask, simt_bits(v), d)); }
+inline int __reduce_min_sync(unsigned mask, int v) { return (int)(long long)simt::collective(simt::K_RMIN, mask, (unsigned long long)(long long)v, 0); }
+inline int __reduce_max_sync(unsigned mask, int v) { return (int)(long long)simt::collective(simt::K_RMAX, mask, (unsigned long long)(long long)v, 0); }

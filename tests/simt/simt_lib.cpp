@@ -1,0 +1,9 @@
+// The whole C-ABI library compiled for the host SIMT interpreter -- TEST INFRASTRUCTURE.
+//   g++ -std=c++17 -O1 -fPIC -shared -ffp-contract=off -I tests/simt/stub -I torchmd_b200/csrc -o tests/simt/libtmd_simt.so tests/simt/simt_lib.cpp
+// tests/simt/stub/cuda_runtime.h shadows the CUDA header: kernels become plain functions, launches
+// run in simt.h's interpreter, "device" memory is host memory.  tests/test_simt_kernels.py drives
+// the C ABI with numpy arrays to check the kernels' logic on the CPU.  tmd_version() returns -100
+// here, and torchmd_b200/_lib.py refuses to load a library that says so: this is not a CPU path of
+// the product.
+#define TMD_SIMT_HOST 1
+#include "../../torchmd_b200/csrc/tmd_b200.cu"

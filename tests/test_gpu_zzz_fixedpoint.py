@@ -27,6 +27,16 @@ PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water
                   "chain_charmm_periodic", "adversarial_cutoff", "ala2_xsc_rf"]
 
 
+def _lib_mod():
+    from torchmd_b200 import _lib
+
+    return _lib
+
+
+# systems whose box only meets the guard-free image condition (cutoff + 2 skin < 0.45 L) with a thin skin
+THIN_SKIN = {"water999_eq": 0.2}
+
+
 def make_forces(g, fx, **kw):
     """fx: 0 float kernel, 1 fixed-point kernel, 2 fixed-point + packed fp32x2 arithmetic (k_pair_fx2, taken
     for every lj/electrostatics term set with <= 16 atom types; other systems fall back to the fixed-point kernel)."""
@@ -40,6 +50,7 @@ def make_forces(g, fx, **kw):
         pos, box = golden_system_tensors(g, torch.float32, DEV)
         F = torch.full_like(pos, 7.0)
         E = f.compute(pos, box, F, returnDetails=True)  # the context reads the switch when it is finalised here
+        f.pair_kernel = _lib_mod().lib().tmd_pair_kernel(f._ctx)  # 0 float, 1 fixed point, 2 packed, 3 packed without a box
     finally:
         if old is None:
             os.environ.pop("TMD_B200_FX", None)
@@ -52,8 +63,13 @@ def make_forces(g, fx, **kw):
 @pytest.mark.parametrize("name", PERIODIC_CASES)
 def test_fixed_point_kernel_matches_golden(name, mode):
     g = load_golden(name)
-    f, pos, box, F, E = make_forces(g, mode)
-    f0, _, _, F0, E0 = make_forces(g, 0)
+    kw = {"skin": THIN_SKIN[name]} if name in THIN_SKIN else {}
+    f, pos, box, F, E = make_forces(g, mode, **kw)
+    f0, _, _, F0, E0 = make_forces(g, 0, **kw)
+    # boxes below (cutoff + 2 skin) / 0.45 keep the float kernel by design (guard-free image condition)
+    expect = 0 if name in ("water291_plain", "water291_rf_switch", "ala2_xsc_rf") else mode
+    assert f.pair_kernel == expect, f"pair kernel {f.pair_kernel} ran instead of {expect}"
+    assert f0.pair_kernel == 0
     if mode == 2:  # also the force-only instantiation of the packed kernel
         os.environ["TMD_B200_FX"] = "2"
         try:
@@ -92,6 +108,7 @@ def test_packed_kernel_without_a_box(name):
     g = load_golden(name)
     f, pos, box, F, E = make_forces(g, 2)
     f0, _, _, F0, E0 = make_forces(g, 0)
+    assert f.pair_kernel == (3 if not np.any(g["box"]) else 0) and f0.pair_kernel == 0  # (argon100_nocut: box without cutoff)
     ref = g["forces_f64"]
     scale = max(1.0, float(np.abs(ref).max()) / 100.0)
     dev = np.abs(g["forces_f32"].astype(np.float64) - ref).max()
@@ -118,6 +135,39 @@ def test_packed_kernel_without_a_box(name):
         assert np.array_equal(f.neighbour_pairs(pos, box).cpu().numpy(), g["pairs_f32"])
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fixed_point_kernels_on_a_3000_atom_water_box(mode):
+    """A generated 1000-water box (L = 31 A: eligible with the default skin) against the oracle."""
+    from torchmd_b200 import Forces, System, testsystems
+
+    sysd = testsystems.water_box(1000, seed=1)
+    terms = ["lj", "electrostatics", "bonds", "angles"]
+    cfg = dict(cutoff=9.0, rfa=True, switch_dist=7.5)
+    os.environ["TMD_B200_FX"] = str(mode)
+    try:
+        par = testsystems.water_parameters(sysd, device=DEV)
+        system = System(len(sysd["coords"]), 1, torch.float32, DEV)
+        system.set_positions(sysd["coords"])
+        system.set_box(sysd["box"])
+        f = Forces(par, terms=terms, **cfg)
+        e = f.compute(system.pos, system.box, system.forces, returnDetails=True)[0]
+        assert _lib_mod().lib().tmd_pair_kernel(f._ctx) == mode
+        pairs = f.neighbour_pairs(system.pos, system.box).cpu().numpy()
+    finally:
+        os.environ.pop("TMD_B200_FX", None)
+    of = refmd.OracleForces(testsystems.water_parameters(sysd, precision=torch.float64), terms, decision_dtype=torch.float32, **cfg)
+    f64 = torch.zeros(system.pos.shape, dtype=torch.float64)
+    e_ref = of.compute(system.pos.cpu().double(), system.box.cpu().double(), f64)[0]
+    err = (system.forces.cpu().double() - f64).abs().max().item()
+    print(f"3000-atom water, TMD_B200_FX={mode}: max|dF| vs fp64 oracle {err:.3e}, max|F| {f64.abs().max():.0f}")
+    assert err < 1e-4 * max(1.0, f64.abs().max().item() / 100.0)
+    for k in terms:
+        assert abs(e[k] - float(e_ref[k])) <= 2e-5 * max(1.0, abs(float(e_ref[k]))) + 2e-3, k
+    of32 = refmd.OracleForces(testsystems.water_parameters(sysd, precision=torch.float32), terms, **cfg)
+    ref_pairs = of32.neighbour_pairs(system.pos[0].cpu(), torch.diagonal(system.box[0]).cpu()).numpy().astype(np.int32)
+    assert np.array_equal(pairs, ref_pairs)
+
+
 def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
     """Molecules several boxes away from the primary cell: the float path loses ~1e-3 there
     (fl(L*n) for |n|>=3), the fixed-point path must stay below 1e-4."""
@@ -142,7 +192,7 @@ def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
     for mode in ("1", "2"):
         os.environ["TMD_B200_FX"] = mode
         try:
-            f = Forces(params_from_golden(g, precision=torch.float32, device=DEV), terms=terms, **cfg)
+            f = Forces(params_from_golden(g, precision=torch.float32, device=DEV), terms=terms, skin=0.2, **cfg)
             pos, bx = pos_c.to(DEV), box_c.to(DEV)
             F = torch.zeros_like(pos)
             f.compute(pos, bx, F)
@@ -152,6 +202,7 @@ def test_fixed_point_kernel_is_accurate_for_drifted_molecules():
                 torch.cuda.synchronize()
         finally:
             os.environ.pop("TMD_B200_FX", None)
+        assert _lib_mod().lib().tmd_pair_kernel(f._ctx) == int(mode)
         err = (F.cpu().double() - f64).abs().max().item()
         print(f"drifted molecules, TMD_B200_FX={mode}: max|dF| vs fp64 oracle {err:.3e}")
         assert err < 1e-4
@@ -174,7 +225,7 @@ def test_fixed_point_trajectory_tracks_float_kernel():
             s.set_positions(g["coords"])
             s.set_box(g["box"])
             s.set_velocities(torch.tensor(g["vel"])[None])
-            f = Forces(par, terms=[str(t) for t in g["terms"]], **cfg)
+            f = Forces(par, terms=[str(t) for t in g["terms"]], skin=0.2, **cfg)
             integ = Integrator(s, f, 1.0, DEV, gamma=None, T=None)
             ek, ep, T = integ.step(niter=100)
             out.append((s.pos.cpu().clone(), float(ek[0]), float(ep[0])))

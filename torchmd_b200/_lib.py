@@ -73,6 +73,7 @@ _SIGNATURES = {
     "tmd_get_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "tmd_set_owned_atoms": (C.c_int, [_P, C.c_int, C.c_int]),
     "tmd_set_force_convention": (C.c_int, [_P, C.c_int]),
+    "tmd_pair_kernel": (C.c_int, [_P]),
     "tmd_dd_create": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "tmd_dd_connect": (C.c_int, [_P, _P]),
     "tmd_dd_load": (C.c_int, [_P, C.c_int, _P, _P]),
@@ -106,6 +107,11 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.tmd_version() < 100:
+            raise ImportError(
+                f"{LIB_PATH} is the host SIMT-interpreter build of the kernels (tests/simt, a unit-test tool): "
+                "torchmd_b200 runs on the CUDA library only"
+            )
         _lib = handle
     return _lib
 

@@ -119,6 +119,7 @@ struct tmd_ctx {
   int coop_blocks = 0;               // CTAs per replica of the cooperative rebuild kernel (0: separate kernels)
   int pair_mode = 0;                 // 1: LJ+switch + reaction-field Coulomb specialisation
   int exact_gradient = 0;            // tmd_set_force_convention: switched-LJ force as the true gradient
+  int last_pair_kernel = 0;          // tmd_pair_kernel(): 0 float (k_pair), 1 k_pair_fx, 2 k_pair_fx2, 3 k_pair2_open
   bool fx_packed = false;            // TMD_B200_FX=2: k_pair_fx2 (packed fp32x2 arithmetic) where it applies
   int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
   // peer-to-peer position exchange (tmd_dd_*): one cudaMalloc holding [pos0 | pos1 | flags | sync]

@@ -156,7 +156,11 @@ static void dd_release(tmd_ctx* ctx) {
 extern "C" {
 
 const char* tmd_last_error(void) { return g_err.c_str(); }
+#if defined(TMD_SIMT_HOST)
+int tmd_version(void) { return -100; }  // host SIMT interpreter build (tests/simt): torchmd_b200/_lib.py refuses it
+#else
 int tmd_version(void) { return 100; }
+#endif
 
 int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   if (!out || natoms <= 0 || nreplicas <= 0) return fail(TMD_ERR_ARG, "tmd_create: bad arguments");
@@ -615,11 +619,13 @@ static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces
   // TMD_B200_FX=2: packed fp32x2 arithmetic for the term sets made of "lj" and "electrostatics"
   const bool lj_el_only = ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0;
   if (ctx->fx_packed && lj_el_only && !ctx->exact_gradient && ctx->d.ntypes <= 128) {
+    ctx->last_pair_kernel = 2;
     const SwitchConsts sc = make_switch_consts(ctx->d.pp);
     if (small) launch(k_pair_fx2<E, true>, pg, th, st, ctx->d, sc, forces, energies);
     else launch(k_pair_fx2<E, false>, pg, th, st, ctx->d, sc, forces, energies);
     return;
   }
+  ctx->last_pair_kernel = 1;
   if (ctx->pair_mode == 1) {
     if (small) launch(k_pair_fx<E, 1, true>, pg, th, st, ctx->d, forces, energies);
     else launch(k_pair_fx<E, 1, false>, pg, th, st, ctx->d, forces, energies);
@@ -630,12 +636,14 @@ static void launch_pair_fx(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces
 }
 static void launch_pair(tmd_ctx* ctx, dim3 pg, cudaStream_t st, float* forces, double* energies) {
   const bool e = energies != nullptr;
+  ctx->last_pair_kernel = 0;
   if (ctx->d.xf_s) {
     if (e) launch_pair_fx<true>(ctx, pg, st, forces, energies);
     else launch_pair_fx<false>(ctx, pg, st, forces, energies);
   } else if (!ctx->periodic && ctx->fx_packed && ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0 &&
              !ctx->exact_gradient) {
     // TMD_B200_FX=2 without a box: packed fp32x2 arithmetic on the float records
+    ctx->last_pair_kernel = 3;
     const SwitchConsts sc = make_switch_consts(ctx->d.pp);
     const bool small = ctx->d.ntypes <= FX_SMALLT_MAX;
     const int th = PAIR_WARPS * 32;
@@ -966,6 +974,8 @@ int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs
   TMD_LAUNCHED(ctx, "k_export_pairs");
   return TMD_OK;
 }
+
+int tmd_pair_kernel(tmd_ctx* ctx) { return ctx ? ctx->last_pair_kernel : -1; }
 
 int tmd_set_force_convention(tmd_ctx* ctx, int exact_gradient) {
   if (!ctx) return fail(TMD_ERR_ARG, "tmd_set_force_convention: null context");

@@ -165,6 +165,14 @@ class Forces:
         handle = C.c_void_p()
         _lib.check(L.tmd_create(C.byref(handle), key[0], self.natoms, nrep))
         ctx = handle
+        self._configure(L, ctx, _lib.check)
+        self._ctx, self._ctx_key, self._box_key = ctx, key, None
+        self._exact_gradient = False
+        return ctx
+
+    def _configure(self, L, ctx, check):
+        """Hand topology and parameters to a fresh context (every tmd_set_* call; host data only).
+        ``L`` is the bound library, ``check`` raises on a non-zero return code."""
         par = self.par
         charges = _np(par.charges, np.float32)
         if par.mapped_atom_types is not None:
@@ -179,13 +187,13 @@ class Forces:
                 par.A, par.B = par.get_AB()
             A, B = _np(par.A, np.float32), _np(par.B, np.float32)
             ntypes = A.shape[0]
-        _lib.check(L.tmd_set_atoms(ctx, _lib.ptr(charges), _lib.ptr(types), ntypes, _lib.ptr(A), _lib.ptr(B)))
+        check(L.tmd_set_atoms(ctx, _lib.ptr(charges), _lib.ptr(types), ntypes, _lib.ptr(A), _lib.ptr(B)))
 
         if self.require_distances:
             row_ptr, cols = _exclusion_csr(self.natoms, par.get_exclusions(self._exclusion_types))
-            _lib.check(L.tmd_set_exclusions(ctx, _lib.ptr(row_ptr), _lib.ptr(cols)))
+            check(L.tmd_set_exclusions(ctx, _lib.ptr(row_ptr), _lib.ptr(cols)))
 
-        _lib.check(
+        check(
             L.tmd_set_nonbonded(
                 ctx,
                 _lib.term_mask(self.energies),
@@ -208,10 +216,10 @@ class Forces:
 
         if "bonds" in self.energies and par.bond_params is not None:
             idx, _, prm = instance_rows(par.bond_params)
-            _lib.check(L.tmd_set_bonds(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
+            check(L.tmd_set_bonds(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
         if "angles" in self.energies and par.angle_params is not None:
             idx, _, prm = instance_rows(par.angle_params)
-            _lib.check(L.tmd_set_angles(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
+            check(L.tmd_set_angles(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
         for which, name, term in (
             (0, "dihedrals", par.dihedral_params),
             (1, "impropers", par.improper_params),
@@ -221,16 +229,12 @@ class Forces:
                 counts = np.bincount(rows, minlength=len(idx))
                 term_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
                 amber = bool(np.all(prm[:, 2] > 0))  # forces.py:566, decided over the whole set
-                _lib.check(
+                check(
                     L.tmd_set_torsions(ctx, which, len(idx), _lib.ptr(idx), _lib.ptr(term_ptr), _lib.ptr(prm), int(amber))
                 )
         if "1-4" in self.energies and par.nonbonded_14_params is not None and len(par.nonbonded_14_params["idx"]):
             idx, _, prm = instance_rows(par.nonbonded_14_params)
-            _lib.check(L.tmd_set_pairs14(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
-
-        self._ctx, self._ctx_key, self._box_key = ctx, key, None
-        self._exact_gradient = False
-        return ctx
+            check(L.tmd_set_pairs14(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
 
     def _ensure_box(self, box):
         """Hand the box diagonal to the context when the tensor changed (one D2H copy)."""
