@@ -100,8 +100,9 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { memset(h, 0, sizeof(*h)); return cudaSuccess; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "inter-process" handles inside one process: the handle carries the pointer (several contexts = several ranks)
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorNotSupported; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 // graphs: never taken in the interpreter (the switches that use them stay off)
 typedef struct simt_graph_* cudaGraph_t;

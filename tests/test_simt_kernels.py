@@ -458,3 +458,67 @@ def test_the_package_refuses_the_interpreter_build(simt):
     env = dict(os.environ, TMD_B200_LIB=os.path.join(SIMT_DIR, "libtmd_simt.so"), PYTHONPATH=ROOT)
     r = subprocess.run(["python", "-c", code], capture_output=True, text=True, env=env)
     assert r.returncode != 0 and "SIMT-interpreter build" in r.stderr
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_to_peer_exchange_between_ranks_in_one_process(simt, world):
+    """Several contexts play the ranks of a decomposed run inside one process (the interpreter's IPC handles
+    carry plain pointers): every rank pushes its owned atoms into all ranks' write buffers and flags them, then
+    every rank waits, evaluates its owned forces and finishes the step.  Gathered positions and velocities must
+    equal the single-context trajectory bit for bit (full neighbour rows: no force reduction needed)."""
+    from torchmd_b200 import _lib
+    from torchmd_b200.domain import SlabDecomposition
+
+    g, t = dict(load_golden("water291_rf_switch")), load_golden("water291_traj")
+    g["cfg_nrep"] = np.int64(1)
+    masses = np.ascontiguousarray(g["par_masses"].astype(np.float32))
+    dt = 1.0 / TIMEFACTOR
+    gamma = 0.1 / (1000.0 / TIMEFACTOR)
+    vcoeff = np.sqrt(2.0 * gamma / masses.astype(np.float64) * BOLTZMAN * 300.0 * dt).astype(np.float32)
+
+    def fresh():
+        c = Ctx(simt, g)
+        c.vel = np.ascontiguousarray(t["vel0_f32"][:1]).copy()
+        c.posw = c.pos.copy()
+        c.F, _ = c.forces(pos=c.posw)
+        c.masses, c.dt = masses, dt
+        c.ene, c.ke = np.zeros((1, _lib.NUM_ENERGIES)), np.zeros(1)
+        return c
+
+    ref = fresh()
+    ranks = [fresh() for _ in range(world)]
+    n = ref.natoms
+    handles = (C.c_ubyte * (64 * world))()
+    for r, c in enumerate(ranks):
+        dec = SlabDecomposition(n, world, r)
+        c.lo, c.cnt = dec.lo, dec.count
+        c.check(simt.tmd_set_owned_atoms(c.h, c.lo, c.cnt))
+        c.F, _ = c.forces(pos=c.posw)  # owned forces of the start configuration
+        h = (C.c_ubyte * 64)()
+        c.check(simt.tmd_dd_create(c.h, r, world, h))
+        handles[64 * r : 64 * (r + 1)] = list(h)
+    for c in ranks:
+        c.check(simt.tmd_dd_connect(c.h, handles))
+    parity, nsteps = 0, 5
+    md_steps(simt, ref, nsteps, gamma=gamma, vcoeff=vcoeff, seed=99)
+    for c in ranks:
+        c.check(simt.tmd_dd_load(c.h, parity, c.posw.ctypes.data, None))
+    for it in range(nsteps):
+        for c in ranks:  # phase 1 on every rank: integrate the owned atoms, push, flag
+            c.check(simt.tmd_dd_vv_first_push(c.h, parity, c.vel.ctypes.data, c.F.ctypes.data, masses.ctypes.data, dt, None))
+        for c in ranks:  # phase 2: every rank finds all flags of this step
+            c.check(simt.tmd_dd_wait(c.h, None))
+            c.check(simt.tmd_dd_forces(c.h, 1 - parity, c.F.ctypes.data, None, None))
+            c.check(simt.tmd_vv_second(c.h, c.vel.ctypes.data, c.F.ctypes.data, masses.ctypes.data, dt, gamma, vcoeff.ctypes.data, None, 99, 0,
+                                       None, None))
+        parity ^= 1
+    for c in ranks:
+        c.check(simt.tmd_dd_store(c.h, parity, c.posw.ctypes.data, None))
+        assert np.array_equal(c.posw, ref.posw), "every rank must hold all final positions"
+        sl = slice(c.lo, c.lo + c.cnt)
+        assert np.array_equal(c.vel[0, sl], ref.vel[0, sl]) and np.array_equal(c.F[0, sl], ref.F[0, sl])
+        st = _lib.Stats()
+        assert simt.tmd_get_stats(c.h, C.byref(st), None) == 0
+    ref.close()
+    for c in ranks:
+        c.close()
