@@ -522,3 +522,53 @@ def test_peer_to_peer_exchange_between_ranks_in_one_process(simt, world):
     ref.close()
     for c in ranks:
         c.close()
+
+
+def test_packed_kernel_and_culled_build_on_a_3000_atom_box(simt_cull):
+    """A generated 1000-water box (L = 31 A, 6x6x6 cells, default skin): culled build + packed fixed-point kernel
+    against the oracle -- forces, energies and the bit-exact pair set."""
+    from oracle import refmd
+    from torchmd_b200 import testsystems
+
+    sysd = testsystems.water_box(1000, seed=1)
+    terms = ["lj", "electrostatics", "bonds", "angles"]
+    cfg = dict(cutoff=9.0, rfa=True, switch_dist=7.5)
+    par64 = testsystems.water_parameters(sysd, precision=torch.float64)
+    g = {"coords": sysd["coords"].astype(np.float32), "box": np.asarray(sysd["box"], np.float32), "cfg_nrep": np.int64(1),
+         "cfg_cutoff": np.float64(9.0), "cfg_rfa": np.bool_(True), "cfg_switch_dist": np.float64(7.5), "terms": np.array(terms)}
+
+    class C2(Ctx):
+        def __init__(self, L, env):
+            from torchmd_b200 import Forces
+
+            self.L, self.g, self.terms, self.env = L, g, terms, dict(env)
+            self.check = lambda rc: (_ for _ in ()).throw(RuntimeError(L.tmd_last_error().decode())) if rc else None
+            self.f = Forces(testsystems.water_parameters(sysd, precision=torch.float32), terms=terms, **cfg)
+            self.pos = np.ascontiguousarray(g["coords"][None])
+            self.nrep, self.natoms = 1, self.pos.shape[1]
+            self.box = np.ascontiguousarray(g["box"][None])
+            self.h = C.c_void_p()
+            self.check(L.tmd_create(C.byref(self.h), 0, self.natoms, 1))
+            self.f._configure(L, self.h, self.check)
+            self.check(L.tmd_set_box(self.h, self.box.ctypes.data))
+
+    c = C2(simt_cull, {"TMD_B200_FX": "2"})
+    F, E = c.forces()
+    assert simt_cull.tmd_pair_kernel(c.h) == 2
+    of = refmd.OracleForces(par64, terms, decision_dtype=torch.float32, **cfg)
+    pos_t = torch.tensor(c.pos)
+    box_t = torch.diag(torch.tensor(g["box"]))[None]
+    f64 = torch.zeros(c.pos.shape, dtype=torch.float64)
+    e_ref = of.compute(pos_t.double(), box_t.double(), f64)[0]
+    err = np.abs(F.astype(np.float64) - f64.numpy()).max()
+    assert err < 1e-4 * max(1.0, f64.abs().max().item() / 100.0), err
+    for k in terms:
+        assert abs(E[k][0] - float(e_ref[k])) <= 2e-5 * max(1.0, abs(float(e_ref[k]))) + 2e-3, k
+    of32 = refmd.OracleForces(testsystems.water_parameters(sysd, precision=torch.float32), terms, **cfg)
+    ref_pairs = of32.neighbour_pairs(pos_t[0], torch.tensor(g["box"])).numpy().astype(np.int32)
+    os.environ["TMD_B200_FX"] = "2"
+    try:
+        assert np.array_equal(c.pairs(), ref_pairs)
+    finally:
+        os.environ.pop("TMD_B200_FX", None)
+    c.close()
