@@ -572,3 +572,23 @@ def test_packed_kernel_and_culled_build_on_a_3000_atom_box(simt_cull):
     finally:
         os.environ.pop("TMD_B200_FX", None)
     c.close()
+
+
+@pytest.fixture(scope="module")
+def simt_smalltable():
+    """A build whose staged-table limit is 2 atom types: the 10-type alanine dipeptide and the 4-type chain then
+    take the packed kernels' global-table path (used for real with more than 16 types, e.g. thrombin's 45)."""
+    return load(build_simt("_t2", ["FX_SMALLT_MAX_N=2"]))
+
+
+@pytest.mark.parametrize("name,kernel", [("ala2_nobox_rf", 3), ("chain_amber_periodic", 2)])
+def test_packed_kernels_with_the_table_in_global_memory(simt_smalltable, name, kernel):
+    g = load_golden(name)
+    assert len(np.unique(g["par_types"])) > 2
+    c = Ctx(simt_smalltable, g, env={"TMD_B200_FX": "2"})
+    F, E = c.forces()
+    assert simt_smalltable.tmd_pair_kernel(c.h) == kernel
+    check_against_golden(c, F, E)
+    F2, _ = c.forces(energies=False)
+    check_against_golden(c, F2, {})
+    c.close()

@@ -171,7 +171,11 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
 // s_max -+ margin the two squared distances provably agree; inside it (about 1e-4 of the
 // pairs) the reference arithmetic is re-done on the original positions.
 // SMALLT: the LJ table (<= 16 types) is staged in shared memory.
-constexpr int FX_SMALLT_MAX = 16;
+#ifndef FX_SMALLT_MAX_N
+#define FX_SMALLT_MAX_N 16  // (tests build a variant with a smaller limit to reach the global-table path with few types)
+#endif
+constexpr int FX_SMALLT_MAX = FX_SMALLT_MAX_N;
+constexpr int FX_PLANE_BYTES = FX_SMALLT_MAX * FX_SMALLT_MAX * 4;  // A plane, then B plane, in the packed kernels' staged table
 #ifndef PAIR_FX_MINBLOCKS
 #define PAIR_FX_MINBLOCKS PAIR_MINBLOCKS
 #endif
@@ -332,7 +336,6 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
 // in packed fp32x2 operations (physics.cuh, pair_coef2): the kernel is issue-bound, a packed
 // operation costs one issue slot for two results.  Decisions, band handling and list layout are
 // those of k_pair_fx; a partner that is not taken contributes through a zeroed coefficient.
-static_assert(FX_SMALLT_MAX * FX_SMALLT_MAX * 4 == 1024, "plane offset used in the shared-memory loads of k_pair_fx2");
 #ifndef PAIR_FX2_MINBLOCKS
 #define PAIR_FX2_MINBLOCKS 4
 #endif
@@ -351,7 +354,7 @@ __device__ __forceinline__ void lj_pair_entries(smem_addr ab_row, const float2* 
   if (SMALLT) {
     const smem_addr a0 = ab_row + ((en0 >> 24) << 2), a1 = ab_row + ((en1 >> 24) << 2);
     A = f2(lds_f32(a0), lds_f32(a1));
-    B = f2(lds_f32_plane1(a0), lds_f32_plane1(a1));
+    B = f2(lds_f32_at<FX_PLANE_BYTES>(a0), lds_f32_at<FX_PLANE_BYTES>(a1));
   } else {
     const float2 v0 = __ldg(ab_global + (en0 >> 24)), v1 = __ldg(ab_global + (en1 >> 24));
     A = lj_on ? f2(v0.x, v1.x) : f2(0.f);  // (the staged planes are zeroed instead when the term is off)

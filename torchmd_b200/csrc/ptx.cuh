@@ -23,9 +23,10 @@ __device__ __forceinline__ float lds_f32(smem_addr a) {
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ float lds_f32_plane1(smem_addr a) {  // the same entry of the second 1 KiB plane
+template <int OFFSET>
+__device__ __forceinline__ float lds_f32_at(smem_addr a) {  // the same entry of a second plane OFFSET bytes further on
   float v;
-  asm("ld.shared.f32 %0, [%1+1024];" : "=f"(v) : "r"(a));
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFFSET));
   return v;
 }
 __device__ __forceinline__ float2 lds_f32x2(smem_addr a) {
@@ -58,7 +59,8 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 typedef const char* smem_addr;
 inline smem_addr smem_address(const void* p) { return static_cast<const char*>(p); }
 inline float lds_f32(smem_addr a) { return *reinterpret_cast<const float*>(a); }
-inline float lds_f32_plane1(smem_addr a) { return *reinterpret_cast<const float*>(a + 1024); }
+template <int OFFSET>
+inline float lds_f32_at(smem_addr a) { return *reinterpret_cast<const float*>(a + OFFSET); }
 inline float2 lds_f32x2(smem_addr a) { return *reinterpret_cast<const float2*>(a); }
 inline int4 ldg_s32x4(unsigned long long addr) { return *reinterpret_cast<const int4*>(addr); }
 inline void stg_u32(unsigned long long addr, int v) { *reinterpret_cast<int*>(addr) = v; }
