@@ -592,3 +592,21 @@ def test_packed_kernels_with_the_table_in_global_memory(simt_smalltable, name, k
     F2, _ = c.forces(energies=False)
     check_against_golden(c, F2, {})
     c.close()
+
+
+@pytest.mark.parametrize("tag,define,mode", [("_fxu4", "PAIR_FX_UNROLL=4", "1"), ("_fx2u2", "PAIR_FX2_UNROLL=2", "2"), ("_fx2pipe", "PAIR_FX2_PIPE=1", "2")])
+def test_tuning_variants_of_the_pair_loops(tag, define, mode):
+    """The loop variants of the round-2 tuning sweep (four entries per lane and iteration, two packed evaluations
+    per iteration, software-pipelined gathers) walk the rows correctly: same results as the plain loops."""
+    L = load(build_simt(tag, [define]))
+    for name, kw in (("chain_amber_periodic", {}), ("water999_eq", {"skin": 0.2})):
+        g = load_golden(name)
+        c = Ctx(L, g, env={"TMD_B200_FX": mode}, **kw)
+        F, E = c.forces()
+        assert L.tmd_pair_kernel(c.h) == int(mode)
+        check_against_golden(c, F, E)
+        F2, _ = c.forces(energies=False)
+        check_against_golden(c, F2, {})
+        if "pairs_f32" in g:
+            assert np.array_equal(c.pairs(), g["pairs_f32"])
+        c.close()
