@@ -610,3 +610,118 @@ def test_tuning_variants_of_the_pair_loops(tag, define, mode):
         if "pairs_f32" in g:
             assert np.array_equal(c.pairs(), g["pairs_f32"])
         c.close()
+
+
+# ---- edge cases of the list machinery (synthetic systems against the oracle) -------------------------------
+def synthetic(natoms, coords, box, bonds=None, seed=0, sigma=3.4, eps=0.238):
+    from torchmd_b200.parameters import TopologyParameters
+
+    rng = np.random.default_rng(seed)
+    kw = {}
+    if bonds is not None and len(bonds):
+        b = np.asarray(bonds, np.int64)
+        kw["bonds"] = (b, np.stack([np.arange(len(b)), np.zeros(len(b), np.int64)], 1), np.array([[100.0, 1.5]]))
+
+    def make(precision):
+        return TopologyParameters(atom_types=np.zeros(natoms, np.int64), type_sigma=[sigma], type_epsilon=[eps],
+                                  charges=np.linspace(-0.3, 0.3, natoms), masses=np.full(natoms, 12.0), precision=precision, **kw)
+
+    return make, np.ascontiguousarray(coords, np.float32), np.asarray(box, np.float32)
+
+
+class SynCtx(Ctx):
+    def __init__(self, L, make, coords, box, terms, env=None, **cfg):
+        from torchmd_b200 import Forces
+
+        self.L, self.terms, self.env = L, terms, dict(env or {})
+        self.check = lambda rc: (_ for _ in ()).throw(RuntimeError(L.tmd_last_error().decode())) if rc else None
+        self.f = Forces(make(torch.float32), terms=terms, **cfg)
+        self.pos = np.ascontiguousarray(coords[None])
+        self.nrep, self.natoms = 1, coords.shape[0]
+        self.box = np.ascontiguousarray(box[None])
+        self.h = C.c_void_p()
+        self.check(L.tmd_create(C.byref(self.h), 0, self.natoms, 1))
+        self.f._configure(L, self.h, self.check)
+        self.check(L.tmd_set_box(self.h, self.box.ctypes.data))
+
+
+def oracle_check(c, make, coords, box, terms, cfg, F, tol=1e-4):
+    from oracle import refmd
+
+    of = refmd.OracleForces(make(torch.float64), terms, decision_dtype=torch.float32, **cfg)
+    pos_t = torch.tensor(coords)[None]
+    box_t = torch.diag(torch.tensor(box))[None]
+    f64 = torch.zeros(pos_t.shape, dtype=torch.float64)
+    of.compute(pos_t.double(), box_t.double(), f64)
+    scale = max(1.0, f64.abs().max().item() / 100.0)
+    assert np.abs(F.astype(np.float64) - f64.numpy()).max() < tol * scale
+    of32 = refmd.OracleForces(make(torch.float32), terms, **cfg)
+    return of32.neighbour_pairs(pos_t[0], torch.tensor(box)).numpy().astype(np.int32)
+
+
+@pytest.mark.parametrize("build", ["default", "culled"])
+def test_row_overflow_grows_the_rows_and_recovers(simt, simt_cull, build):
+    """200 atoms inside a 17 A ball of a 77 A box: the density-based row capacity (64) is far too small; the
+    overflow protocol (flag -> TMD_ERR_OVERFLOW -> grown rows -> rebuild) must end in the right answer."""
+    L = simt_cull if build == "culled" else simt
+    rng = np.random.default_rng(4)
+    pts = []
+    while len(pts) < 200:  # min distance 2.2 A inside the ball
+        p = rng.uniform(-8.5, 8.5, 3)
+        if np.linalg.norm(p) < 8.5 and (not pts or np.min(np.linalg.norm(np.array(pts) - p, axis=1)) > 2.2):
+            pts.append(p)
+    coords = np.array(pts) + 38.0
+    make, coords, box = synthetic(200, coords, [77.0, 77.0, 77.0])
+    terms, cfg = ["lj", "electrostatics"], dict(cutoff=9.0, rfa=True, switch_dist=7.5)
+    for env in ({}, {"TMD_B200_FX": "2"}):
+        c = SynCtx(L, make, coords, box, terms, env=env, **cfg)
+        F, E = c.forces()
+        assert c.stats.row_capacity >= c.stats.max_neighbours > 64 and not c.stats.overflow
+        # (atoms 2.2 A apart with sigma 3.4: |F| ~ 1000 from ~200 large terms of both signs -- fp32 summation error)
+        ref_pairs = oracle_check(c, make, coords, box, terms, cfg, F, tol=3e-4)
+        os.environ.update(env)
+        try:
+            assert np.array_equal(c.pairs(), ref_pairs)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        c.close()
+
+
+@pytest.mark.parametrize("build", ["default", "culled"])
+def test_more_than_32_exclusions_per_atom(simt, simt_cull, build):
+    """A hub atom bonded to 40 others (its exclusion list no longer fits one per lane)."""
+    L = simt_cull if build == "culled" else simt
+    rng = np.random.default_rng(5)
+    n = 120
+    coords = rng.uniform(2.0, 22.0, (n, 3))
+    hub = 7
+    leaves = [i for i in range(n) if i != hub][:40]
+    for k, i in enumerate(leaves):  # put the bonded atoms around the hub
+        d = rng.normal(size=3)
+        coords[i] = coords[hub] + 1.5 * d / np.linalg.norm(d) + 0.05 * k * np.array([1, 0, 0])
+    bonds = [(hub, i) for i in leaves]
+    make, coords, box = synthetic(n, coords, [24.0, 24.0, 24.0], bonds=bonds)
+    terms, cfg = ["lj", "electrostatics", "bonds"], dict(cutoff=5.0, rfa=True, switch_dist=4.0)
+    c = SynCtx(L, make, coords, box, terms, skin=0.4, **cfg)
+    F, E = c.forces()
+    ref_pairs = oracle_check(c, make, coords, box, terms, cfg, F, tol=2e-4)
+    got = c.pairs()
+    assert np.array_equal(got, ref_pairs)
+    assert not any((min(hub, i), max(hub, i)) in set(map(tuple, got.tolist())) for i in leaves)
+    c.close()
+
+
+def test_tiny_systems(simt):
+    for n in (1, 2, 3):
+        coords = np.array([[1.0, 1.0, 1.0], [3.5, 1.2, 0.8], [2.0, 4.0, 1.0]])[:n]
+        make, coords, box = synthetic(n, coords, [30.0, 30.0, 30.0])
+        terms, cfg = ["lj", "electrostatics"], dict(cutoff=9.0, rfa=True, switch_dist=7.5)
+        for env in ({}, {"TMD_B200_FX": "1"}, {"TMD_B200_FX": "2"}):
+            c = SynCtx(simt, make, coords, box, terms, env=env, **cfg)
+            F, E = c.forces()
+            if n == 1:
+                assert np.array_equal(F, np.zeros_like(F))
+            else:
+                oracle_check(c, make, coords, box, terms, cfg, F)
+            c.close()
