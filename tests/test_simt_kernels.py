@@ -27,6 +27,8 @@ def build_simt(tag="", defines=()):
     srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(SIMT_DIR, "stub"), "-I", CSRC]
+        if "TMD_SIMT_ASAN=1" in defines:  # scripts/asan_interpreter.py
+            cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
         cmd += [f"-D{d}" for d in defines] + ["-o", out, os.path.join(SIMT_DIR, "simt_lib.cpp")]
         subprocess.run(cmd, check=True, cwd=ROOT)
     return out
