@@ -12,6 +12,8 @@
 #pragma once
 #include <ucontext.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <vector>
@@ -161,6 +163,48 @@ inline void fiber_main() {
   swapcontext(&b->fibers[t].ctx, &b->sched);
 }
 
+// Scheduling order, from the environment (read once): SIMT_SCHEDULE = "forward" (default), "reverse", or
+// "random:<seed>" (a new permutation of the threads every scheduler round; blocks of a grid in a shuffled order too).
+// A kernel without races between its synchronisation points gives the same results under every order (up to the
+// order of floating-point atomics); one that relies on lane 3 running before lane 5 does not.
+struct Schedule {
+  int mode = 0;  // 0 forward, 1 reverse, 2 random
+  unsigned long long state = 0x9E3779B97F4A7C15ull;
+  Schedule() {
+    const char* e = getenv("SIMT_SCHEDULE");
+    if (!e) return;
+    if (!strcmp(e, "reverse")) mode = 1;
+    else if (!strncmp(e, "random", 6)) {
+      mode = 2;
+      if (e[6] == ':') state ^= strtoull(e + 7, nullptr, 10) * 0xD1342543DE82EF95ull;
+    }
+  }
+  unsigned next() {  // xorshift64*
+    state ^= state >> 12;
+    state ^= state << 25;
+    state ^= state >> 27;
+    return (unsigned)((state * 0x2545F4914F6CDD1Dull) >> 33);
+  }
+  void order(std::vector<int>& idx) {
+    const int n = (int)idx.size();
+    if (mode == 0) for (int i = 0; i < n; ++i) idx[i] = i;
+    else if (mode == 1) for (int i = 0; i < n; ++i) idx[i] = n - 1 - i;
+    else {
+      for (int i = 0; i < n; ++i) idx[i] = i;
+      for (int i = n - 1; i > 0; --i) {
+        const int j = (int)(next() % (unsigned)(i + 1));
+        const int t = idx[i];
+        idx[i] = idx[j];
+        idx[j] = t;
+      }
+    }
+  }
+};
+inline Schedule& schedule() {
+  static Schedule s;
+  return s;
+}
+
 inline void run_block(Block& b) {
   constexpr size_t STACK = 192 * 1024;
   b.nthreads = (int)(b.block.x * b.block.y * b.block.z);
@@ -184,9 +228,13 @@ inline void run_block(Block& b) {
   current() = &b;
   int remaining = b.nthreads;
   long long idle_rounds = 0;
+  std::vector<int> turn(b.nthreads);
+  schedule().order(turn);
   while (remaining > 0) {
     int progressed = 0;
-    for (int t = 0; t < b.nthreads; ++t) {
+    if (schedule().mode == 2) schedule().order(turn);
+    for (int k = 0; k < b.nthreads; ++k) {
+      const int t = turn[k];
       if (b.fibers[t].done) continue;
       b.cur = t;
       swapcontext(&b.sched, &b.fibers[t].ctx);
@@ -209,16 +257,18 @@ inline void run_block(Block& b) {
 template <typename F>
 inline void run_grid(dim3 grid, dim3 block, F&& f) {
   const std::function<void()> body(f);
-  for (unsigned z = 0; z < grid.z; ++z)
-    for (unsigned y = 0; y < grid.y; ++y)
-      for (unsigned x = 0; x < grid.x; ++x) {
-        Block b;
-        b.grid = grid;
-        b.block = block;
-        b.bidx = dim3(x, y, z);
-        b.body = &body;
-        run_block(b);
-      }
+  const unsigned nblocks = grid.x * grid.y * grid.z;
+  std::vector<int> turn(nblocks);
+  schedule().order(turn);
+  for (unsigned k = 0; k < nblocks; ++k) {
+    const unsigned id = (unsigned)turn[k];
+    Block b;
+    b.grid = grid;
+    b.block = block;
+    b.bidx = dim3(id % grid.x, (id / grid.x) % grid.y, id / (grid.x * grid.y));
+    b.body = &body;
+    run_block(b);
+  }
 }
 
 struct ThreadIdxProxy {
@@ -260,6 +310,7 @@ inline unsigned __ballot_sync(unsigned mask, int p) { return (unsigned)simt::col
 inline int __any_sync(unsigned mask, int p) { return (int)simt::collective(simt::K_ANY, mask, p != 0, 0); }
 inline unsigned __activemask() {
   simt::yield();  // let every other thread reach its next parking point (or return) first
+  if (simt::schedule().mode == 2) simt::yield();  // orders change between rounds: two rounds reach everyone
   return simt::warp().live;
 }
 template <typename T>
