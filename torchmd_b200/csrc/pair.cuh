@@ -391,7 +391,8 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   const int* __restrict__ row = S.nbr + (base + k) * (size_t)S.row_cap;
   const int n = S.nnbr[base + k];
   const int4 pi = xf[k];
-  const float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
+  float nqi = (S.pp.terms & T_ELEC) ? -__int_as_float(pi.w) : 0.f;  // term off: no charge
+  if (!ENERGY) TMD_PIN_F(nqi);  // (otherwise the select is redone from the constant bank for every pair; the energy variant has no register to spare)
   const int ti = S.type_s[base + k] * S.ntypes;
   smem_addr ab_row = smem_address(ab_s) + (unsigned)ti * 4u;
   TMD_PIN_R(ab_row);  // keep it in a register (otherwise re-derived from the CTA's shared window per pair)
@@ -400,23 +401,29 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
   const F2 ux = f2(g->fx_unit[0]), uy = f2(g->fx_unit[1]), uz = f2(g->fx_unit[2]);
   const float margin = fmaf(g->fx_c1, __int_as_float(S.flags[r * F_COUNT + F_PMAX]), g->fx_c0);
   const float s_hi = S.pp.s_max + margin, s_lo = S.pp.s_max - margin;
+  // d = fl(s - s_lo) has the sign of s - s_lo, and fl is monotone: s <= s_hi implies d <= fl(s_hi - s_lo).  For
+  // d >= +0 the bit pattern orders like the value and a negative d has the top bit set, so the smallest d >= 0 seen is
+  // the unsigned minimum of the bit patterns, and "some pair was inside the band" is one comparison after the loop.
+  // An empty slot (record 0) may raise it spuriously, which only costs the pass.
+  const F2 ns_lo = f2(-s_lo);
+  unsigned d_min = 0xffffffffu;
   F2 FX = f2(0.f), FY = f2(0.f), FZ = f2(0.f);  // the two halves are added at the end
   F2 ELJ = f2(0.f), NEEL = f2(0.f);             // switched LJ energy / minus the Coulomb energy
-  float s_skipped = INFINITY;
 
-  // two list entries evaluated together
-  // an empty slot (entry -1) reads record 0 and is masked later
-  auto record_of = [&](int j) { return fx_record(xf_base, ((j >= 0 ? (unsigned)j : 0u) << 4) & 0x0ffffff0u); };
-  auto pair2r = [&](int j0, int j1, const int4 p0, const int4 p1) {
-    const bool v0 = j0 >= 0, v1 = j1 >= 0;
-    const unsigned en0 = v0 ? (unsigned)j0 : 0u, en1 = v1 ? (unsigned)j1 : 0u;
+  // two list entries evaluated together: slots e0 and e0 + 32 of the row
+  // a slot past the end of the row holds entry 0 (reads record 0) and is masked by its position
+  auto entry_at = [&](int e) { return (e < n) ? __ldcs(row + e) : 0; };
+  auto record_of = [&](int j) { return ldg_s32x4(mad_wide_u32((unsigned)j & 0xffffffu, 16u, xf_base)); };
+  auto pair2r = [&](int e0, int j0, int j1, const int4 p0, const int4 p1) {
+    const bool v0 = e0 < n, v1 = e0 + 32 < n;
+    const unsigned en0 = (unsigned)j0, en1 = (unsigned)j1;
     const F2 wx = f2_mul(f2((float)(int)((unsigned)pi.x - (unsigned)p0.x), (float)(int)((unsigned)pi.x - (unsigned)p1.x)), ux);
     const F2 wy = f2_mul(f2((float)(int)((unsigned)pi.y - (unsigned)p0.y), (float)(int)((unsigned)pi.y - (unsigned)p1.y)), uy);
     const F2 wz = f2_mul(f2((float)(int)((unsigned)pi.z - (unsigned)p0.z), (float)(int)((unsigned)pi.z - (unsigned)p1.z)), uz);
     const F2 s = f2_fma(wz, wz, f2_fma(wy, wy, f2_mul(wx, wx)));
-    const bool in0 = v0 && s.x < s_lo, in1 = v1 && s.y < s_lo;
-    if (v0 && !in0) s_skipped = fminf(s_skipped, s.x);
-    if (v1 && !in1) s_skipped = fminf(s_skipped, s.y);
+    const F2 d = f2_add(s, ns_lo);
+    const bool in0 = v0 && d.x < 0.f, in1 = v1 && d.y < 0.f;
+    d_min = min(d_min, min(__float_as_uint(d.x), __float_as_uint(d.y)));
     if (in0 || in1) {
       F2 A, B;
       lj_pair_entries<SMALLT>(ab_row, ab_global, (S.pp.terms & T_LJ) != 0, en0, en1, A, B);
@@ -434,20 +441,16 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
       }
     }
   };
-  auto pair2 = [&](int j0, int j1) { pair2r(j0, j1, record_of(j0), record_of(j1)); };
+  auto pair2 = [&](int e0, int j0, int j1) { pair2r(e0, j0, j1, record_of(j0), record_of(j1)); };
 #if PAIR_FX2_PIPE
   {  // tuning variant: list entries two iterations ahead, partner records one iteration ahead
     int e = lane;
-    int j0 = (e < n) ? __ldcs(row + e) : -1;
-    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
-    int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-    int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    int j0 = entry_at(e), j1 = entry_at(e + 32), jn0 = entry_at(e + 64), jn1 = entry_at(e + 96);
     int4 p0 = record_of(j0), p1 = record_of(j1);
     while (e < n) {
-      const int jnn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
-      const int jnn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
+      const int jnn0 = entry_at(e + 128), jnn1 = entry_at(e + 160);
       const int4 pn0 = record_of(jn0), pn1 = record_of(jn1);
-      pair2r(j0, j1, p0, p1);
+      pair2r(e, j0, j1, p0, p1);
       j0 = jn0;
       j1 = jn1;
       jn0 = jnn0;
@@ -460,17 +463,11 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
 #elif PAIR_FX2_UNROLL == 2
   {  // tuning variant: two packed evaluations (four list entries) per iteration
     int e = lane;
-    int j0 = (e < n) ? __ldcs(row + e) : -1;
-    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
-    int j2 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-    int j3 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
+    int j0 = entry_at(e), j1 = entry_at(e + 32), j2 = entry_at(e + 64), j3 = entry_at(e + 96);
     while (e < n) {
-      const int jn0 = (e + 128 < n) ? __ldcs(row + e + 128) : -1;
-      const int jn1 = (e + 160 < n) ? __ldcs(row + e + 160) : -1;
-      const int jn2 = (e + 192 < n) ? __ldcs(row + e + 192) : -1;
-      const int jn3 = (e + 224 < n) ? __ldcs(row + e + 224) : -1;
-      pair2(j0, j1);
-      pair2(j2, j3);
+      const int jn0 = entry_at(e + 128), jn1 = entry_at(e + 160), jn2 = entry_at(e + 192), jn3 = entry_at(e + 224);
+      pair2(e, j0, j1);
+      pair2(e + 64, j2, j3);
       j0 = jn0;
       j1 = jn1;
       j2 = jn2;
@@ -481,12 +478,10 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
 #else
   {
     int e = lane;
-    int j0 = (e < n) ? __ldcs(row + e) : -1;
-    int j1 = (e + 32 < n) ? __ldcs(row + e + 32) : -1;
+    int j0 = entry_at(e), j1 = entry_at(e + 32);
     while (e < n) {
-      const int jn0 = (e + 64 < n) ? __ldcs(row + e + 64) : -1;
-      const int jn1 = (e + 96 < n) ? __ldcs(row + e + 96) : -1;
-      pair2(j0, j1);
+      const int jn0 = entry_at(e + 64), jn1 = entry_at(e + 96);
+      pair2(e, j0, j1);
       j0 = jn0;
       j1 = jn1;
       e += 64;
@@ -498,7 +493,7 @@ k_pair_fx2(DeviceState S, SwitchConsts sc, float* __restrict__ forces, double* _
     e_lj = ELJ.x + ELJ.y;
     e_el = -(NEEL.x + NEEL.y);
   }
-  if (__any_sync(0xffffffffu, s_skipped <= s_hi)) {
+  if (__any_sync(0xffffffffu, d_min <= __float_as_uint(s_hi - s_lo))) {
     // pairs inside the decision band: the reference's own decision, scalar arithmetic
     const float4* __restrict__ xq = S.xq_s + (size_t)r * (N + 1);
     const PairParams pp = S.pp;

@@ -39,6 +39,12 @@ __device__ __forceinline__ int4 ldg_s32x4(unsigned long long addr) {
   asm("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
   return v;
 }
+// base + a * b as one IMAD.WIDE.U32 (the address of a 16-byte record from its index)
+__device__ __forceinline__ unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long long c) {
+  unsigned long long d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void stg_u32(unsigned long long addr, int v) {
   asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
@@ -63,6 +69,7 @@ template <int OFFSET>
 inline float lds_f32_at(smem_addr a) { return *reinterpret_cast<const float*>(a + OFFSET); }
 inline float2 lds_f32x2(smem_addr a) { return *reinterpret_cast<const float2*>(a); }
 inline int4 ldg_s32x4(unsigned long long addr) { return *reinterpret_cast<const int4*>(addr); }
+inline unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long long c) { return (unsigned long long)a * b + c; }
 inline void stg_u32(unsigned long long addr, int v) { *reinterpret_cast<int*>(addr) = v; }
 inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
