@@ -7,8 +7,9 @@
 #   2  gated tests of the new code paths        3  pair kernels: A/B bench TMD_B200_FX=0/1/2 + register/unroll variants
 #   4  list build with chunk culling            5  bonded kernel overlapped on a second stream
 #   6  captured step + conditional-node rebuild on one GPU
+#   7  integrate + prepare in one kernel (TMD_B200_FUSEPREP=1), then everything together
 mkdir -p gpurun_out /tmp/var
-SECTIONS="${*:-0 1 2 3 4 5 6}"
+SECTIONS="${*:-0 1 2 3 4 5 6 7}"
 has() { [[ " $SECTIONS " == *" $1 "* ]]; }
 NVCC="nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared"
 BENCH="python bench.py --steps 1000 --warmup 50 --equil 400 --no-cpu-baseline --e2e-steps 10"
@@ -78,6 +79,11 @@ fi
 if has 6; then
   run_suite graph TMD_B200_GRAPH=1
   for fx in 0 2; do run_bench "GRAPH=1 FX=$fx" graph_fx$fx TMD_B200_GRAPH=1 TMD_B200_FX=$fx; done
+fi
+if has 7; then
+  run_suite fuseprep TMD_B200_FUSEPREP=1
+  for fx in 0 2; do run_bench "FUSEPREP=1 FX=$fx" fuse_fx$fx TMD_B200_FUSEPREP=1 TMD_B200_FX=$fx; done
   [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
   run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
+  run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1
 fi

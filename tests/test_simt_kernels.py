@@ -21,16 +21,43 @@ SIMT_DIR = os.path.join(ROOT, "tests", "simt")
 CSRC = os.path.join(ROOT, "torchmd_b200", "csrc")
 
 
-def build_simt(tag="", defines=()):
-    out = os.path.join(SIMT_DIR, f"libtmd_simt{tag}.so")
+VARIANTS = {  # tag -> defines; every interpreter build the tests use (built together, in parallel, when stale)
+    "": [],
+    "_cull": ["BT_CULL=1"],
+    "_t2": ["FX_SMALLT_MAX_N=2"],
+    "_fxu4": ["PAIR_FX_UNROLL=4"],
+    "_fx2u2": ["PAIR_FX2_UNROLL=2"],
+    "_fx2pipe": ["PAIR_FX2_PIPE=1"],
+}
+
+
+def _simt_command(out, defines):
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(SIMT_DIR, "stub"), "-I", CSRC]
+    if "TMD_SIMT_ASAN=1" in defines:  # scripts/asan_interpreter.py
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
+    return cmd + [f"-D{d}" for d in defines] + ["-o", out, os.path.join(SIMT_DIR, "simt_lib.cpp")]
+
+
+def _simt_stale(out):
     srcs = [os.path.join(SIMT_DIR, f) for f in ("simt_lib.cpp", "simt.h", os.path.join("stub", "cuda_runtime.h"))]
     srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(SIMT_DIR, "stub"), "-I", CSRC]
-        if "TMD_SIMT_ASAN=1" in defines:  # scripts/asan_interpreter.py
-            cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
-        cmd += [f"-D{d}" for d in defines] + ["-o", out, os.path.join(SIMT_DIR, "simt_lib.cpp")]
-        subprocess.run(cmd, check=True, cwd=ROOT)
+    return not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs)
+
+
+def build_simt(tag="", defines=()):
+    out = os.path.join(SIMT_DIR, f"libtmd_simt{tag}.so")
+    if _simt_stale(out):
+        jobs = {tag: (out, list(defines))}
+        if tag in VARIANTS:  # one of the suite's builds is stale: the others are too -- compile them side by side
+            for t, d in VARIANTS.items():
+                o = os.path.join(SIMT_DIR, f"libtmd_simt{t}.so")
+                if t != tag and _simt_stale(o):
+                    jobs[t] = (o, d)
+        procs = [(o, subprocess.Popen(_simt_command(o + ".tmp", d), cwd=ROOT)) for o, d in jobs.values()]
+        for o, pr in procs:
+            if pr.wait() != 0:
+                raise RuntimeError(f"building {o} failed")
+            os.replace(o + ".tmp", o)
     return out
 
 
@@ -313,6 +340,39 @@ def test_fused_md_steps_follow_the_reference_trajectories(simt):
     md_steps(simt, c, 4, gamma=gamma, vcoeff=vcoeff, noise=noise)
     assert np.abs(c.posw - t["lan_pos4_f32"]).max() < 2e-5 and np.abs(c.vel - t["lan_vel4_f32"]).max() < 5e-5
     c.close()
+
+
+@pytest.mark.parametrize("extra", [{}, {"TMD_B200_OVERLAP": "1", "TMD_B200_FX": "2"}])
+def test_integrate_and_prepare_in_one_kernel_is_bit_identical(simt, extra):
+    """TMD_B200_FUSEPREP=1: k_vv_first_prepare (move the atoms, check the list, refresh the sorted records) against
+    k_vv_first followed by k_prepare -- same trajectory to the last bit across list rebuilds, one launch fewer per
+    step; a plain force call after fused steps still prepares for itself."""
+    from torchmd_b200 import _lib
+
+    g, t, a = md_setup(simt, env=dict(extra))
+    _, _, b = md_setup(simt, env=dict(extra, TMD_B200_FUSEPREP="1"))
+    gamma = 0.1 / (1000.0 / TIMEFACTOR)
+    vcoeff = np.sqrt(2.0 * gamma / a.masses.astype(np.float64) * BOLTZMAN * 300.0 * a.dt).astype(np.float32)
+    st = [_lib.Stats(), _lib.Stats()]
+    for k, c in enumerate((a, b)):
+        assert simt.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
+    l0 = [s.kernel_launches for s in st]
+    total = 0
+    for niter in (1, 2, 17):
+        for c in (a, b):
+            md_steps(simt, c, niter, gamma=gamma, vcoeff=vcoeff, seed=5)
+        total += niter
+        assert np.array_equal(a.posw, b.posw) and np.array_equal(a.vel, b.vel) and np.array_equal(a.F, b.F)
+        assert np.array_equal(a.ene, b.ene) and np.array_equal(a.ke, b.ke)
+    for k, c in enumerate((a, b)):
+        assert simt.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
+    assert st[0].rebuilds == st[1].rebuilds and st[0].rebuilds >= 2  # the list is rebuilt on the way
+    assert (st[0].kernel_launches - l0[0]) - (st[1].kernel_launches - l0[1]) == total
+    Fa, Ea = a.forces(pos=a.posw)
+    Fb, Eb = b.forces(pos=b.posw)
+    assert np.array_equal(Fa, Fb) and repr(Ea) == repr(Eb)
+    a.close()
+    b.close()
 
 
 @pytest.mark.parametrize("thermostat", [False, True])

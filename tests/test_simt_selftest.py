@@ -60,10 +60,10 @@ def test_schedules_change_the_order_and_expose_a_missing_barrier(selftest_lib):
     assert len(seen) == 3
 
 
-@pytest.mark.parametrize("schedule", ["reverse", "random:11"])
+@pytest.mark.parametrize("schedule", ["random:11"])
 def test_kernel_results_do_not_depend_on_the_thread_order(schedule):
     """The quick half of tests/test_simt_kernels.py again under another thread and block order (the whole file
-    passes under reverse and random orders too; that takes four minutes per order and is run by hand)."""
+    passes under SIMT_SCHEDULE=reverse and random orders too; that takes four minutes per order and is run by hand)."""
     pick = "chain or argon or wrap_kernel or tiny or owned or exclusions or overlap or replicas or in_one_process"
     env = dict(os.environ, SIMT_SCHEDULE=schedule)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_simt_kernels.py"), "-q", "-x", "-k", pick,

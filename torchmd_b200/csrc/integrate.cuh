@@ -7,6 +7,7 @@
 // the last bit as long as the forces do.
 #pragma once
 #include "context.cuh"
+#include "neighbor.cuh"
 #include "pair.cuh"
 #include "ptx.cuh"
 
@@ -33,6 +34,33 @@ k_vv_first(int natoms, int lo, int cnt, unsigned long long* counters, float* __r
     pos[a + d] = add_rn(pos[a + d], drift);
     vel[a + d] = add_rn(v, mul_rn(hdt, acc));
   }
+}
+
+// k_vv_first followed by k_prepare (neighbor.cuh) in one pass over the atoms: the thread that moved an atom still
+// holds its new position, so the list check and the refresh of the sorted records cost no second read of the
+// positions and no second launch.  Whole-system runs only (a decomposed run prepares after the exchange).
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_vv_first_prepare(DeviceState S, float* __restrict__ pos, float* __restrict__ vel, const float* __restrict__ forces,
+                   const float* __restrict__ masses, float dt, float hdt) {
+  const int parity = (int)(S.counters[0] & 1ull);
+  const int r = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[1] += 1;  // Philox position of this step
+  if (i == 0) S.flags[r * F_COUNT + F_REBUILD0 + (parity ^ 1)] = 0;
+  if (i >= S.natoms) return;
+  const float m = masses[i];
+  const size_t a = ((size_t)r * S.natoms + i) * 3;
+  float x[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float acc = div_rn(forces[a + d], m);
+    const float v = vel[a + d];
+    const float drift = add_rn(mul_rn(v, dt), mul_rn(mul_rn(mul_rn(0.5f, acc), dt), dt));
+    x[d] = add_rn(pos[a + d], drift);
+    pos[a + d] = x[d];
+    vel[a + d] = add_rn(v, mul_rn(hdt, acc));
+  }
+  prepare_atom(S, r, i, parity, x[0], x[1], x[2]);
 }
 
 // ---- fused integrate + exchange (decomposed runs, include/tmd_b200.h tmd_dd_*) -----------

@@ -60,15 +60,12 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, fl
 }
 
 // ---- every call ---------------------------------------------------------------
-__global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
-  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
-  const int r = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One atom of the per-call preparation: displacement trigger against the positions of the last
+// rebuild, far-position check, refresh of the sorted records (float and fixed-point), largest
+// |coordinate|.  (x, y, z) is the atom's current position.
+__device__ __forceinline__ void prepare_atom(const DeviceState& S, int r, int i, int parity, float x, float y, float z) {
   int* fl = S.flags + r * F_COUNT;
-  if (i == 0) fl[F_REBUILD0 + (parity ^ 1)] = 0;  // nobody reads or sets that one now
-  if (i >= S.natoms) return;
   const size_t a = (size_t)r * S.natoms + i;
-  const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
   const float4 ref = S.pos_ref[a];
   const float dx = x - ref.x, dy = y - ref.y, dz = z - ref.z;
   const float d2 = dx * dx + dy * dy + dz * dz;
@@ -97,6 +94,16 @@ __global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
     const int mb = __reduce_max_sync(am, __float_as_int(m));  // non-negative floats order like ints
     if ((threadIdx.x & 31) == __ffs(am) - 1 && mb > fl[F_PMAX]) atomicMax(fl + F_PMAX, mb);
   }
+}
+
+__global__ void k_prepare(DeviceState S, const float* __restrict__ pos) {
+  const int parity = (int)(S.counters[0] & 1ull);  // device-resident: the launch sequence is CUDA-graph replayable
+  const int r = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) S.flags[r * F_COUNT + F_REBUILD0 + (parity ^ 1)] = 0;  // nobody reads or sets that one now
+  if (i >= S.natoms) return;
+  const size_t a = (size_t)r * S.natoms + i;
+  prepare_atom(S, r, i, parity, pos[a * 3 + 0], pos[a * 3 + 1], pos[a * 3 + 2]);
 }
 
 // ---- rebuild phases -----------------------------------------------------------------

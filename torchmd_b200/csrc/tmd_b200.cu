@@ -120,6 +120,11 @@ struct CtxPriv {
   DeviceState step_state{};          // the kernel arguments baked into the captured steps
   bool steps_valid = false;
   int64_t step_launches[2] = {0, 0};  // kernels of one captured step (rebuild body included)
+  // TMD_B200_FUSEPREP=1: tmd_md_steps moves the atoms and prepares the force call in one kernel
+  // (k_vv_first_prepare); the handle of the rebuild's conditional node is then made before that launch
+  bool fuse_prepare = false;
+  bool prepared = false;                        // the next enqueue_forces finds k_prepare's work done
+  cudaGraphConditionalHandle prepared_cond = 0; // and this handle already handed to the kernel
   bool dirty = true;
   size_t nbr_entries = 0;
   std::vector<cudaEvent_t> ev;  // pair-kernel timing samples (begin,end interleaved)
@@ -601,6 +606,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_in, cudaEventDisableTiming));
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_out, cudaEventDisableTiming));
     }
+    const char* ef = getenv("TMD_B200_FUSEPREP");
+    pv.fuse_prepare = ef && ef[0] == '1';
     pv.steps_valid = false;  // buffers may have moved: captured steps are rebuilt
   }
   priv(ctx).dirty = false;
@@ -715,14 +722,19 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
           cs != cudaStreamCaptureStatusActive)
         cap_graph = nullptr;
     }
-    DeviceState dp = d;  // k_prepare's copy carries the handle it switches on
     cudaGraphConditionalHandle handle = 0;
-    if (cap_graph) {
-      TMD_CUDA(cudaGraphConditionalHandleCreate(&handle, cap_graph, 0, cudaGraphCondAssignDefault));
-      dp.cond = (unsigned long long)handle;
+    if (priv(ctx).prepared) {  // k_vv_first_prepare did k_prepare's work (tmd_md_steps)
+      handle = priv(ctx).prepared_cond;
+      priv(ctx).prepared = false;
+    } else {
+      DeviceState dp = d;  // k_prepare's copy carries the handle it switches on
+      if (cap_graph) {
+        TMD_CUDA(cudaGraphConditionalHandleCreate(&handle, cap_graph, 0, cudaGraphCondAssignDefault));
+        dp.cond = (unsigned long long)handle;
+      }
+      launch(k_prepare, atoms_grid(ctx, 256), 256, st, dp, pos);
+      TMD_LAUNCHED(ctx, "k_prepare");
     }
-    launch(k_prepare, atoms_grid(ctx, 256), 256, st, dp, pos);
-    TMD_LAUNCHED(ctx, "k_prepare");
     const int need_bounds = (!ctx->periodic && ctx->cutoff >= 0) ? 1 : 0;
     cudaStream_t rs = st;  // stream the rebuild kernels are enqueued on
     cudaGraphNode_t cond_node = nullptr;
@@ -804,7 +816,27 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
 }
 
 static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses,
-                            double dt, cudaStream_t st) {
+                            double dt, cudaStream_t st, bool forces_follow = false) {
+  CtxPriv& pv = priv(ctx);
+  if (forces_follow && pv.fuse_prepare && ctx->d.own_all && ctx->pair_mask) {
+    // the force call that follows on this stream finds its preparation done
+    DeviceState dp = ctx->d;
+    pv.prepared_cond = 0;
+    if (pv.use_cond) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaGraph_t cap_graph = nullptr;
+      if (cudaStreamGetCaptureInfo(st, &cs, nullptr, &cap_graph, nullptr, nullptr) == cudaSuccess &&
+          cs == cudaStreamCaptureStatusActive && cap_graph) {
+        TMD_CUDA(cudaGraphConditionalHandleCreate(&pv.prepared_cond, cap_graph, 0, cudaGraphCondAssignDefault));
+        dp.cond = (unsigned long long)pv.prepared_cond;
+      }
+    }
+    launch(k_vv_first_prepare, atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, dp, pos, vel, forces, masses, (float)dt,
+           (float)(0.5 * dt));
+    TMD_LAUNCHED(ctx, "k_vv_first_prepare");
+    pv.prepared = true;
+    return TMD_OK;
+  }
   launch(k_vv_first, owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, 
       ctx->natoms, ctx->d.own_lo, ctx->d.own_n, ctx->d.counters, pos, vel, forces, masses, (float)dt, (float)(0.5 * dt));
   TMD_LAUNCHED(ctx, "k_vv_first");
@@ -839,6 +871,7 @@ int tmd_forces(tmd_ctx* ctx, const float* pos, float* forces, double* energies, 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (priv(ctx).dirty && (rc = finalize(ctx, st))) return rc;
+  priv(ctx).prepared = false;  // (only tmd_md_steps prepares ahead of the force call)
   return enqueue_forces(ctx, pos, forces, energies, st);
 }
 
@@ -878,6 +911,7 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
   if (priv(ctx).dirty && (rc = finalize(ctx, st))) return rc;
   const size_t per_step = (size_t)ctx->nrep * ctx->natoms * 3;
   CtxPriv& pv = priv(ctx);
+  pv.prepared = false;
   if (pv.use_graph && !noise && !pv.profiling && niter > 0) {
     // One MD step captured once (with and without the energy outputs) and replayed: one graph
     // launch per step, the rebuild kernels inside a conditional node.  Everything that changes
@@ -896,7 +930,7 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
           const bool with_e = (k == 1);
           const int64_t l0 = ctx->launches, f0 = ctx->force_calls;
           TMD_CUDA(cudaStreamBeginCapture(pv.gstream, cudaStreamCaptureModeRelaxed));
-          rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, pv.gstream);
+          rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, pv.gstream, true);
           if (!rc) rc = enqueue_forces(ctx, pos, forces, with_e ? energies : nullptr, pv.gstream);
           if (!rc) rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, nullptr, seed, first_step,
                                           with_e ? ke : nullptr, pv.gstream);
@@ -925,7 +959,7 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
   }
   for (int it = 0; it < niter; ++it) {
     const bool last = (it == niter - 1);
-    if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st))) return rc;
+    if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st, true))) return rc;
     if ((rc = enqueue_forces(ctx, pos, forces, last ? energies : nullptr, st))) return rc;
     if ((rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, noise ? noise + it * per_step : nullptr,
                                 seed, first_step, last ? ke : nullptr, st)))
