@@ -8,6 +8,7 @@
 #   4  list build with chunk culling            5  bonded kernel overlapped on a second stream
 #   6  captured step + conditional-node rebuild on one GPU
 #   7  integrate + prepare in one kernel (TMD_B200_FUSEPREP=1), then everything together
+#   8  FAST PATH instead of 4-7: the GPU suite and the bench once with every switch on (bisect with 4-7 only if it fails)
 mkdir -p gpurun_out /tmp/var
 SECTIONS="${*:-0 1 2 3 4 5 6 7}"
 has() { [[ " $SECTIONS " == *" $1 "* ]]; }
@@ -86,4 +87,13 @@ if has 7; then
   [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
   run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
   run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1
+fi
+if has 8; then
+  [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
+  ALL="TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_FUSEPREP=1"
+  run_suite all $ALL
+  run_suite all_graph $ALL TMD_B200_GRAPH=1
+  run_bench "baseline (default switches)" base TMD_B200_FX=0
+  run_bench "all switches, stream launches" all_stream $ALL
+  run_bench "all switches, captured step" all_graph $ALL TMD_B200_GRAPH=1
 fi
