@@ -78,19 +78,24 @@ if has 5; then
   for fx in 0 2; do run_bench "OVERLAP=1 FX=$fx" ov_fx$fx TMD_B200_OVERLAP=1 TMD_B200_FX=$fx; done
 fi
 if has 6; then
-  run_suite graph TMD_B200_GRAPH=1
-  for fx in 0 2; do run_bench "GRAPH=1 FX=$fx" graph_fx$fx TMD_B200_GRAPH=1 TMD_B200_FX=$fx; done
+  # (the device-side switch of the conditional node is compiled in with -DTMD_COND_NODE=1; without it GRAPH=1
+  # captures the five gated rebuild kernels)
+  run_suite graph_nocond TMD_B200_GRAPH=1
+  run_bench "GRAPH=1 without the conditional node" graph_nocond TMD_B200_GRAPH=1
+  $NVCC -DTMD_COND_NODE=1 -o /tmp/var/lib_cond.so torchmd_b200/csrc/tmd_b200.cu
+  run_suite graph TMD_B200_LIB=/tmp/var/lib_cond.so TMD_B200_GRAPH=1
+  for fx in 0 2; do run_bench "GRAPH=1 + conditional node, FX=$fx" graph_fx$fx TMD_B200_LIB=/tmp/var/lib_cond.so TMD_B200_GRAPH=1 TMD_B200_FX=$fx; done
 fi
 if has 7; then
   run_suite fuseprep TMD_B200_FUSEPREP=1
   for fx in 0 2; do run_bench "FUSEPREP=1 FX=$fx" fuse_fx$fx TMD_B200_FUSEPREP=1 TMD_B200_FX=$fx; done
-  [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
-  run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
-  run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1
+  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
+  run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
+  run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1
 fi
 if has 8; then
-  [ -f /tmp/var/lib_cull.so ] || $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
-  ALL="TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_FUSEPREP=1"
+  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
+  ALL="TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_FUSEPREP=1"
   run_suite all $ALL
   run_suite all_graph $ALL TMD_B200_GRAPH=1
   run_bench "baseline (default switches)" base TMD_B200_FX=0

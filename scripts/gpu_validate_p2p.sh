@@ -30,6 +30,8 @@ grep -E "identical|P2P_CHECK|unavailable|Error|error" gpurun_out/p2p_check_$N.lo
 bench "N=$N all-gather" allgather TMD_B200_EXCHANGE=allgather
 bench "N=$N p2p push" p2p TMD_B200_EXCHANGE=p2p
 if [ "$MODE" = full ]; then
-  bench "N=$N all-gather + cond node" cond_allgather TMD_B200_EXCHANGE=allgather TMD_B200_COND=1
-  bench "N=$N p2p push + cond node" cond_p2p TMD_B200_EXCHANGE=p2p TMD_B200_COND=1
+  mkdir -p /tmp/var
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DTMD_COND_NODE=1 -o /tmp/var/lib_cond.so torchmd_b200/csrc/tmd_b200.cu
+  bench "N=$N all-gather + cond node" cond_allgather TMD_B200_LIB=/tmp/var/lib_cond.so TMD_B200_EXCHANGE=allgather TMD_B200_COND=1
+  bench "N=$N p2p push + cond node" cond_p2p TMD_B200_LIB=/tmp/var/lib_cond.so TMD_B200_EXCHANGE=p2p TMD_B200_COND=1
 fi

@@ -16,6 +16,8 @@ from conftest import golden_cfg, golden_system_tensors, load_golden, params_from
 from oracle import refmd
 
 
+DEV = "cuda:0"  # (tests/test_mirrors_on_interpreter.py runs the gpu tests on the host interpreter with "cpu")
+
 @pytest.fixture()
 def cpu_forces(monkeypatch):
     from torchmd_b200 import Forces
@@ -154,7 +156,7 @@ def test_external_potential_in_both_force_modes(cpu_forces):
 def test_gpu_energy_backward_and_vmap():
     from torchmd_b200 import Forces
 
-    dev = "cuda:0"
+    dev = DEV
     g = load_golden("ala2_xsc_rf")
     par = params_from_golden(g, precision=torch.float32, device=dev)
     f = Forces(par, terms=[str(t) for t in g["terms"]], **golden_cfg(g))
@@ -240,7 +242,7 @@ def test_kernel_switch_term_in_exact_gradient_form():
 def test_gpu_autograd_mode_returns_the_reference_autograd_forces():
     from torchmd_b200 import Forces
 
-    dev = "cuda:0"
+    dev = DEV
     g, ga = load_golden("water291_rf_switch"), load_golden("water291_autograd")
     par = params_from_golden(g, precision=torch.float32, device=dev)
     f = Forces(par, terms=[str(t) for t in g["terms"]], **golden_cfg(g))

@@ -99,3 +99,82 @@ def test_decomposed_step_matches_single_process_gloo():
         assert p.exitcode == 0
     results = dict(out.get(timeout=10) for _ in range(world))
     assert results == {0: True, 1: True}
+
+
+def _worker_integrator(rank, world, port, out):
+    """DecomposedIntegrator itself (its real step sequence through the C ABI, gloo all-gather) on the host
+    SIMT-interpreter build of the library (tests/simt) against the undecomposed Integrator in the same process."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import test_simt_kernels as T
+    from torchmd_b200 import Forces, Integrator, System, _lib, maxwell_boltzmann, testsystems
+    from torchmd_b200.domain import DecomposedIntegrator
+
+    class _Stream:
+        cuda_stream = None
+
+    _lib._lib = T.load(os.path.join(T.SIMT_DIR, "libtmd_simt.so"))  # (built by the parent)
+    _lib.on_device = lambda t: True
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.current_device = lambda: 0
+    torch.cuda.synchronize = lambda *a, **k: None
+
+    sysd = testsystems.water_box(64, seed=3)
+    n = len(sysd["coords"])
+
+    def make():
+        par = testsystems.water_parameters(sysd)
+        s = System(n, 1, torch.float32, "cpu")
+        s.set_positions(sysd["coords"])
+        s.set_box(sysd["box"])
+        torch.manual_seed(4)
+        s.set_velocities(maxwell_boltzmann(par.masses, 300.0, 1))
+        f = Forces(par, terms=["lj", "electrostatics", "bonds", "angles"], cutoff=5.0, rfa=True, switch_dist=4.0, skin=0.4)
+        return par, s, f
+
+    par, s1, f1 = make()
+    f1.compute(s1.pos, s1.box, s1.forces)
+    torch.manual_seed(9)
+    single = Integrator(s1, f1, 1.0, "cpu", gamma=0.1, T=300.0)
+    par, s2, f2 = make()
+    f2.compute(s2.pos, s2.box, s2.forces)
+    torch.manual_seed(9)
+    dec = DecomposedIntegrator(s2, f2, 1.0, "cpu", gamma=0.1, T=300.0, use_graph=False)
+    ok = dec.exchange == "allgather" and single.seed == dec.integ.seed
+    for niter in (1, 6):
+        e1 = single.step(niter)
+        e2 = dec.step(niter)
+        lo, hi = dec.dec.lo, dec.dec.hi
+        ok = ok and torch.equal(s1.pos, s2.pos) and torch.equal(s1.vel[:, lo:hi], s2.vel[:, lo:hi])
+        ok = ok and abs(e1[1][0] - e2[1][0]) <= 1e-9 * abs(e1[1][0]) + 1e-9 and abs(float(e1[0][0]) - float(e2[0][0])) <= 1e-4 * abs(float(e1[0][0]))
+    ok = ok and f2.stats()["rebuilds"] >= 2
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_decomposed_integrator_on_the_interpreter_matches_single_process_gloo():
+    """world_size 2 over gloo: the N>1 host path (owned ranges, exchange, energy all-reduce, shared noise seed)
+    follows the single-process trajectory bit for bit."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_simt_kernels as T
+
+    T.build_simt()
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_integrator, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    results = dict(out.get(timeout=10) for _ in range(world))
+    assert results == {0: True, 1: True}

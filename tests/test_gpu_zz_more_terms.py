@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from conftest import load_golden
+import test_gpu_forces
 from test_gpu_forces import force_tol, run_gpu
 
 pytestmark = pytest.mark.gpu
@@ -37,8 +38,8 @@ def test_device_cell_grid_matches_host_description():
     from torchmd_b200.neighbourlist import cell_grid, neighbour_list
 
     sysd = testsystems.water_box(1000, seed=5)
-    par = testsystems.water_parameters(sysd, device="cuda:0")
-    system = System(len(sysd["coords"]), 1, torch.float32, "cuda:0")
+    par = testsystems.water_parameters(sysd, device=test_gpu_forces.DEV)
+    system = System(len(sysd["coords"]), 1, torch.float32, test_gpu_forces.DEV)
     system.set_positions(sysd["coords"])
     system.set_box(sysd["box"])
     f = Forces(par, terms=["lj", "electrostatics"], cutoff=9.0, rfa=True, switch_dist=7.5, skin=1.0)

@@ -1,0 +1,87 @@
+"""The `-m gpu` tests themselves, run on the CPU: the Python mirrors (Forces, Integrator, Wrapper, the autograd
+path) drive the C ABI of the host SIMT-interpreter build of the library (tests/simt) with CPU tensors.
+
+The product refuses that build (torchmd_b200/_lib.py) and refuses CPU tensors; here, and only here, the loaded
+handle, the "is on the device" predicate and torch's stream query are patched so that the *same test functions*
+that run on the B200 execute every line of the host classes and of the C entry points without a GPU.  It checks
+plumbing and logic (argument marshalling, return formats, rebuild protocol, error paths) -- what the B200 run adds
+is the device arithmetic and speed.  The slow cases stay with the GPU suite.
+"""
+import numpy as np
+import pytest
+import torch
+
+import test_simt_kernels as T
+
+
+class _Stream:
+    cuda_stream = None  # the interpreter runs every launch on the spot
+
+
+@pytest.fixture
+def hostsim(monkeypatch):
+    from torchmd_b200 import _lib
+
+    handle = T.load(T.build_simt())
+    monkeypatch.setattr(_lib, "_lib", handle)
+    monkeypatch.setattr(_lib, "on_device", lambda t: True)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    import test_autograd_path, test_gpu_forces, test_gpu_integrator, test_wrapper
+
+    for mod in (test_autograd_path, test_gpu_forces, test_gpu_integrator, test_wrapper):
+        monkeypatch.setattr(mod, "DEV", "cpu")
+    return handle
+
+
+FORCE_CASES = ["water291_rf_switch", "water291_plain", "argon100_nocut", "chain_amber_vacuum", "chain_amber_periodic",
+               "chain_charmm_periodic", "ala2_xsc_rf"]
+
+
+@pytest.mark.parametrize("name", FORCE_CASES)
+def test_forces_compute_against_the_goldens(hostsim, name):
+    import test_gpu_forces as G
+
+    G.test_golden_forces_energies(name)
+    if name != "water291_plain":
+        G.test_golden_neighbour_pairs_bit_exact(name)
+
+
+def test_forces_api_formats_errors_replicas_and_skin(hostsim):
+    import test_gpu_forces as G
+
+    G.test_api_errors_and_formats()
+    G.test_forces_deterministic_and_replicas_identical()
+    G.test_results_do_not_depend_on_skin(0.3)
+
+
+def test_repulsion_terms(hostsim):
+    import test_gpu_zz_more_terms as M
+
+    M.test_repulsion_terms("argon100_lj_rep_mix")
+
+
+def test_integrator_step(hostsim):
+    import test_gpu_integrator as I
+
+    I.test_initialization_attributes()
+    I.test_velocity_verlet_constant_force_known_answer(2)
+    I.test_batch_kinetic_energy()
+    I.test_nve_trajectory_matches_reference()
+    I.test_langevin_with_injected_noise_matches_reference()
+    I.test_stepwise_and_fused_paths_agree()
+
+
+@pytest.mark.parametrize("name", ["water", "mixed", "nobonds", "zerobox"])
+def test_wrapper_wrap(hostsim, name):
+    import test_wrapper as W
+
+    getattr(W.test_gpu_wrap_matches_reference_golden, "__wrapped__", W.test_gpu_wrap_matches_reference_golden)(name)
+
+
+def test_autograd_path(hostsim):
+    import test_autograd_path as A
+
+    A.test_gpu_autograd_mode_returns_the_reference_autograd_forces()
+    A.test_gpu_energy_backward_and_vmap()

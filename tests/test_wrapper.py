@@ -17,6 +17,7 @@ import torch
 from conftest import ROOT, load_golden
 from oracle import refmd
 
+DEV = "cuda:0"  # (tests/test_mirrors_on_interpreter.py runs the gpu tests on the host interpreter with "cpu")
 CASES = ["water", "mixed", "nobonds", "zerobox"]
 
 
@@ -89,7 +90,7 @@ def test_gpu_wrap_matches_reference_golden(name):
 
     g = load_golden("wrap_cases")
     natoms, bonds, pos, box, after = case(g, name)
-    w = Wrapper(natoms, bonds, "cuda:0")
-    p = torch.tensor(pos, device="cuda:0")
-    w.wrap(p, torch.tensor(box, device="cuda:0"))
+    w = Wrapper(natoms, bonds, DEV)
+    p = torch.tensor(pos, device=DEV)
+    w.wrap(p, torch.tensor(box, device=DEV))
     assert np.array_equal(p.cpu().numpy(), after)

@@ -116,6 +116,11 @@ def lib():
     return _lib
 
 
+def on_device(t):
+    """True for a tensor in CUDA memory -- the one definition the host classes use for "must be a CUDA tensor"."""
+    return bool(t.is_cuda)
+
+
 class TmdError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"tmd_b200 error {code}: {msg}")

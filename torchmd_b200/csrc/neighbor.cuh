@@ -60,6 +60,13 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, fl
 }
 
 // ---- every call ---------------------------------------------------------------
+// -DTMD_COND_NODE=1 compiles the device-side switch of the rebuild's CUDA-graph conditional node
+// (cudaGraphSetConditional, a driver-resolved builtin: the module then carries an undefined symbol
+// that is bound at load time).  Off in the default build until a B200 has loaded such a module:
+// the standing library contains nothing that has not run on the hardware.
+#ifndef TMD_COND_NODE
+#define TMD_COND_NODE 0
+#endif
 // One atom of the per-call preparation: displacement trigger against the positions of the last
 // rebuild, far-position check, refresh of the sorted records (float and fixed-point), largest
 // |coordinate|.  (x, y, z) is the atom's current position.
@@ -72,8 +79,10 @@ __device__ __forceinline__ void prepare_atom(const DeviceState& S, int r, int i,
   if (!(d2 <= S.trigger2)) {  // also true for NaN (= no list yet)
     if (fl[F_REBUILD0 + parity] == 0) {
       fl[F_REBUILD0 + parity] = 1;
+#if TMD_COND_NODE
       // inside a CUDA graph the rebuild kernels sit in the body of a conditional node: switch it on
       if (S.cond) cudaGraphSetConditional((cudaGraphConditionalHandle)S.cond, 1u);
+#endif
     }
   }
   if (S.check_far) {

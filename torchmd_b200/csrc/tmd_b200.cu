@@ -599,7 +599,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     const char* ec = getenv("TMD_B200_COND");
     const char* eg = getenv("TMD_B200_GRAPH");
     pv.use_graph = eg && eg[0] == '1';
-    pv.use_cond = (ec && ec[0] == '1') || pv.use_graph;
+    pv.use_cond = TMD_COND_NODE && ((ec && ec[0] == '1') || pv.use_graph);  // (without the node: five gated kernels, as in stream order)
     if (pv.use_cond && !pv.helper) TMD_CUDA(cudaStreamCreateWithFlags(&pv.helper, cudaStreamNonBlocking));
     if (pv.use_graph && !pv.gstream) {
       TMD_CUDA(cudaStreamCreateWithFlags(&pv.gstream, cudaStreamNonBlocking));

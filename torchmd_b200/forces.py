@@ -139,7 +139,7 @@ class Forces:
         return self._ava_idx
 
     def _check_tensor(self, t, name, shape=None):
-        if not torch.is_tensor(t) or not t.is_cuda:
+        if not torch.is_tensor(t) or not _lib.on_device(t):
             raise RuntimeError(f"{name} must be a CUDA tensor: torchmd_b200 has no CPU path")
         if t.dtype != torch.float32:
             raise NotImplementedError(f"{name} must be float32 (precision: single); got {t.dtype}")

@@ -89,14 +89,14 @@ class Integrator:
         s = self.systems
         for name in ("pos", "vel", "forces"):
             t = getattr(s, name)
-            if not t.is_cuda:
+            if not _lib.on_device(t):
                 raise RuntimeError(f"systems.{name} must live on a CUDA device: torchmd_b200 has no CPU path")
             if t.dtype != torch.float32 or not t.is_contiguous():
                 raise NotImplementedError(f"systems.{name} must be contiguous float32")
         m = self.masses
-        if not m.is_cuda or m.dtype != torch.float32 or not m.is_contiguous():
+        if not _lib.on_device(m) or m.dtype != torch.float32 or not m.is_contiguous():
             self.masses = m.to(device=s.pos.device, dtype=torch.float32).contiguous()
-        if self.T and (not self.vcoeff.is_cuda or self.vcoeff.dtype != torch.float32 or not self.vcoeff.is_contiguous()):
+        if self.T and (not _lib.on_device(self.vcoeff) or self.vcoeff.dtype != torch.float32 or not self.vcoeff.is_contiguous()):
             self.vcoeff = self.vcoeff.to(device=s.pos.device, dtype=torch.float32).contiguous()
 
     def _ctx(self):

@@ -79,7 +79,7 @@ class Wrapper:
 
     def _ensure(self, pos):
         if self._handle is None:
-            if pos.device.type != "cuda":
+            if not _lib.on_device(pos):
                 raise RuntimeError("torchmd_b200.Wrapper runs on CUDA tensors only (no CPU fallback)")
             h = C.c_void_p()
             _lib.check(_lib.lib().tmd_wrapper_create(C.byref(h), pos.device.index or 0, self.natoms, len(self._ptr) - 1,
