@@ -85,3 +85,11 @@ def test_autograd_path(hostsim):
 
     A.test_gpu_autograd_mode_returns_the_reference_autograd_forces()
     A.test_gpu_energy_backward_and_vmap()
+
+
+def test_smoke_entry_point(hostsim, capsys):
+    """__graft_entry__.smoke(), the function the driver runs on the B200 before the bench."""
+    import __graft_entry__ as g
+
+    g.smoke(dev="cpu")
+    assert "neighbour pairs bit-exact" in capsys.readouterr().out
