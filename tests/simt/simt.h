@@ -10,6 +10,7 @@
 // returned do not take part (CUDA semantics).  __activemask() first lets every other fiber advance
 // to its next parking point, then reports the lanes of the warp that are still alive.
 #pragma once
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <cstdlib>
@@ -33,10 +34,16 @@ struct Warp {
   unsigned long long in[32], aux[32], out[32];
 };
 
+// Context switches: a fiber is ENTERED through ucontext (makecontext/swapcontext), every later switch is a
+// _setjmp/_longjmp pair -- glibc's swapcontext saves and restores the signal mask with a system call per switch,
+// which was a third of the suite's run time.  -DSIMT_UCONTEXT_ONLY keeps swapcontext throughout (AddressSanitizer
+// build: it follows swapcontext but not a longjmp between stacks).  The build passes -U_FORTIFY_SOURCE: the
+// fortified longjmp refuses jumps to a lower stack address.
 struct Fiber {
   ucontext_t ctx;
-  std::unique_ptr<char[]> stack;
+  jmp_buf jb;
   bool done = false;
+  bool started = false;
 };
 
 struct Block {
@@ -45,6 +52,7 @@ struct Block {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   ucontext_t sched;
+  jmp_buf sched_jb;
   int cur = -1;           // running fiber
   int live = 0;           // threads that have not returned
   int bar_arrived = 0;    // __syncthreads
@@ -61,9 +69,27 @@ inline Block*& current() {
 inline int tid() { return current()->cur; }
 inline int lane() { return current()->cur & 31; }
 inline Warp& warp() { return current()->warps[current()->cur >> 5]; }
+inline void to_scheduler(Block* b, Fiber& f) {
+#if defined(SIMT_UCONTEXT_ONLY)
+  swapcontext(&f.ctx, &b->sched);
+#else
+  if (_setjmp(f.jb) == 0) _longjmp(b->sched_jb, 1);
+#endif
+}
+inline void to_fiber(Block& b, Fiber& f) {
+#if defined(SIMT_UCONTEXT_ONLY)
+  swapcontext(&b.sched, &f.ctx);
+#else
+  if (_setjmp(b.sched_jb) == 0) {
+    if (f.started) _longjmp(f.jb, 1);
+    f.started = true;
+    swapcontext(&b.sched, &f.ctx);  // first entry; the fiber comes back through sched_jb
+  }
+#endif
+}
 inline void yield() {
   Block* b = current();
-  swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+  to_scheduler(b, b->fibers[b->cur]);
 }
 inline long long fake_clock() { return current()->clock += 1000; }
 
@@ -160,7 +186,7 @@ inline void fiber_main() {
     b->bar_arrived = 0;
     b->bar_gen++;
   }
-  swapcontext(&b->fibers[t].ctx, &b->sched);
+  to_scheduler(b, b->fibers[t]);
 }
 
 // Scheduling order, from the environment (read once): SIMT_SCHEDULE = "forward" (default), "reverse", or
@@ -216,9 +242,12 @@ inline void run_block(Block& b) {
   b.bar_or = 0;
   for (int t = 0; t < b.nthreads; ++t) {
     Fiber& f = b.fibers[t];
-    f.stack.reset(new char[STACK]);
+    // stacks are kept for the next block (blocks run one after the other): no mmap/munmap and page faults per fiber
+    static std::vector<std::unique_ptr<char[]>> pool;
+    if ((int)pool.size() <= t) pool.resize(t + 1);
+    if (!pool[t]) pool[t].reset(new char[STACK]);
     getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack.get();
+    f.ctx.uc_stack.ss_sp = pool[t].get();
     f.ctx.uc_stack.ss_size = STACK;
     f.ctx.uc_link = &b.sched;
     makecontext(&f.ctx, (void (*)())fiber_main, 0);
@@ -237,7 +266,7 @@ inline void run_block(Block& b) {
       const int t = turn[k];
       if (b.fibers[t].done) continue;
       b.cur = t;
-      swapcontext(&b.sched, &b.fibers[t].ctx);
+      to_fiber(b, b.fibers[t]);
       if (b.fibers[t].done) {
         --remaining;
         ++progressed;

@@ -18,12 +18,14 @@ pytestmark = [
                        reason="peer-to-peer exchange: not yet validated on a B200 (set TMD_B200_VALIDATE=1)"),
 ]
 DEV = "cuda:0"
+# (tests/test_mirrors_on_interpreter.py runs this test on the host interpreter with a smaller system)
+SIZE = dict(waters=1000, cutoff=9.0, switch=7.5, skin=None, steps=(1, 2, 37), backend="nccl")
 
 
 def _setup(seed=3):
     from torchmd_b200 import Forces, System, maxwell_boltzmann, testsystems
 
-    sysd = testsystems.water_box(1000, seed=seed)
+    sysd = testsystems.water_box(SIZE["waters"], seed=seed)
     par = testsystems.water_parameters(sysd, device=DEV)
     n = len(sysd["coords"])
     system = System(n, 1, torch.float32, DEV)
@@ -31,7 +33,7 @@ def _setup(seed=3):
     system.set_box(sysd["box"])
     torch.manual_seed(5)
     system.set_velocities(maxwell_boltzmann(par.masses, 300.0, 1))
-    forces = Forces(par, terms=["lj", "electrostatics", "bonds", "angles"], cutoff=9.0, rfa=True, switch_dist=7.5)
+    forces = Forces(par, terms=["lj", "electrostatics", "bonds", "angles"], cutoff=SIZE["cutoff"], rfa=True, switch_dist=SIZE["switch"], skin=SIZE["skin"])
     forces.compute(system.pos, system.box, system.forces)
     return system, forces
 
@@ -44,7 +46,10 @@ def test_p2p_world1_matches_integrator_bitwise(use_graph):
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29573")
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+        if SIZE["backend"] == "nccl":
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+        else:
+            dist.init_process_group(SIZE["backend"], rank=0, world_size=1)
     sa, fa = _setup()
     torch.manual_seed(9)
     ia = Integrator(sa, fa, 1.0, DEV, gamma=0.1, T=300.0)
@@ -52,7 +57,7 @@ def test_p2p_world1_matches_integrator_bitwise(use_graph):
     torch.manual_seed(9)
     ib = DecomposedIntegrator(sb, fb, 1.0, DEV, gamma=0.1, T=300.0, use_graph=use_graph, exchange="p2p")
     assert ib.integ.seed == ia.seed and ib.exchange == "p2p"
-    for niter in (1, 2, 37):  # odd and even counts: both buffer parities start and end a call
+    for niter in SIZE["steps"]:  # odd and even counts: both buffer parities start and end a call
         ea = ia.step(niter=niter)
         eb = ib.step(niter=niter)
         assert torch.equal(sa.pos, sb.pos) and torch.equal(sa.vel, sb.vel)

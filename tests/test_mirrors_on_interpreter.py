@@ -93,3 +93,42 @@ def test_smoke_entry_point(hostsim, capsys):
 
     g.smoke(dev="cpu")
     assert "neighbour pairs bit-exact" in capsys.readouterr().out
+
+
+# ---- the gated tests (TMD_B200_VALIDATE=1 on a B200) of the opt-in kernels, as written, on the interpreter ----
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gated_fixed_point_tests_run_as_written(hostsim, monkeypatch, mode):
+    import test_gpu_zzz_fixedpoint as X
+
+    monkeypatch.setattr(X, "DEV", "cpu")
+    X.test_fixed_point_kernel_matches_golden("chain_amber_periodic", mode)
+    X.test_fixed_point_kernel_matches_golden("water999_eq", mode)
+    if mode == 2:
+        X.test_packed_kernel_without_a_box("chain_amber_vacuum")
+        X.test_fixed_point_kernel_is_accurate_for_drifted_molecules()
+    # (test_fixed_point_trajectory_tracks_float_kernel and the 3000-atom box stay with the B200: hundreds of steps)
+
+
+def test_gated_peer_to_peer_test_runs_as_written(hostsim, monkeypatch):
+    """DecomposedIntegrator(exchange="p2p") with one rank: IPC set-up, double-buffered positions, push kernel, flag
+    wait -- bitwise equal to Integrator.step (smaller system than on the B200, gloo instead of NCCL)."""
+    import torch.distributed as dist
+
+    import test_gpu_zzz_p2p as P
+
+    monkeypatch.setattr(P, "DEV", "cpu")
+    monkeypatch.setattr(P, "SIZE", dict(waters=64, cutoff=5.0, switch=4.0, skin=0.3, steps=(1, 2, 7), backend="gloo"))
+    monkeypatch.setenv("MASTER_PORT", str(T_free_port()))
+    try:
+        P.test_p2p_world1_matches_integrator_bitwise(False)
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def T_free_port():
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]

@@ -32,9 +32,9 @@ VARIANTS = {  # tag -> defines; every interpreter build the tests use (built tog
 
 
 def _simt_command(out, defines):
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(SIMT_DIR, "stub"), "-I", CSRC]
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-U_FORTIFY_SOURCE", "-I", os.path.join(SIMT_DIR, "stub"), "-I", CSRC]
     if "TMD_SIMT_ASAN=1" in defines:  # scripts/asan_interpreter.py
-        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DSIMT_UCONTEXT_ONLY"]
     return cmd + [f"-D{d}" for d in defines] + ["-o", out, os.path.join(SIMT_DIR, "simt_lib.cpp")]
 
 

@@ -27,7 +27,7 @@ def selftest_lib():
     out = os.path.join(SIMT_DIR, "libsimt_selftest.so")
     srcs = [os.path.join(SIMT_DIR, f) for f in ("selftest.cpp", "simt.h", os.path.join("stub", "cuda_runtime.h"))]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(SIMT_DIR, "stub"), "-I", SIMT_DIR,
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-U_FORTIFY_SOURCE", "-I", os.path.join(SIMT_DIR, "stub"), "-I", SIMT_DIR,
                         "-o", out, os.path.join(SIMT_DIR, "selftest.cpp")], check=True, cwd=ROOT)
     return out
 
