@@ -14,17 +14,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(dev=None, waters=1000, cutoff=9.0, switch=7.5, skin=None, steps=(1, 2, 61), graphs=(False, True)):
+    """(The keyword arguments exist for tests/test_mirrors_on_interpreter.py, which runs this function with one
+    rank on the host interpreter build; under torchrun on a GPU box the defaults apply.)"""
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ.pop("NCCL_DEBUG", None)
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    dist.init_process_group("nccl", device_id=torch.device(dev))
+    if dev is None:
+        torch.cuda.set_device(local)
+        dev = f"cuda:{local}"
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    else:
+        dist.init_process_group("gloo")
     from torchmd_b200 import Forces, System, maxwell_boltzmann, testsystems
     from torchmd_b200.domain import DecomposedIntegrator
 
     def make(exchange, use_graph):
-        sysd = testsystems.water_box(1000, seed=3)
+        sysd = testsystems.water_box(waters, seed=3)
         par = testsystems.water_parameters(sysd, device=dev)
         n = len(sysd["coords"])
         system = System(n, 1, torch.float32, dev)
@@ -32,14 +37,14 @@ def main():
         system.set_box(sysd["box"])
         torch.manual_seed(5)
         system.set_velocities(maxwell_boltzmann(par.masses, 300.0, 1))
-        forces = Forces(par, terms=["lj", "electrostatics", "bonds", "angles"], cutoff=9.0, rfa=True, switch_dist=7.5)
+        forces = Forces(par, terms=["lj", "electrostatics", "bonds", "angles"], cutoff=cutoff, rfa=True, switch_dist=switch, skin=skin)
         torch.manual_seed(9)
         integ = DecomposedIntegrator(system, forces, 1.0, dev, gamma=0.1, T=300.0, use_graph=use_graph, exchange=exchange)
         forces.compute(system.pos, system.box, system.forces)
         return system, forces, integ
 
     ok = True
-    for use_graph in (False, True):
+    for use_graph in graphs:
         sa, fa, ia = make("allgather", use_graph)
         sb, fb, ib = make("p2p", use_graph)
         if ib.exchange != "p2p":
@@ -47,7 +52,7 @@ def main():
                 print("P2P_CHECK FAIL: the peer-to-peer exchange could not be set up (see stderr)", flush=True)
             dist.destroy_process_group()
             sys.exit(2)
-        for niter in (1, 2, 61):
+        for niter in steps:
             ea = ia.step(niter=niter)
             eb = ib.step(niter=niter)
             same = bool(torch.equal(sa.pos, sb.pos) and torch.equal(sa.vel, sb.vel))

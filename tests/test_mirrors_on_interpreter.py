@@ -132,3 +132,25 @@ def T_free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def test_multi_rank_check_script_runs_with_one_rank(hostsim, monkeypatch, capsys):
+    """scripts/p2p_check.py (the round-2 multi-GPU check of the peer-to-peer exchange against the all-gather path)
+    executed with a single rank: its own logic is sound before box time is spent on it."""
+    import importlib.util
+    import os
+
+    import torch.distributed as dist
+
+    spec = importlib.util.spec_from_file_location("p2p_check", os.path.join(T.ROOT, "scripts", "p2p_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for k, v in dict(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(T_free_port())).items():
+        monkeypatch.setenv(k, v)
+    try:
+        with pytest.raises(SystemExit) as done:
+            mod.main(dev="cpu", waters=64, cutoff=5.0, switch=4.0, skin=0.3, steps=(1, 2, 7), graphs=(False,))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    assert done.value.code == 0 and "P2P_CHECK PASS" in capsys.readouterr().out
