@@ -220,6 +220,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------
+DEVICE_OVERRIDE = None  # tests/test_mirrors_on_interpreter.py dry-runs gpu_arm on the host interpreter build with "cpu"
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -233,8 +236,9 @@ def gpu_arm(args):
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None)  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
+    dev = DEVICE_OVERRIDE or f"cuda:{local}"
+    if DEVICE_OVERRIDE is None:
+        torch.cuda.set_device(local)
     if world > 1:
         from torchmd_b200 import domain  # spatial decomposition driver
 

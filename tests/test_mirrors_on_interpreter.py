@@ -154,3 +154,54 @@ def test_multi_rank_check_script_runs_with_one_rank(hostsim, monkeypatch, capsys
         if dist.is_initialized():
             dist.destroy_process_group()
     assert done.value.code == 0 and "P2P_CHECK PASS" in capsys.readouterr().out
+
+
+def test_bench_single_gpu_arm_dry_run(hostsim, monkeypatch, capsys):
+    """bench.py's own single-GPU body on a 64-water box: every library call, the profiling hooks, the host-buffer
+    entry and the JSON line's keys -- a bench that dies on a typo at round end has no number at all."""
+    import argparse
+    import json
+
+    import bench
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, *a):
+            import time
+
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    real_empty = torch.empty
+
+    def empty(*a, **k):
+        k.pop("pin_memory", None)
+        return real_empty(*a, **k)
+
+    class _NoSampler:
+        def __init__(self, *a):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch, "empty", empty)
+    monkeypatch.setattr(bench, "ClockSampler", _NoSampler)
+    monkeypatch.setattr(bench, "N_WATERS", 64)
+    monkeypatch.setattr(bench, "CFG", dict(bench.CFG, cutoff=5.0, switch_dist=4.0))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(bench, "DEVICE_OVERRIDE", "cpu")
+    args = argparse.Namespace(gpus=1, steps=6, warmup=3, equil=100, e2e_steps=3, no_cpu_baseline=True, impl="ours")
+    bench.gpu_arm(args)
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["gpu_launches"] > 0 and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["roofline"]["pairs_in_cutoff"] > 0 and line["roofline"]["launches_sampled"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
