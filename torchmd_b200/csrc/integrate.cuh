@@ -164,13 +164,13 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t step, uint64_t s
 
 // [vel += ((-gamma*vel)*dt + xi*vcoeff)]  then  vel += (0.5*dt)*(F/m)
 // (integrator.py:72-74 then 67-69), optionally followed by the kinetic energy.
-template <bool THERMOSTAT, bool KINETIC>
-__global__ void __launch_bounds__(INTEG_THREADS)
-k_vv_second(int natoms, int lo, int cnt, const unsigned long long* __restrict__ counters,
-            float* __restrict__ vel, const float* __restrict__ forces,
-            const float* __restrict__ masses, float dt, float hdt, float neg_gamma,
-            const float* __restrict__ vcoeff, const float* __restrict__ noise, uint64_t seed,
-            uint64_t step_offset, double* __restrict__ ke) {
+template <bool THERMOSTAT, bool KINETIC, bool FOLD>
+__device__ __forceinline__ void vv_second_body(int natoms, int lo, int cnt, const unsigned long long* __restrict__ counters,
+                                               float* __restrict__ vel, const float* __restrict__ forces,
+                                               const float* __restrict__ masses, float dt, float hdt, float neg_gamma,
+                                               const float* __restrict__ vcoeff, const float* __restrict__ noise,
+                                               uint64_t seed, uint64_t step_offset, double* __restrict__ ke,
+                                               float* forces_rw, const double* __restrict__ scratch) {
   const int r = blockIdx.y;
   const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t step = step_offset + counters[1];  // device-resident step count: graph replayable
@@ -192,9 +192,20 @@ k_vv_second(int natoms, int lo, int cnt, const unsigned long long* __restrict__ 
     float v2 = 0.f;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
+      float f;
+      if (FOLD) {  // k_add_bonded's work (bonded.cuh): the bonded sums of the overlapped k_bonded, rounded once
+        f = forces_rw[a + d];
+        const double sb = scratch[a + d];
+        if (sb != 0.0) {
+          f = (float)((double)f + sb);
+          forces_rw[a + d] = f;
+        }
+      } else {
+        f = forces[a + d];
+      }
       float v = vel[a + d];
       if (THERMOSTAT) v = add_rn(v, add_rn(mul_rn(mul_rn(neg_gamma, v), dt), mul_rn(xi[d], vc)));
-      v = add_rn(v, mul_rn(hdt, div_rn(forces[a + d], m)));
+      v = add_rn(v, mul_rn(hdt, div_rn(f, m)));
       vel[a + d] = v;
       v2 += v * v;
     }
@@ -204,6 +215,30 @@ k_vv_second(int natoms, int lo, int cnt, const unsigned long long* __restrict__ 
     __shared__ double red[INTEG_THREADS / 32];
     block_accumulate<INTEG_THREADS / 32>(ek, ke + r, red);
   }
+}
+
+template <bool THERMOSTAT, bool KINETIC>
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_vv_second(int natoms, int lo, int cnt, const unsigned long long* __restrict__ counters,
+            float* __restrict__ vel, const float* __restrict__ forces,
+            const float* __restrict__ masses, float dt, float hdt, float neg_gamma,
+            const float* __restrict__ vcoeff, const float* __restrict__ noise, uint64_t seed,
+            uint64_t step_offset, double* __restrict__ ke) {
+  vv_second_body<THERMOSTAT, KINETIC, false>(natoms, lo, cnt, counters, vel, forces, masses, dt, hdt, neg_gamma, vcoeff, noise, seed,
+                                             step_offset, ke, nullptr, nullptr);
+}
+
+// k_add_bonded + k_vv_second in one pass (tmd_md_steps with the bonded kernel overlapped on a second stream): the
+// forces get the bonded sums with the same single rounding and are written back for the next half-kick.
+template <bool THERMOSTAT, bool KINETIC>
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_vv_second_fold(int natoms, int lo, int cnt, const unsigned long long* __restrict__ counters,
+                 float* __restrict__ vel, float* __restrict__ forces,
+                 const float* __restrict__ masses, float dt, float hdt, float neg_gamma,
+                 const float* __restrict__ vcoeff, const float* __restrict__ noise, uint64_t seed,
+                 uint64_t step_offset, double* __restrict__ ke, const double* __restrict__ scratch) {
+  vv_second_body<THERMOSTAT, KINETIC, true>(natoms, lo, cnt, counters, vel, nullptr, masses, dt, hdt, neg_gamma, vcoeff, noise, seed,
+                                            step_offset, ke, forces, scratch);
 }
 
 __global__ void __launch_bounds__(INTEG_THREADS)

@@ -123,6 +123,8 @@ struct CtxPriv {
   // TMD_B200_FUSEPREP=1: tmd_md_steps moves the atoms and prepares the force call in one kernel
   // (k_vv_first_prepare); the handle of the rebuild's conditional node is then made before that launch
   bool fuse_prepare = false;
+  bool fold_next = false;                       // tmd_md_steps: the vv_second that follows folds the bonded sums in (k_vv_second_fold)
+  bool fold_pending = false;                    // set by enqueue_forces when it left them in the scratch buffer
   bool prepared = false;                        // the next enqueue_forces finds k_prepare's work done
   cudaGraphConditionalHandle prepared_cond = 0; // and this handle already handed to the kernel
   bool dirty = true;
@@ -806,8 +808,12 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   if (overlap) {
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_join, 0));
-    launch(k_add_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
-    TMD_LAUNCHED(ctx, "k_add_bonded");
+    if (pv.fold_next) {  // the integrator kernel that follows adds them (enqueue_vv_second)
+      pv.fold_pending = true;
+    } else {
+      launch(k_add_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
+      TMD_LAUNCHED(ctx, "k_add_bonded");
+    }
   } else if (have_bonded) {
     launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, d, T, ctx->q, pos, forces, energies, nullptr);
     TMD_LAUNCHED(ctx, "k_bonded");
@@ -852,6 +858,20 @@ static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, cons
   const unsigned long long* ctr = ctx->d.counters;
   const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-gamma);
   if (ke) TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
+  if (priv(ctx).fold_pending) {
+    priv(ctx).fold_pending = false;
+    float* fw = const_cast<float*>(forces);  // (tmd_md_steps owns this buffer: it handed it to enqueue_forces as the output)
+    const double* sc = priv(ctx).bonded_scratch;
+    if (thermo) {
+      if (ke) launch(k_vv_second_fold<true, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+      else launch(k_vv_second_fold<true, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+    } else {
+      if (ke) launch(k_vv_second_fold<false, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+      else launch(k_vv_second_fold<false, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+    }
+    TMD_LAUNCHED(ctx, "k_vv_second_fold");
+    return TMD_OK;
+  }
   if (thermo) {
     if (ke) launch(k_vv_second<true, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
     else launch(k_vv_second<true, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, forces, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
@@ -912,6 +932,12 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
   const size_t per_step = (size_t)ctx->nrep * ctx->natoms * 3;
   CtxPriv& pv = priv(ctx);
   pv.prepared = false;
+  pv.fold_pending = false;
+  struct FoldScope {  // only inside tmd_md_steps does a vv_second follow every force call
+    CtxPriv& p;
+    explicit FoldScope(CtxPriv& q, bool on) : p(q) { p.fold_next = on; }
+    ~FoldScope() { p.fold_next = false; }
+  } fold_scope(pv, pv.fuse_prepare);
   if (pv.use_graph && !noise && !pv.profiling && niter > 0) {
     // One MD step captured once (with and without the energy outputs) and replayed: one graph
     // launch per step, the rebuild kernels inside a conditional node.  Everything that changes
