@@ -21,7 +21,7 @@ def main():
     import test_simt_kernels as T
     from conftest import load_golden
 
-    L = T.load(T.build_simt("_asan", ["BT_CULL=1", "TMD_SIMT_ASAN=1"]))
+    L = T.load(T.build_simt("_asan", ["BT_CULL=1", "BT_PAIRED=1", "TMD_SIMT_ASAN=1"]))
     for name, env, kw in (
         ("chain_amber_periodic", {"TMD_B200_FX": "2"}, {}),
         ("water291_rf_switch", {}, {}),

@@ -72,6 +72,10 @@ if has 4; then
   $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
   run_suite cull TMD_B200_LIB=/tmp/var/lib_cull.so
   for fx in 0 2; do run_bench "BT_CULL=1 FX=$fx" cull_fx$fx TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=$fx; done
+  # two atoms of a cell per warp pass, packed distance arithmetic
+  $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -o /tmp/var/lib_paired.so torchmd_b200/csrc/tmd_b200.cu
+  run_suite paired TMD_B200_LIB=/tmp/var/lib_paired.so
+  for fx in 0 2; do run_bench "BT_CULL=1 BT_PAIRED=1 FX=$fx" paired_fx$fx TMD_B200_LIB=/tmp/var/lib_paired.so TMD_B200_FX=$fx; done
 fi
 if has 5; then
   run_suite overlap TMD_B200_OVERLAP=1
@@ -89,12 +93,12 @@ fi
 if has 7; then
   run_suite fuseprep TMD_B200_FUSEPREP=1
   for fx in 0 2; do run_bench "FUSEPREP=1 FX=$fx" fuse_fx$fx TMD_B200_FUSEPREP=1 TMD_B200_FX=$fx; done
-  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
+  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
   run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
   run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1
 fi
 if has 8; then
-  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
+  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
   ALL="TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_FUSEPREP=1"
   run_suite all $ALL
   run_suite all_graph $ALL TMD_B200_GRAPH=1

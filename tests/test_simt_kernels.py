@@ -24,6 +24,7 @@ CSRC = os.path.join(ROOT, "torchmd_b200", "csrc")
 VARIANTS = {  # tag -> defines; every interpreter build the tests use (built together, in parallel, when stale)
     "": [],
     "_cull": ["BT_CULL=1"],
+    "_paired": ["BT_CULL=1", "BT_PAIRED=1"],
     "_t2": ["FX_SMALLT_MAX_N=2"],
     "_fxu4": ["PAIR_FX_UNROLL=4"],
     "_fx2u2": ["PAIR_FX2_UNROLL=2"],
@@ -77,9 +78,10 @@ def simt():
     return load(build_simt())
 
 
-@pytest.fixture(scope="module")
-def simt_cull():
-    return load(build_simt("_cull", ["BT_CULL=1"]))
+@pytest.fixture(scope="module", params=["_cull", "_paired"])
+def simt_cull(request):
+    """The list build with chunk culling, one atom or two atoms of a cell per warp pass."""
+    return load(build_simt(request.param, VARIANTS[request.param]))
 
 
 class Ctx:

@@ -381,6 +381,7 @@ struct BuildShared {
 #if BT_CULL
   float bb[BT_CHUNKS][6];   // per chunk: min x,y,z, max x,y,z over its finite records
   int jr[BT_CHUNKS][2];     // per chunk: smallest / largest sorted atom index among its records
+  float2 pp[BT_WARPS][4];   // BT_PAIRED: per warp, the x / y / z of its two atoms side by side (read back as register pairs)
 #endif
 };
 
@@ -555,6 +556,190 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
   }
 }
 
+// BT_PAIRED=1 (with BT_CULL=1): a warp takes TWO atoms of the cell through the staged chunks at a time.  The
+// candidate record is loaded once for both, the two separations and squared distances are packed fp32x2
+// operations (physics.cuh F2: same rounding per half as the scalar expressions), and a chunk is visited if either
+// atom's bounding-box test asks for it -- a chunk that an atom's own test had culled holds no candidate within its
+// list radius, so visiting it adds nothing to that atom's row.  Rows come out in the same order as in the one-atom
+// loop.  Off until measured on a B200.
+#ifndef BT_PAIRED
+#define BT_PAIRED 0
+#endif
+#if BT_CULL && BT_PAIRED
+struct BuildAtom {
+  int k;                        // sorted index
+  float4 pi;                    // folded position
+  int ne, e0, my_excl;          // exclusions: count, CSR offset, this lane's (first 32) as a sorted index
+  int exlo, exhi;               // index range that holds the atom and its exclusions
+  unsigned long long row_addr;  // its row
+  int count;
+  unsigned store;               // all ones if rows are written for this atom, 0 for a stand-in
+};
+
+template <bool WRAP>
+__device__ __forceinline__ void build_process_tile_paired(const DeviceState& S, const Grid& g, size_t base,
+                                                          BuildShared& sh, int fill, int b0, int nib, bool w0,
+                                                          bool w1, bool w2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  float rl2 = S.rlist2;
+  int cap = S.row_cap;
+  TMD_PIN_F(rl2);
+  TMD_PIN_R(cap);
+  const int nchunks = (fill + 31) >> 5;
+
+  auto owned = [&](int k) {
+    if (S.own_all) return true;
+    const int io = S.perm[base + k];
+    return io >= S.own_lo && io < S.own_lo + S.own_n;
+  };
+  auto load_atom = [&](int k, int ii, bool store) {
+    BuildAtom a;
+    a.k = k;
+    a.pi = S.xw_s[base + k];
+    a.ne = 0; a.e0 = 0; a.my_excl = -1;
+    a.exlo = 0x7fffffff; a.exhi = -1;
+    if (S.excl_ptr) {
+      const int io = S.perm[base + k];
+      a.e0 = S.excl_ptr[io];
+      a.ne = S.excl_ptr[io + 1] - a.e0;
+      for (int eb = 0; eb < a.ne; eb += 32) {
+        const int v = (eb + lane < a.ne) ? S.inv[base + S.excl_idx[a.e0 + eb + lane]] : -1;
+        if (eb == 0) a.my_excl = v;
+        if (v >= 0) { a.exlo = min(a.exlo, v); a.exhi = max(a.exhi, v); }
+      }
+      for (int o = 16; o; o >>= 1) {
+        a.exlo = min(a.exlo, __shfl_xor_sync(0xffffffffu, a.exlo, o));
+        a.exhi = max(a.exhi, __shfl_xor_sync(0xffffffffu, a.exhi, o));
+      }
+    }
+    a.exlo = min(a.exlo, k);
+    a.exhi = max(a.exhi, k);
+    a.row_addr = reinterpret_cast<unsigned long long>(S.nbr + (base + k) * (size_t)cap);
+    a.count = sh.counts[ii];
+    a.store = store ? 0xffffffffu : 0u;
+    return a;
+  };
+  // chunks within the list radius of the atom (lane c tests chunks c and c+32) and, of those, the ones
+  // whose index range can hold the atom or one of its exclusions
+  auto chunk_masks = [&](const BuildAtom& a, unsigned mh[2], unsigned sp[2]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = lane + 32 * h;
+      bool v = false;
+      if (c < nchunks) {
+        const float* bb = sh.bb[c];
+        float dx = fmaxf(fmaxf(bb[0] - a.pi.x, a.pi.x - bb[3]), 0.f);
+        float dy = fmaxf(fmaxf(bb[1] - a.pi.y, a.pi.y - bb[4]), 0.f);
+        float dz = fmaxf(fmaxf(bb[2] - a.pi.z, a.pi.z - bb[5]), 0.f);
+        if (WRAP) {
+          if (w0) dx = 0.f;
+          if (w1) dy = 0.f;
+          if (w2) dz = 0.f;
+        }
+        v = (dx * dx + dy * dy + dz * dz) * 0.99999f <= rl2;
+      }
+      mh[h] = __ballot_sync(0xffffffffu, v);
+      sp[h] = __ballot_sync(0xffffffffu, v && sh.jr[c][0] <= a.exhi && sh.jr[c][1] >= a.exlo);
+    }
+  };
+  // lanes whose candidate j is the atom itself or one of its exclusions
+  auto excluded = [&](const BuildAtom& a, int j) {
+    bool excl = (j == a.k);
+    const int nfast = min(a.ne, 32);
+#pragma unroll 1
+    for (int e = 0; e < nfast; ++e) excl |= (__shfl_sync(0xffffffffu, a.my_excl, e) == j);
+#pragma unroll 1
+    for (int e = 32; e < a.ne; ++e) excl |= (S.inv[base + S.excl_idx[a.e0 + e]] == j);
+    return __ballot_sync(0xffffffffu, excl);
+  };
+  auto finish = [&](const BuildAtom& a, int ii) {
+    if (!a.store) return;
+    int* row = reinterpret_cast<int*>(a.row_addr);
+    const int end = min((a.count + 31) & ~31, cap);
+    for (int e = a.count + lane; e < end; e += 32) row[e] = S.natoms;
+    if (lane == 0) sh.counts[ii] = a.count;
+  };
+
+  for (int ii = 2 * warp; ii < nib; ii += 2 * BT_WARPS) {
+    const bool have1 = ii + 1 < nib;
+    const bool s0 = owned(b0 + ii), s1 = have1 && owned(b0 + ii + 1);
+    if (!s0 && !s1) continue;
+    // a missing or foreign partner is replaced by a stand-in (the atom itself once more) that writes nothing
+    const int i0 = s0 ? ii : ii + 1, i1 = (s0 && s1) ? ii + 1 : i0;
+    BuildAtom A = load_atom(b0 + i0, i0, true);
+    BuildAtom B = load_atom(b0 + i1, i1, s0 && s1);
+    unsigned mhA[2], spA[2], mhB[2], spB[2];
+    chunk_masks(A, mhA, spA);
+    chunk_masks(B, mhB, spB);
+    // values the chunk loop needs on every pass stay in registers (otherwise re-derived from the constant bank,
+    // the row address with a dozen integer operations per store).  The two atoms' coordinates go through shared
+    // memory once and come back as 64-bit loads: that is what makes them adjacent register PAIRS, the operand form
+    // of the packed instructions (assembled from the two float4 records they cost two moves per use).
+    __syncwarp();
+    if (lane == 0) {
+      sh.pp[warp][0] = make_float2(A.pi.x, B.pi.x);
+      sh.pp[warp][1] = make_float2(A.pi.y, B.pi.y);
+      sh.pp[warp][2] = make_float2(A.pi.z, B.pi.z);
+    }
+    __syncwarp();
+    const float2 PX = sh.pp[warp][0], PY = sh.pp[warp][1], PZ = sh.pp[warp][2];
+    unsigned lt_r = lt, lb_r = 1u << lane;
+    smem_addr tile_lane = smem_address(sh.tile) + 16u * (unsigned)lane;  // this lane's record of chunk 0
+    TMD_PIN_R(tile_lane);
+    TMD_PIN_L(A.row_addr);
+    TMD_PIN_L(B.row_addr);
+    TMD_PIN_R(lt_r);
+    TMD_PIN_R(lb_r);
+    TMD_PIN_F(rl2);
+    TMD_PIN_R(cap);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      unsigned visit = mhA[h] | mhB[h];
+      const unsigned special = spA[h] | spB[h];
+#pragma unroll 1
+      while (visit) {
+        const int cbit = __ffs((int)visit) - 1;
+        visit &= visit - 1;
+        const float4 pj = lds_f32x4(tile_lane + 512u * (unsigned)(cbit + 32 * h));  // a chunk is 32 records of 16 bytes
+        const int entry = __float_as_int(pj.w);
+        const int j = entry & 0xffffff;
+        F2 s;
+        if (WRAP) {  // a dimension too short for cells: one cell spans it, fold per pair (scalar: rare small boxes)
+          float d[2][3] = {{A.pi.x - pj.x, A.pi.y - pj.y, A.pi.z - pj.z}, {B.pi.x - pj.x, B.pi.y - pj.y, B.pi.z - pj.z}};
+          float q[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (w0) d[t][0] -= g.L[0] * rintf(d[t][0] * g.invL[0]);
+            if (w1) d[t][1] -= g.L[1] * rintf(d[t][1] * g.invL[1]);
+            if (w2) d[t][2] -= g.L[2] * rintf(d[t][2] * g.invL[2]);
+            q[t] = d[t][0] * d[t][0] + d[t][1] * d[t][1] + d[t][2] * d[t][2];
+          }
+          s = f2(q[0], q[1]);
+        } else {
+          const F2 px = f2(PX.x, PX.y), py = f2(PY.x, PY.y), pz = f2(PZ.x, PZ.y);
+          const F2 dx = f2_add(px, f2(-pj.x)), dy = f2_add(py, f2(-pj.y)), dz = f2_add(pz, f2(-pj.z));
+          s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+        }
+        unsigned mA = __ballot_sync(0xffffffffu, s.x <= rl2);
+        unsigned mB = __ballot_sync(0xffffffffu, s.y <= rl2) & B.store;
+        if ((special >> cbit) & 1u) {  // rare, warp-uniform: an atom itself or an exclusion may be in this chunk
+          mA &= ~excluded(A, j);
+          mB &= ~excluded(B, j);
+        }
+        const int slotA = A.count + __popc(mA & lt_r), slotB = B.count + __popc(mB & lt_r);
+        if ((mA & lb_r) && slotA < cap) stg_u32(A.row_addr + 4ull * (unsigned)slotA, entry);
+        if ((mB & lb_r) && slotB < cap) stg_u32(B.row_addr + 4ull * (unsigned)slotB, entry);
+        A.count += __popc(mA);
+        B.count += __popc(mB);
+      }
+    }
+    finish(A, i0);
+    finish(B, i1);
+  }
+}
+#endif
+
 __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx, int nbx, BuildShared& sh) {
   int* fl = S.flags + r * F_COUNT;
   if (bx == 0 && threadIdx.x == 0) atomicAdd(fl + F_NREBUILD, 1);
@@ -675,8 +860,13 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
         build_chunk_boxes(sh, fill);
         __syncthreads();
 #endif
+#if BT_CULL && BT_PAIRED
+        if (w0 || w1 || w2) build_process_tile_paired<true>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
+        else build_process_tile_paired<false>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
+#else
         if (w0 || w1 || w2) build_process_tile<true>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
         else build_process_tile<false>(S, g, base, sh, fill, b0, nib, w0, w1, w2);
+#endif
       }
       __syncthreads();
       for (int t = tid; t < nib; t += nthr) {

@@ -34,10 +34,26 @@ __device__ __forceinline__ float2 lds_f32x2(smem_addr a) {
   asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
+// (volatile: the staged tile is rewritten between barriers, the load must not be merged with an earlier one)
+__device__ __forceinline__ float4 lds_f32x4(smem_addr a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ int4 ldg_s32x4(unsigned long long addr) {
   int4 v;
   asm("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
   return v;
+}
+// two floats as one 64-bit register pair (the operand form of the packed fp32x2 instructions); pinning the packed
+// value keeps the pair adjacent across a loop instead of re-assembling it with two moves per use
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 // base + a * b as one IMAD.WIDE.U32 (the address of a 16-byte record from its index)
 __device__ __forceinline__ unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long long c) {
@@ -68,7 +84,19 @@ inline float lds_f32(smem_addr a) { return *reinterpret_cast<const float*>(a); }
 template <int OFFSET>
 inline float lds_f32_at(smem_addr a) { return *reinterpret_cast<const float*>(a + OFFSET); }
 inline float2 lds_f32x2(smem_addr a) { return *reinterpret_cast<const float2*>(a); }
+inline float4 lds_f32x4(smem_addr a) { return *reinterpret_cast<const float4*>(a); }
 inline int4 ldg_s32x4(unsigned long long addr) { return *reinterpret_cast<const int4*>(addr); }
+inline unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned a, b;
+  memcpy(&a, &lo, 4);
+  memcpy(&b, &hi, 4);
+  return (unsigned long long)a | ((unsigned long long)b << 32);
+}
+inline void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  const unsigned a = (unsigned)v, b = (unsigned)(v >> 32);
+  memcpy(&lo, &a, 4);
+  memcpy(&hi, &b, 4);
+}
 inline unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long long c) { return (unsigned long long)a * b + c; }
 inline void stg_u32(unsigned long long addr, int v) { *reinterpret_cast<int*>(addr) = v; }
 inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
