@@ -458,6 +458,11 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
 #if BT_CULL
     unsigned long long row_addr = reinterpret_cast<unsigned long long>(row);
     TMD_PIN_L(row_addr);  // one 64-bit base; a store address is then base + 4*slot
+    unsigned lt_r = lt, lb_r = 1u << lane;
+    smem_addr tile_lane = smem_address(sh.tile) + 16u * (unsigned)lane;  // this lane's record of chunk 0
+    TMD_PIN_R(lt_r);
+    TMD_PIN_R(lb_r);
+    TMD_PIN_R(tile_lane);
     // chunks whose bounding box is within the list radius of this atom (lane c tests chunks
     // c and c+32); a dimension folded per pair (WRAP) cannot be used for culling.  `special`:
     // chunks whose index range can hold the atom itself or one of its exclusions -- only those
@@ -496,9 +501,8 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
 #pragma unroll 1
     while (visit) {
       const int cbit = __ffs((int)visit) - 1;
-      const int c0 = (cbit + 32 * h) << 5;
       visit &= visit - 1;
-      const float4 pj = sh.tile[c0 + lane];
+      const float4 pj = lds_f32x4(tile_lane + 512u * (unsigned)(cbit + 32 * h));  // a chunk is 32 records of 16 bytes
       const bool check_index = (special >> cbit) & 1u;  // warp-uniform
 #else
     const float4* __restrict__ tp = sh.tile + lane;
@@ -533,11 +537,12 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
         for (int e = 32; e < ne; ++e) excl |= (S.inv[base + S.excl_idx[e0 + e]] == j);
         m &= ~__ballot_sync(0xffffffffu, excl);
       }
-      const int slot = count + __popc(m & lt);
 #if BT_CULL
-      if (((m >> lane) & 1u) && slot < cap)
+      const int slot = count + __popc(m & lt_r);
+      if ((m & lb_r) && slot < cap)
         stg_u32(row_addr + 4ull * (unsigned)slot, entry);
 #else
+      const int slot = count + __popc(m & lt);
       if (((m >> lane) & 1u) && slot < cap) row[slot] = entry;
 #endif
       count += __popc(m);
