@@ -221,6 +221,7 @@ class ClockSampler:
 # our arm
 # ------------------------------------------------------------------------------------
 DEVICE_OVERRIDE = None  # tests/test_mirrors_on_interpreter.py dry-runs gpu_arm on the host interpreter build with "cpu"
+MIN_DECOMPOSED_WARMUP = 5000  # N > 1: steps before the timed region (>= 0.4 s under load for the clock sampler)
 
 
 def gpu_arm(args):

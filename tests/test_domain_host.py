@@ -178,3 +178,88 @@ def test_decomposed_integrator_on_the_interpreter_matches_single_process_gloo():
         assert p.exitcode == 0
     results = dict(out.get(timeout=10) for _ in range(world))
     assert results == {0: True, 1: True}
+
+
+def _worker_bench(rank, world, port, out):
+    """bench.py's N>1 body (torchmd_b200.domain.bench_decomposed) with two gloo ranks on the interpreter build."""
+    import argparse
+    import contextlib
+    import io
+    import json
+    import sys
+    import time
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import bench
+    import test_simt_kernels as T
+    from torchmd_b200 import _lib, domain
+
+    class _Stream:
+        cuda_stream = None
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, *a):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    class _NoSampler:
+        def __init__(self, *a):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+    _lib._lib = T.load(os.path.join(T.SIMT_DIR, "libtmd_simt.so"))
+    _lib.on_device = lambda t: True
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.current_device = lambda: 0
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = _Event
+    bench.DEVICE_OVERRIDE, bench.MIN_DECOMPOSED_WARMUP, bench.N_WATERS = "cpu", 4, 64
+    bench.CFG = dict(bench.CFG, cutoff=5.0, switch_dist=4.0)
+    bench.ClockSampler = _NoSampler
+    args = argparse.Namespace(gpus=world, steps=5, warmup=3, equil=6, e2e_steps=2, no_cpu_baseline=True, impl="ours")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+        domain.bench_decomposed(args, world, rank, 0, bench.workload_config(world))
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    out.put((rank, json.loads(lines[-1]) if lines else None))
+    dist.destroy_process_group()
+
+
+def test_bench_decomposed_dry_run_gloo():
+    """The N>1 arm of bench.py end to end (equilibration, warm-up, timed steps, eager profiling stretch, pair count,
+    end-to-end loop, the JSON line) with two ranks -- rank 0 prints the one line, the others none."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_simt_kernels as T
+
+    T.build_simt()
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_bench, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    results = dict(out.get(timeout=10) for _ in range(world))
+    assert results[1] is None
+    line = results[0]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
+    assert line["roofline"]["pair_entries_counted"] > 0 and line["scaling"] == "strong"

@@ -257,7 +257,7 @@ def bench_decomposed(args, world, rank, local, config):
     from . import Forces, System, maxwell_boltzmann, testsystems
     import bench as B
 
-    dev = f"cuda:{local}"
+    dev = B.DEVICE_OVERRIDE or f"cuda:{local}"  # (the override: tests/test_domain_host.py dry-runs this function over gloo)
     sysd = testsystems.water_box(B.N_WATERS, seed=0)
     n = len(sysd["coords"])
     par = testsystems.water_parameters(sysd, device=dev)
@@ -281,7 +281,7 @@ def bench_decomposed(args, world, rank, local, config):
     st_a = forces.stats()
     # warm-up: at least 5000 steps (>= 0.4 s under load for the clock sampler); a FIXED count, the
     # same on every rank -- a wall-clock criterion could give ranks different numbers of collectives
-    ekin, pot, T = integ.step(niter=max(3, args.warmup, 5000))
+    ekin, pot, T = integ.step(niter=max(3, args.warmup, B.MIN_DECOMPOSED_WARMUP))
     launches_per_step = None
     if integ.use_graph:  # kernels of one captured step (the capture itself went through the counting path)
         st_b = forces.stats()
@@ -325,7 +325,7 @@ def bench_decomposed(args, world, rank, local, config):
 
     # end to end: host-resident positions in and out every step
     e2e_steps = min(args.steps, args.e2e_steps)
-    hpos = torch.empty(system.pos.shape, dtype=torch.float32, pin_memory=True)
+    hpos = torch.empty(system.pos.shape, dtype=torch.float32, pin_memory=B.DEVICE_OVERRIDE is None)
     hpos.copy_(system.pos)
     for k in range(3 + e2e_steps):
         if k == 3:
