@@ -18,11 +18,10 @@ class _Stream:
     cuda_stream = None  # the interpreter runs every launch on the spot
 
 
-@pytest.fixture
-def hostsim(monkeypatch):
+def _install(monkeypatch, tag):
     from torchmd_b200 import _lib
 
-    handle = T.load(T.build_simt())
+    handle = T.load(T.build_simt(tag, T.VARIANTS[tag]))
     monkeypatch.setattr(_lib, "_lib", handle)
     monkeypatch.setattr(_lib, "on_device", lambda t: True)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
@@ -33,6 +32,18 @@ def hostsim(monkeypatch):
     for mod in (test_autograd_path, test_gpu_forces, test_gpu_integrator, test_wrapper):
         monkeypatch.setattr(mod, "DEV", "cpu")
     return handle
+
+
+@pytest.fixture
+def hostsim(monkeypatch):
+    return _install(monkeypatch, "")
+
+
+@pytest.fixture
+def hostsim_r2(monkeypatch):
+    """The build with every opt-in path compiled in as the default (packed fixed-point pair kernel, culled two-atom
+    list build, overlapped bonded kernel, fused integrate+prepare and bonded fold)."""
+    return _install(monkeypatch, "_r2")
 
 
 FORCE_CASES = ["water291_rf_switch", "water291_plain", "argon100_nocut", "chain_amber_vacuum", "chain_amber_periodic",
@@ -205,3 +216,24 @@ def test_bench_single_gpu_arm_dry_run(hostsim, monkeypatch, capsys):
     assert line["gpu_launches"] > 0 and line["value"] > 0 and line["e2e"]["value"] > 0
     assert line["roofline"]["pairs_in_cutoff"] > 0 and line["roofline"]["launches_sampled"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+
+
+def test_round2_default_configuration_passes_the_gpu_tests(hostsim_r2, capsys):
+    """The same GPU test functions with every opt-in path switched on by default: what `pytest -m gpu`, smoke() and the
+    integrator will see once round 2 flips the defaults."""
+    import __graft_entry__ as g
+    import test_gpu_forces as G
+    import test_gpu_integrator as I
+
+    for name in ("water291_rf_switch", "chain_amber_periodic", "chain_charmm_periodic", "ala2_xsc_rf", "argon100_nocut"):
+        G.test_golden_forces_energies(name)
+        G.test_golden_neighbour_pairs_bit_exact(name)
+    from conftest import load_golden
+
+    f, *_ = G.run_gpu(load_golden("chain_amber_periodic"))
+    assert hostsim_r2.tmd_pair_kernel(f._ctx) == 2  # the packed fixed-point kernel is what ran
+    G.test_api_errors_and_formats()
+    I.test_nve_trajectory_matches_reference()
+    I.test_langevin_with_injected_noise_matches_reference()
+    I.test_stepwise_and_fused_paths_agree()
+    g.smoke(dev="cpu")

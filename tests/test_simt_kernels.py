@@ -25,6 +25,8 @@ VARIANTS = {  # tag -> defines; every interpreter build the tests use (built tog
     "": [],
     "_cull": ["BT_CULL=1"],
     "_paired": ["BT_CULL=1", "BT_PAIRED=1"],
+    # every opt-in path as the default (what round 2 switches on once the B200 has confirmed it)
+    "_r2": ["BT_CULL=1", "BT_PAIRED=1", "TMD_DEFAULT_FX=2", "TMD_DEFAULT_OVERLAP=1", "TMD_DEFAULT_FUSEPREP=1"],
     "_t2": ["FX_SMALLT_MAX_N=2"],
     "_fxu4": ["PAIR_FX_UNROLL=4"],
     "_fx2u2": ["PAIR_FX2_UNROLL=2"],

@@ -45,6 +45,31 @@ int fail(int code, const std::string& msg) {
       return fail(TMD_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// Run-time switches: the environment decides ("0" off, "1"/"2" on), otherwise the default below.  Everything is off
+// until it has run on a B200; flipping a default is this one line (or -DTMD_DEFAULT_<NAME>=... for an A/B build).
+#ifndef TMD_DEFAULT_FX
+#define TMD_DEFAULT_FX 0        // TMD_B200_FX: 1 fixed-point pair kernel, 2 + packed fp32x2 arithmetic
+#endif
+#ifndef TMD_DEFAULT_COOP
+#define TMD_DEFAULT_COOP 0      // TMD_B200_COOP: rebuild as one cooperative launch
+#endif
+#ifndef TMD_DEFAULT_OVERLAP
+#define TMD_DEFAULT_OVERLAP 0   // TMD_B200_OVERLAP: bonded kernel on a second stream
+#endif
+#ifndef TMD_DEFAULT_COND
+#define TMD_DEFAULT_COND 0      // TMD_B200_COND: rebuild as a conditional node when captured (needs TMD_COND_NODE)
+#endif
+#ifndef TMD_DEFAULT_GRAPH
+#define TMD_DEFAULT_GRAPH 0     // TMD_B200_GRAPH: tmd_md_steps replays a captured step
+#endif
+#ifndef TMD_DEFAULT_FUSEPREP
+#define TMD_DEFAULT_FUSEPREP 0  // TMD_B200_FUSEPREP: integrate + prepare in one kernel, bonded fold in the second kick
+#endif
+static int env_switch(const char* name, int def) {
+  const char* e = getenv(name);
+  return (e && e[0] >= '0' && e[0] <= '9') ? (e[0] - '0') : def;
+}
+
 // Every kernel launch goes through here.  The product enqueues on the stream; the SIMT interpreter
 // build of tests/simt (TMD_SIMT_HOST: the same kernels compiled for the CPU to check their logic
 // without a GPU) runs the grid on the spot.
@@ -463,9 +488,9 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   // image condition.  Opt-in (TMD_B200_FX=1) until it has been through the B200 parity suite.
   d.xf_s = nullptr;
   {
-    const char* env = getenv("TMD_B200_FX");
-    ctx->fx_packed = env && env[0] == '2';
-    if (env && (env[0] == '1' || env[0] == '2') && ctx->safe_image && ctx->pair_mask) {
+    const int fx = env_switch("TMD_B200_FX", TMD_DEFAULT_FX);
+    ctx->fx_packed = fx == 2;
+    if ((fx == 1 || fx == 2) && ctx->safe_image && ctx->pair_mask) {
       const size_t n = (size_t)R * N + R;
       if ((rc = device_alloc(&ctx->xf_buf, n))) return rc;
       TMD_CUDA(cudaMemset(ctx->xf_buf, 0, n * sizeof(int4)));
@@ -567,13 +592,13 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   // cooperative rebuild kernel: as many CTAs as can be co-resident, split over the replicas
   ctx->coop_blocks = 0;
   {
-    const char* env = getenv("TMD_B200_COOP");
+    const bool want_coop = env_switch("TMD_B200_COOP", TMD_DEFAULT_COOP) == 1;
     int coop = 0, nsm = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     // opt-in (TMD_B200_COOP=1): measured +2 % on B200, but a grid-wide barrier can only deadlock,
     // never fail, if co-residency is ever violated -- the separate gated kernels are the default
-    if (coop && (env && env[0] == '1') &&
+    if (coop && want_coop &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rebuild, BT_WARPS * 32, 0) == cudaSuccess) {
       const int total = per_sm * nsm;
       if (total >= R) ctx->coop_blocks = std::max(1, total / R);
@@ -582,8 +607,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   // bonded kernel concurrent with the pair kernel (opt-in until validated on a B200)
   {
     CtxPriv& pv = priv(ctx);
-    const char* env = getenv("TMD_B200_OVERLAP");
-    const bool want = env && env[0] == '1' && ctx->bonded_nentries > 0 && ctx->pair_mask;
+    const bool want = env_switch("TMD_B200_OVERLAP", TMD_DEFAULT_OVERLAP) == 1 && ctx->bonded_nentries > 0 && ctx->pair_mask;
     if (want && !pv.side) {
       TMD_CUDA(cudaStreamCreateWithFlags(&pv.side, cudaStreamNonBlocking));
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_fork, cudaEventDisableTiming));
@@ -598,18 +622,16 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   }
   {
     CtxPriv& pv = priv(ctx);
-    const char* ec = getenv("TMD_B200_COND");
-    const char* eg = getenv("TMD_B200_GRAPH");
-    pv.use_graph = eg && eg[0] == '1';
-    pv.use_cond = TMD_COND_NODE && ((ec && ec[0] == '1') || pv.use_graph);  // (without the node: five gated kernels, as in stream order)
+    pv.use_graph = env_switch("TMD_B200_GRAPH", TMD_DEFAULT_GRAPH) == 1;
+    // (without the compiled-in node: five gated kernels, as in stream order)
+    pv.use_cond = TMD_COND_NODE && (env_switch("TMD_B200_COND", TMD_DEFAULT_COND) == 1 || pv.use_graph);
     if (pv.use_cond && !pv.helper) TMD_CUDA(cudaStreamCreateWithFlags(&pv.helper, cudaStreamNonBlocking));
     if (pv.use_graph && !pv.gstream) {
       TMD_CUDA(cudaStreamCreateWithFlags(&pv.gstream, cudaStreamNonBlocking));
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_in, cudaEventDisableTiming));
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_out, cudaEventDisableTiming));
     }
-    const char* ef = getenv("TMD_B200_FUSEPREP");
-    pv.fuse_prepare = ef && ef[0] == '1';
+    pv.fuse_prepare = env_switch("TMD_B200_FUSEPREP", TMD_DEFAULT_FUSEPREP) == 1;
     pv.steps_valid = false;  // buffers may have moved: captured steps are rebuilt
   }
   priv(ctx).dirty = false;
