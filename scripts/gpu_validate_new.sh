@@ -3,7 +3,7 @@
 #   gpurun --timeout 1700 -- 'bash scripts/gpu_validate_new.sh'            all sections (~25-30 min of box time)
 #   gpurun --timeout 700  -- 'bash scripts/gpu_validate_new.sh 0 1 2'      only the named sections
 # Sections:
-#   0  FFMA2 issue microbenchmark              1  standing GPU suite (default switches; must stay green)
+#   0  FFMA2 issue + RED throughput ubench            1  standing GPU suite (default switches; must stay green)
 #   2  gated tests of the new code paths        3  pair kernels: A/B bench TMD_B200_FX=0/1/2 + register/unroll variants
 #   4  list build with chunk culling            5  bonded kernel overlapped on a second stream
 #   6  captured step + conditional-node rebuild on one GPU
@@ -41,6 +41,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/validate_build.l
 
 if has 0; then
   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_f32x2 scripts/ubench_f32x2.cu && /tmp/ubench_f32x2 | tee gpurun_out/ubench_f32x2.txt
+  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_red scripts/ubench_red.cu && timeout -s KILL 60 /tmp/ubench_red | tee gpurun_out/ubench_red.txt
 fi
 if has 1; then
   run_suite default TMD_B200_VALIDATE=0
