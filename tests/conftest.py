@@ -72,7 +72,10 @@ def golden_cfg(g):
 
 def golden_system_tensors(g, dtype, device="cpu"):
     nrep = int(g["cfg_nrep"])
-    pos = torch.tensor(g["coords"], dtype=dtype, device=device)[None].repeat(nrep, 1, 1).contiguous()
+    if "coords_replicas" in g:  # fixtures whose replicas are distinct configurations
+        pos = torch.tensor(g["coords_replicas"], dtype=dtype, device=device).contiguous()
+    else:
+        pos = torch.tensor(g["coords"], dtype=dtype, device=device)[None].repeat(nrep, 1, 1).contiguous()
     box = torch.zeros(nrep, 3, 3, dtype=dtype, device=device)
     for k in range(3):
         box[:, k, k] = float(g["box"][k])

@@ -37,6 +37,10 @@ CASES = [
     "ala2_nobox_rf",  # BASELINE.json config 3 (all AMBER terms), 2 replicas, no box
     "ala2_xsc_rf",  # same system in its periodic box (the tutorial's run)
     "thrombin_nobox_rf",  # config 5: 4676-atom protein + ligand in vacuum, cutoff 7.3, 2 replicas
+    # the two small AMBER fixtures of the reference's own test matrix (tests/data), configured as test_torchmd.py:363-365
+    # does without a box: no cutoff, plain Coulomb, all terms; the two replicas are different configurations
+    "benzamidine_amber_nocut",
+    "ligand_amber_nocut",
 ]
 
 

@@ -101,7 +101,7 @@ def test_fixed_point_kernel_matches_golden(name, mode):
         assert torch.equal(F, F1)
 
 
-@pytest.mark.parametrize("name", ["ala2_nobox_rf", "thrombin_nobox_rf", "argon100_nocut", "chain_amber_vacuum"])
+@pytest.mark.parametrize("name", ["ala2_nobox_rf", "thrombin_nobox_rf", "argon100_nocut", "chain_amber_vacuum", "benzamidine_amber_nocut", "ligand_amber_nocut"])
 def test_packed_kernel_without_a_box(name):
     """TMD_B200_FX=2 on systems without a box: k_pair2_open (packed arithmetic on the float records; thrombin has
     45 atom types and reads the LJ table from global memory).  Decisions are exact by construction: pairs bit-exact."""

@@ -203,7 +203,7 @@ def test_fixed_point_and_packed_pair_kernels(simt, name, mode):
     c0.close()
 
 
-@pytest.mark.parametrize("name", ["chain_amber_vacuum", "argon100_nocut", "ala2_nobox_rf"])
+@pytest.mark.parametrize("name", ["chain_amber_vacuum", "argon100_nocut", "ala2_nobox_rf", "benzamidine_amber_nocut", "ligand_amber_nocut"])
 def test_packed_kernel_without_a_box(simt, name):
     g = load_golden(name)
     c = Ctx(simt, g, env={"TMD_B200_FX": "2"})
