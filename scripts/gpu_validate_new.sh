@@ -53,34 +53,37 @@ if has 2; then
   grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
 fi
 if has 3; then
-  for fx in 0 1 2; do run_bench "TMD_B200_FX=$fx" fx$fx TMD_B200_FX=$fx; done
+  VARS=("FX=0|TMD_B200_FX=0" "FX=1|TMD_B200_FX=1" "FX=2|TMD_B200_FX=2")  # scripts/ab_bench.py variants: "label|env|library"
   for cfg in "5 2" "6 4" "5 4"; do
     set -- $cfg
     $NVCC -DPAIR_FX_MINBLOCKS=$1 -DPAIR_FX_UNROLL=$2 -o /tmp/var/lib_fx_$1_$2.so torchmd_b200/csrc/tmd_b200.cu
-    run_bench "FX=1, $1 CTAs/SM, $2 entries/lane/iteration" fx1_$1_$2 TMD_B200_LIB=/tmp/var/lib_fx_$1_$2.so TMD_B200_FX=1
+    VARS+=("FX=1, $1 CTAs/SM, $2 entries/lane/iteration|TMD_B200_FX=1|/tmp/var/lib_fx_$1_$2.so")
   done
   for cfg in "5 1" "4 2" "3 2"; do
     set -- $cfg
     $NVCC -DPAIR_FX2_MINBLOCKS=$1 -DPAIR_FX2_UNROLL=$2 -o /tmp/var/lib_fx2_$1_$2.so torchmd_b200/csrc/tmd_b200.cu
-    run_bench "FX=2, $1 CTAs/SM, $2 packed evaluations/iteration" fx2_$1_$2 TMD_B200_LIB=/tmp/var/lib_fx2_$1_$2.so TMD_B200_FX=2
+    VARS+=("FX=2, $1 CTAs/SM, $2 packed evaluations/iteration|TMD_B200_FX=2|/tmp/var/lib_fx2_$1_$2.so")
   done
   for mb in 4 3; do
     $NVCC -DPAIR_FX2_MINBLOCKS=$mb -DPAIR_FX2_PIPE=1 -o /tmp/var/lib_fx2_pipe_$mb.so torchmd_b200/csrc/tmd_b200.cu
-    run_bench "FX=2, $mb CTAs/SM, pipelined gathers" fx2_pipe_$mb TMD_B200_LIB=/tmp/var/lib_fx2_pipe_$mb.so TMD_B200_FX=2
+    VARS+=("FX=2, $mb CTAs/SM, pipelined gathers|TMD_B200_FX=2|/tmp/var/lib_fx2_pipe_$mb.so")
   done
+  # the whole sweep in one process; the two configurations that matter also through bench.py (the published line)
+  timeout -s KILL 600 python scripts/ab_bench.py --steps 1000 "${VARS[@]}" 2> gpurun_out/ab_pair.err | tee gpurun_out/ab_pair.txt
+  for fx in 0 2; do run_bench "bench.py TMD_B200_FX=$fx" fx$fx TMD_B200_FX=$fx; done
 fi
 if has 4; then
   $NVCC -DBT_CULL=1 -o /tmp/var/lib_cull.so torchmd_b200/csrc/tmd_b200.cu
   run_suite cull TMD_B200_LIB=/tmp/var/lib_cull.so
-  for fx in 0 2; do run_bench "BT_CULL=1 FX=$fx" cull_fx$fx TMD_B200_LIB=/tmp/var/lib_cull.so TMD_B200_FX=$fx; done
   # two atoms of a cell per warp pass, packed distance arithmetic
   $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -o /tmp/var/lib_paired.so torchmd_b200/csrc/tmd_b200.cu
   run_suite paired TMD_B200_LIB=/tmp/var/lib_paired.so
-  for fx in 0 2; do run_bench "BT_CULL=1 BT_PAIRED=1 FX=$fx" paired_fx$fx TMD_B200_LIB=/tmp/var/lib_paired.so TMD_B200_FX=$fx; done
+  timeout -s KILL 400 python scripts/ab_bench.py --steps 1000 "plain build FX=0|TMD_B200_FX=0" "culled FX=0|TMD_B200_FX=0|/tmp/var/lib_cull.so" "culled+paired FX=0|TMD_B200_FX=0|/tmp/var/lib_paired.so" \
+      "plain build FX=2|TMD_B200_FX=2" "culled FX=2|TMD_B200_FX=2|/tmp/var/lib_cull.so" "culled+paired FX=2|TMD_B200_FX=2|/tmp/var/lib_paired.so" 2> gpurun_out/ab_build.err | tee gpurun_out/ab_build.txt
 fi
 if has 5; then
   run_suite overlap TMD_B200_OVERLAP=1
-  for fx in 0 2; do run_bench "OVERLAP=1 FX=$fx" ov_fx$fx TMD_B200_OVERLAP=1 TMD_B200_FX=$fx; done
+  timeout -s KILL 300 python scripts/ab_bench.py --steps 1000 "FX=0|TMD_B200_FX=0" "OVERLAP=1 FX=0|TMD_B200_OVERLAP=1,TMD_B200_FX=0" "FX=2|TMD_B200_FX=2" "OVERLAP=1 FX=2|TMD_B200_OVERLAP=1,TMD_B200_FX=2" 2> gpurun_out/ab_overlap.err | tee gpurun_out/ab_overlap.txt
 fi
 if has 6; then
   # (the device-side switch of the conditional node is compiled in with -DTMD_COND_NODE=1; without it GRAPH=1
@@ -93,7 +96,7 @@ if has 6; then
 fi
 if has 7; then
   run_suite fuseprep TMD_B200_FUSEPREP=1
-  for fx in 0 2; do run_bench "FUSEPREP=1 FX=$fx" fuse_fx$fx TMD_B200_FUSEPREP=1 TMD_B200_FX=$fx; done
+  timeout -s KILL 300 python scripts/ab_bench.py --steps 1000 "FX=2|TMD_B200_FX=2" "FUSEPREP=1 FX=2|TMD_B200_FUSEPREP=1,TMD_B200_FX=2" "FUSEPREP=1 OVERLAP=1 FX=2|TMD_B200_FUSEPREP=1,TMD_B200_OVERLAP=1,TMD_B200_FX=2" 2> gpurun_out/ab_fuse.err | tee gpurun_out/ab_fuse.txt
   [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
   run_bench "everything: CULL FX=2 OVERLAP GRAPH" all TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1
   run_bench "everything + FUSEPREP" all_fuse TMD_B200_LIB=/tmp/var/lib_all.so TMD_B200_FX=2 TMD_B200_OVERLAP=1 TMD_B200_GRAPH=1 TMD_B200_FUSEPREP=1

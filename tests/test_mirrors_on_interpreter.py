@@ -237,3 +237,38 @@ def test_round2_default_configuration_passes_the_gpu_tests(hostsim_r2, capsys):
     I.test_langevin_with_injected_noise_matches_reference()
     I.test_stepwise_and_fused_paths_agree()
     g.smoke(dev="cpu")
+
+
+def test_ab_bench_script_dry_run(hostsim, monkeypatch, capsys):
+    """scripts/ab_bench.py (round-2 tuning sweeps in one process) on a 64-water box."""
+    import importlib.util
+    import os
+    import time
+
+    import bench
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, *a):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    spec = importlib.util.spec_from_file_location("ab_bench", os.path.join(T.ROOT, "scripts", "ab_bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(mod, "DEVICE", "cpu")
+    monkeypatch.setattr(bench, "N_WATERS", 64)
+    monkeypatch.setattr(bench, "CFG", dict(bench.CFG, cutoff=5.0, switch_dist=4.0))
+    mod.main(["default", "packed+overlap+fused|TMD_B200_FX=2,TMD_B200_OVERLAP=1,TMD_B200_FUSEPREP=1", "--steps", "6", "--equil", "10", "--warmup", "2", "--skin", "0.3"])
+    out = capsys.readouterr().out
+    rows = [l for l in out.splitlines() if l.startswith(("default", "packed"))]
+    assert len(rows) == 2 and "failed" not in out, out
+    # same start, same seeds: the variants end at the same temperature, the fused one with fewer launches per step
+    t = [float(r.split()[5]) for r in rows]
+    launches = [float(r.split()[4]) for r in rows]
+    assert abs(t[0] - t[1]) < 1e-3 * t[0] and launches[1] < launches[0], rows
