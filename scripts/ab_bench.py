@@ -3,7 +3,8 @@ bench.py's full contract (JSON line, end-to-end loop, CPU baseline, clock sampli
 
     python scripts/ab_bench.py --steps 1000 "default" "FX=2|TMD_B200_FX=2" "cull+FX=2|TMD_B200_FX=2|/tmp/var/lib_cull.so"
 
-A variant is "label|ENV=VALUE,ENV=VALUE|library path" (the last two optional).  Every variant starts from the same
+A variant is "label|ENV=VALUE,ENV=VALUE|library path" (the last two optional); the pseudo-variable SKIN=<A> sets the
+Verlet skin of that variant.  Every variant starts from the same
 equilibrated state and runs the same number of steps with the same noise seed; prints steps/s, ms/step, the mean
 pair-kernel time, launches per step and the final temperature.  The numbers to publish come from bench.py.
 """
@@ -39,6 +40,8 @@ def main(argv=None):
     default_lib = _lib.LIB_PATH
 
     def fresh(variant_env):
+        variant_env = dict(variant_env)
+        skin = float(variant_env.pop("SKIN")) if "SKIN" in variant_env else args.skin
         system = System(n, 1, torch.float32, dev)
         system.set_positions(sysd["coords"])
         system.set_box(sysd["box"])
@@ -47,7 +50,7 @@ def main(argv=None):
         old = {k: os.environ.get(k) for k in variant_env}
         os.environ.update(variant_env)
         try:  # the switches are read when the context is finalised: at the first force call
-            forces = Forces(par, terms=B.TERMS, skin=args.skin, **B.CFG)
+            forces = Forces(par, terms=B.TERMS, skin=skin, **B.CFG)
             forces.compute(system.pos, system.box, system.forces)
         finally:
             for k, v in old.items():

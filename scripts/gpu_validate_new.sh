@@ -8,6 +8,7 @@
 #   4  list build with chunk culling            5  bonded kernel overlapped on a second stream
 #   6  captured step + conditional-node rebuild on one GPU
 #   7  integrate + prepare in one kernel (TMD_B200_FUSEPREP=1), then everything together
+#   9  skin sweep with every switch on (the optimum moves when pair and build costs change)
 #   8  FAST PATH instead of 4-7: the GPU suite and the bench once with every switch on (bisect with 4-7 only if it fails)
 mkdir -p gpurun_out /tmp/var
 SECTIONS="${*:-0 1 2 3 4 5 6 7}"
@@ -109,4 +110,11 @@ if has 8; then
   run_bench "baseline (default switches)" base TMD_B200_FX=0
   run_bench "all switches, stream launches" all_stream $ALL
   run_bench "all switches, captured step" all_graph $ALL TMD_B200_GRAPH=1
+fi
+if has 9; then
+  [ -f /tmp/var/lib_all.so ] || $NVCC -DBT_CULL=1 -DBT_PAIRED=1 -DTMD_COND_NODE=1 -o /tmp/var/lib_all.so torchmd_b200/csrc/tmd_b200.cu
+  E="TMD_B200_FX=2,TMD_B200_OVERLAP=1,TMD_B200_FUSEPREP=1"
+  VARS=()
+  for sk in 0.6 0.8 1.0 1.2 1.5; do VARS+=("skin $sk, all switches|$E,SKIN=$sk|/tmp/var/lib_all.so"); done
+  timeout -s KILL 400 python scripts/ab_bench.py --steps 1500 "${VARS[@]}" 2> gpurun_out/ab_skin.err | tee gpurun_out/ab_skin.txt
 fi
