@@ -44,6 +44,9 @@ CASES = [
 # AMBER fixtures of the reference's own test matrix (tests/data), configured as test_torchmd.py:363-365 does without a
 # box -- no cutoff, plain Coulomb, all terms; the two replicas are different configurations.
 NEW_CASES = ["benzamidine_amber_nocut", "ligand_amber_nocut"]
+# ... and its small CHARMM fixtures (PSF + PDB + .prm; goldens from the reference's own Parameters + Forces.compute,
+# tests/golden/make_golden_charmm.py)
+NEW_CASES += ["charmm_" + n for n in ("1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine")]
 
 
 def force_tol(ref_F, ref_dev=0.0):

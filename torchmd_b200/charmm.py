@@ -3,6 +3,7 @@ moleculekit ``Molecule`` for these formats (parameters.py:25,110-133; npzmol.py:
 atom types, charges, masses, bonds, angles, dihedrals, impropers, coordinates and box.
 The reference needs moleculekit for this; the hot path does not.
 """
+import math
 import types
 
 import numpy as np
@@ -94,3 +95,121 @@ def load_molecule(psf_path, pdb_path=None):
         mol.coords = xyz[:, :, None].copy()
         mol.box = box[:, None].copy()
     return mol
+
+
+class CharmmPrmForceField:
+    """A CHARMM parameter file (``.prm`` / ``.par``) behind the reference's force-field interface
+    (torchmd/forcefields/forcefield.py:5-43), with the look-up semantics of its parmed adapter
+    (ff_parmed.py:49-129), which this image cannot run (no parmed):
+
+    * bonds, angles: exact type tuple, either direction; Urey-Bradley columns are ignored (ff_parmed.py:73-75
+      returns only k, theta_eq);
+    * dihedrals: exact type tuple or its reverse (ff_parmed.py:77-95, no wildcard matching there); lines that
+      repeat a key add a term, a repeated periodicity replaces the earlier one (parmed's CharmmParameterSet);
+    * 1-4: scnb = scee = 1 (parmed's default for CHARMM dihedral types) and the types' 1-4 sigma / epsilon -- the
+      second column triple of a NONBONDED line when present, else the ordinary values (ff_parmed.py:97-113);
+    * LJ: epsilon = |eps|, sigma = (Rmin/2) * 2 * 2^(-1/6); NBFIX pairs are not used (the adapter reads only the
+      per-type values; the reference's own test notes "I don't have nbfix", tests/test_torchmd.py:326);
+    * impropers (harmonic, periodicity 0): parmed keys them by the SORTED type tuple; the adapter tries the
+      permutations that keep position 2 (ff_parmed.py:115-129).  This part of parmed is restated from its
+      documentation, not pinned: fixtures with impropers are labelled so in tests/golden.
+    """
+
+    SECTIONS = ("ATOMS", "BONDS", "ANGLES", "THETAS", "DIHEDRALS", "PHI", "IMPROPER", "IMPROPERS", "IMPHI", "CMAP", "NONBONDED",
+                "NBONDED", "NBFIX", "HBOND", "END")
+
+    def __init__(self, path, mol=None):
+        self.mol = mol
+        self.bonds, self.angles, self.dihedrals, self.impropers, self.lj, self.masses = {}, {}, {}, {}, {}, {}
+        section, carry = None, ""
+        for raw in open(path):
+            line = raw.split("!")[0].strip()
+            if not line or line.startswith("*"):
+                continue
+            if line.endswith("-"):  # continuation (the NONBONDED header)
+                carry += line[:-1] + " "
+                continue
+            line, carry = carry + line, ""
+            w = line.split()
+            head = w[0].upper()
+            if head in self.SECTIONS:
+                section = {"THETAS": "ANGLES", "PHI": "DIHEDRALS", "IMPROPERS": "IMPROPER", "IMPHI": "IMPROPER", "NBONDED": "NONBONDED"}.get(head, head)
+                continue
+            if head == "MASS" and len(w) >= 4:
+                self.masses[w[2].upper()] = float(w[3])
+                continue
+            try:
+                if section == "BONDS":
+                    a, b = w[0].upper(), w[1].upper()
+                    self.bonds[(a, b)] = self.bonds[(b, a)] = (float(w[2]), float(w[3]))
+                elif section == "ANGLES":
+                    a, b, c = (x.upper() for x in w[:3])
+                    self.angles[(a, b, c)] = self.angles[(c, b, a)] = (float(w[3]), float(w[4]))
+                elif section == "DIHEDRALS":
+                    key = tuple(x.upper() for x in w[:4])
+                    term = [float(w[4]), math.radians(float(w[6])), int(float(w[5]))]
+                    for k in (key, key[::-1]):
+                        terms = [t for t in self.dihedrals.get(k, []) if t[2] != term[2]]
+                        self.dihedrals[k] = terms + [term]
+                elif section == "IMPROPER":
+                    key = tuple(sorted(x.upper() for x in w[:4]))
+                    k, per = float(w[4]), int(float(w[5]))
+                    psi = float(w[6]) if len(w) > 6 else float(w[5])
+                    self.impropers[key] = (k, math.radians(psi), per)
+                elif section == "NONBONDED":
+                    t = w[0].upper()
+                    eps, rmin_half = abs(float(w[2])), float(w[3])
+                    eps14, rmin14_half = (abs(float(w[5])), float(w[6])) if len(w) >= 7 else (eps, rmin_half)
+                    f = 2.0 * 2.0 ** (-1.0 / 6.0)
+                    self.lj[t] = (rmin_half * f, eps, rmin14_half * f, eps14)
+            except (ValueError, IndexError):
+                continue  # keyword lines inside a section (cutnb ..., HBOND CUTHB ...)
+
+    # ---- the reference's _ForceFieldBase interface -------------------------------------------------
+    def get_atom_types(self):
+        return np.unique(self.mol.atomtype)
+
+    def get_charge(self, at):
+        return self.mol.charge[np.where(self.mol.atomtype == at)[0][0]]
+
+    def get_mass(self, at):
+        if self.mol is not None and getattr(self.mol, "masses", None) is not None and len(self.mol.masses):
+            return self.mol.masses[np.where(self.mol.atomtype == at)[0][0]]
+        return self.masses[str(at).upper()]
+
+    def get_LJ(self, at):
+        s = self.lj[str(at).upper()]
+        return s[0], s[1]
+
+    def get_bond(self, at1, at2):
+        return self.bonds[(str(at1).upper(), str(at2).upper())]
+
+    def get_angle(self, at1, at2, at3):
+        k, theta = self.angles[(str(at1).upper(), str(at2).upper(), str(at3).upper())]
+        return k, math.radians(theta)
+
+    def _dihedral_terms(self, at):
+        key = tuple(str(a).upper() for a in at)
+        if key not in self.dihedrals:
+            raise RuntimeError(f"Could not find dihedral parameters for {key}")
+        return self.dihedrals[key]
+
+    def get_dihedral(self, at1, at2, at3, at4):
+        return [list(t) for t in self._dihedral_terms((at1, at2, at3, at4))]
+
+    def get_14(self, at1, at2, at3, at4):
+        self._dihedral_terms((at1, at2, at3, at4))
+        l1, l4 = self.lj[str(at1).upper()], self.lj[str(at4).upper()]
+        return 1.0, 1.0, l1[2], l1[3], l4[2], l4[3]
+
+    def get_improper(self, at1, at2, at3, at4):
+        from itertools import permutations
+
+        types = [str(a).upper() for a in (at1, at2, at3, at4)]
+        for p in permutations((0, 1, 2, 3)):
+            if p[2] != 2:
+                continue
+            key = tuple(types[i] for i in p)
+            if key in self.impropers:  # (parmed's keys are sorted tuples: a permutation matches only if it is sorted)
+                return self.impropers[key]
+        raise RuntimeError(f"Could not find improper parameters for key {types}")

@@ -103,7 +103,8 @@ def yaml_parameters(mol, forcefield, terms=None, precision=torch.float32, device
     terms)`` -- same unique-term ordering, same first-appearance parameter rows.  Like the
     reference (``torch.tensor(list of Python floats)`` is fp32, then ``.type(precision)``) every
     parameter value passes through fp32, also for ``precision=torch.float64``."""
-    ff = forcefield if isinstance(forcefield, YamlForceField) else YamlForceField(forcefield)
+    # a force-field object with the reference's interface (YamlForceField, charmm.CharmmPrmForceField), or a YAML path / dict
+    ff = forcefield if hasattr(forcefield, "get_LJ") else YamlForceField(forcefield)
     if terms is None:
         terms = ("bonds", "angles", "dihedrals", "impropers", "1-4", "electrostatics", "lj")
     terms = [t.lower() for t in terms]
