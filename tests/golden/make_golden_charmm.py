@@ -1,12 +1,12 @@
-"""Golden vectors for the reference's small CHARMM fixtures (tests/data/{1water,2ions,3ions,1dihedral,singledihedral,
-4dihedrals,benzamidine}: PSF + PDB + CHARMM .prm), configured as tests/test_torchmd.py:363-365 configures a fixture
-without a box (no cutoff, no switching, plain Coulomb, all terms).
+"""Golden vectors for the reference's ten CHARMM fixtures (tests/data/{1water,2ions,3ions,1dihedral,singledihedral,
+4dihedrals,benzamidine,2watersperiodic,sodiumperiodic,waterbox}: PSF + PDB + CHARMM .prm [+ .xtc]), configured as
+tests/test_torchmd.py:363-369 configures them: all terms; without a box no cutoff, no switching, plain Coulomb; with a
+box cutoff = min(box)/2 - 0.01, switch_dist 6, reaction field.
 
 The values come from the UNMODIFIED reference: its Parameters (torchmd/parameters.py) builds the tables, its
 Forces.compute evaluates them, in fp32 and fp64.  What the reference cannot do here is read the files (it needs
-moleculekit + parmed): the molecule comes from repo torchmd_b200/charmm.py (load_molecule) and the force-field object
-the reference queries is repo CharmmPrmForceField, a restatement of its parmed adapter's look-ups.  The periodic
-CHARMM fixtures take their box from .xtc trajectories and stay out.
+moleculekit + parmed): the molecule comes from repo torchmd_b200/charmm.py (load_molecule, read_xtc_first_frame) and the
+force-field object the reference queries is repo CharmmPrmForceField, a restatement of its parmed adapter's look-ups.
 
     PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=/root/reference python tests/golden/make_golden_charmm.py
 """
@@ -33,14 +33,26 @@ from torchmd_b200 import charmm  # noqa: E402
 
 ALLTERMS = ["bonds", "angles", "dihedrals", "impropers", "1-4", "electrostatics", "lj"]
 CASES = ["1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine"]
+# box from the .xtc header as the reference's test reads it (tests/test_torchmd.py:349-351); periodic fixtures are configured
+# as :366-369 does: cutoff = min(box)/2 - 0.01, switch_dist 6, reaction field.  waterbox's trajectory has a zero box (no
+# cutoff); its 293-atom frames are compressed, so the coordinates of its structure.pdb are used.
+XTC_CASES = ["2watersperiodic", "sodiumperiodic", "waterbox"]
 
 
-def case(name, nrep=2):
+def case(name, nrep=2, xtc=False):
     folder = os.path.join(REF, "tests/data", name)
     psf, pdb, prm = (glob.glob(os.path.join(folder, e))[0] for e in ("*.psf", "*.pdb", "*.prm"))
     mol = charmm.load_molecule(psf, pdb)
     ff = charmm.CharmmPrmForceField(prm, mol)
     xyz = np.asarray(mol.coords, dtype=np.float32).reshape(-1, 3)
+    boxv = np.zeros(3, dtype=np.float32)
+    if xtc:
+        frame, boxv = charmm.read_xtc_first_frame(glob.glob(os.path.join(folder, "*.xtc"))[0])
+        if frame is not None:
+            assert np.abs(frame - xyz).max() < 2e-3, name  # the trajectory's first frame is the PDB structure
+    cfg = dict(cutoff=None, rfa=False, switch_dist=None)
+    if np.any(boxv != 0):
+        cfg = dict(cutoff=float(np.min(boxv)) / 2 - 0.01, rfa=True, switch_dist=6.0)
     start = torch.tensor(xyz)[None].repeat(nrep, 1, 1).contiguous()
     g = torch.Generator().manual_seed(11)
     start[1] += (0.02 * torch.randn(start[1].shape, generator=g, dtype=torch.float64)).float()
@@ -49,9 +61,11 @@ def case(name, nrep=2):
     for tag, prec in (("f32", torch.float32), ("f64", torch.float64)):
         par = RefParameters(ff, mol, terms, precision=prec, device="cpu")
         use = [t for t in terms if not (t == "impropers" and par.improper_params is None)]
-        f = RefForces(par, terms=use, cutoff=None, rfa=False, switch_dist=None)
+        f = RefForces(par, terms=use, **cfg)
         pos = start.to(prec)
         box = torch.zeros(nrep, 3, 3, dtype=prec)
+        for k in range(3):
+            box[:, k, k] = float(boxv[k])
         F = torch.zeros_like(pos)
         E = f.compute(pos, box, F, returnDetails=True)
         keys = [k for k in E[0] if k != "external"]
@@ -59,7 +73,7 @@ def case(name, nrep=2):
         res[f"energies_{tag}"] = np.array([[e[k] for k in keys] for e in E])
         res[f"forces_{tag}"] = F.numpy().copy()
         # the oracle must agree bit for bit with the reference on the same tables
-        of = refmd.OracleForces(par, use, cutoff=None, rfa=False, switch_dist=None)
+        of = refmd.OracleForces(par, use, **cfg)
         Fo = torch.zeros_like(pos)
         Eo = of.compute(pos, box, Fo)
         assert torch.equal(F, Fo), name
@@ -73,9 +87,9 @@ def case(name, nrep=2):
             res.update({"par_" + k: v for k, v in pack_params(par).items()})
     res["coords"] = xyz
     res["coords_replicas"] = start.numpy().copy()
-    res["box"] = np.zeros(3, dtype=np.float32)
+    res["box"] = boxv
     res["terms"] = np.array(use)
-    for k, v in dict(cutoff=None, rfa=False, switch_dist=None).items():
+    for k, v in cfg.items():
         res["cfg_" + k] = np.array(np.nan if v is None else v)
     res["cfg_nrep"] = np.int64(nrep)
     res["source"] = np.array("reference Parameters + Forces.compute on a molecule / force field read by torchmd_b200/charmm.py")
@@ -86,3 +100,5 @@ def case(name, nrep=2):
 if __name__ == "__main__":
     for c in CASES:
         case(c)
+    for c in XTC_CASES:
+        case(c, xtc=True)

@@ -13,7 +13,7 @@ from conftest import golden_cfg, golden_system_tensors, load_golden, params_from
 from oracle import refmd
 
 DATA = "/root/reference/tests/data"
-CASES = ["1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine"]
+CASES = ["1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine", "2watersperiodic", "sodiumperiodic", "waterbox"]
 needs_files = pytest.mark.skipif(not os.path.isdir(DATA), reason="reference data files not present")
 
 

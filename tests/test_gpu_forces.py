@@ -46,7 +46,7 @@ CASES = [
 NEW_CASES = ["benzamidine_amber_nocut", "ligand_amber_nocut"]
 # ... and its small CHARMM fixtures (PSF + PDB + .prm; goldens from the reference's own Parameters + Forces.compute,
 # tests/golden/make_golden_charmm.py)
-NEW_CASES += ["charmm_" + n for n in ("1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine")]
+NEW_CASES += ["charmm_" + n for n in ("1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine", "2watersperiodic", "sodiumperiodic", "waterbox")]
 
 
 def force_tol(ref_F, ref_dev=0.0):

@@ -48,7 +48,7 @@ def hostsim_r2(monkeypatch):
 
 FORCE_CASES = ["water291_rf_switch", "water291_plain", "argon100_nocut", "chain_amber_vacuum", "chain_amber_periodic",
                "chain_charmm_periodic", "ala2_xsc_rf", "benzamidine_amber_nocut", "ligand_amber_nocut"]
-FORCE_CASES += ["charmm_" + n for n in ("1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine")]
+FORCE_CASES += ["charmm_" + n for n in ("1water", "2ions", "3ions", "1dihedral", "singledihedral", "4dihedrals", "benzamidine", "2watersperiodic", "sodiumperiodic", "waterbox")]
 
 
 @pytest.mark.parametrize("name", FORCE_CASES)

@@ -79,6 +79,25 @@ def read_pdb(path):
     return np.array(xyz, dtype=np.float32).reshape(-1, 3), box
 
 
+def read_xtc_first_frame(path):
+    """(coords (N,3) or None, box (3,)) in Angstrom from the first frame of a GROMACS .xtc file.  The header (XDR:
+    magic 1995, atom count, step, time, 3x3 box in nm) is always plain; the coordinates are plain floats only for up
+    to nine atoms (larger frames are compressed -- None is returned for them)."""
+    import struct
+
+    with open(path, "rb") as fh:
+        b = fh.read()
+    magic, natoms, _step = struct.unpack(">iii", b[:12])
+    if magic != 1995:
+        raise ValueError(f"{path}: not an xtc file (magic {magic})")
+    box = np.array(struct.unpack(">9f", b[16:52]), dtype=np.float64).reshape(3, 3)
+    xyz = None
+    if natoms <= 9:
+        xyz = 10.0 * np.array(struct.unpack(">%df" % (3 * natoms), b[56 : 56 + 12 * natoms]), dtype=np.float64).reshape(natoms, 3)
+        xyz = xyz.astype(np.float32)
+    return xyz, (10.0 * np.diag(box)).astype(np.float32)
+
+
 def load_molecule(psf_path, pdb_path=None):
     """The duck-typed ``mol`` the reference's Parameters / System set-up reads
     (SURVEY.md section 8c): numAtoms, atomtype, charge, masses, bonds, angles, dihedrals,
