@@ -7,6 +7,8 @@ that run on the B200 execute every line of the host classes and of the C entry p
 plumbing and logic (argument marshalling, return formats, rebuild protocol, error paths) -- what the B200 run adds
 is the device arithmetic and speed.  The slow cases stay with the GPU suite.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -273,3 +275,31 @@ def test_ab_bench_script_dry_run(hostsim, monkeypatch, capsys):
     t = [float(r.split()[5]) for r in rows]
     launches = [float(r.split()[4]) for r in rows]
     assert abs(t[0] - t[1]) < 1e-3 * t[0] and launches[1] < launches[0], rows
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/tests/test_integrator.py"), reason="reference checkout not present")
+def test_the_references_own_integrator_tests_pass_against_this_package(hostsim, monkeypatch):
+    """/root/reference/tests/test_integrator.py, unmodified, with `torchmd.integrator` and `torchmd.systems` resolving
+    to this package's mirrors: its eleven known-answer tests -- kinetic energy with and without
+    batches, constructor attributes, velocity-Verlet arithmetic with one and two replicas -- run through Integrator.step
+    and the integrator kernels of the (host-interpreted) library."""
+    import importlib.util
+    import sys
+    import types
+
+    import torchmd_b200.integrator
+    import torchmd_b200.systems
+
+    monkeypatch.setattr(sys, "dont_write_bytecode", True)  # the reference tree is read-only
+    pkg = types.ModuleType("torchmd")
+    pkg.integrator, pkg.systems = torchmd_b200.integrator, torchmd_b200.systems
+    monkeypatch.setitem(sys.modules, "torchmd", pkg)
+    monkeypatch.setitem(sys.modules, "torchmd.integrator", torchmd_b200.integrator)
+    monkeypatch.setitem(sys.modules, "torchmd.systems", torchmd_b200.systems)
+    spec = importlib.util.spec_from_file_location("reference_test_integrator", "/root/reference/tests/test_integrator.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    names = [n for n in dir(mod) if n.startswith("test_")]
+    assert len(names) == 11
+    for n in names:
+        getattr(mod, n)()
