@@ -7,3 +7,10 @@
 // the product.
 #define TMD_SIMT_HOST 1
 #include "../../torchmd_b200/csrc/tmd_b200.cu"
+
+// what the record-and-replay graph model did (tests/test_simt_kernels.py): replays, IF bodies run / skipped
+extern "C" void simt_graph_counters(long long* out) {
+  out[0] = simt_stub::state().graph_launches;
+  out[1] = simt_stub::state().bodies_run;
+  out[2] = simt_stub::state().bodies_skipped;
+}

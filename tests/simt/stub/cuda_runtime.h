@@ -78,9 +78,9 @@ inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n +
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st = nullptr);  // (capture-aware: below)
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr);
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -94,11 +94,11 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { static long n = 0; *s = reinterpret_cast<cudaStream_t>(++n); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned);  // (a captured event pulls the waiting stream into the capture: below)
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { static long n = 0; *e = reinterpret_cast<cudaEvent_t>(++n); return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 struct cudaIpcMemHandle_t { char reserved[64]; };
@@ -107,10 +107,27 @@ enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorNotSupported; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
-// graphs: never taken in the interpreter (the switches that use them stay off)
-typedef struct simt_graph_* cudaGraph_t;
-typedef struct simt_graph_exec_* cudaGraphExec_t;
-typedef struct simt_graph_node_* cudaGraphNode_t;
+// ---- graphs: record and replay -------------------------------------------------------------------
+// A capturing stream records its work (kernel launches through the library's launch() helper, async memsets and
+// copies) as closures in program order -- a valid topological order of the real graph -- and cudaGraphLaunch runs them
+// again.  A stream that waits on an event recorded in a capturing stream joins that capture, as in CUDA.  An IF node
+// holds a body graph and runs it when its handle is non-zero; handles created with cudaGraphCondAssignDefault fall
+// back to their default after every launch.  This models the CONTROL structure the library builds (what is captured
+// where, what a replay executes); it says nothing about the real API's argument checking.
+#include <functional>
+#include <map>
+#include <vector>
+struct simt_graph_;
+struct simt_graph_node_ {
+  std::function<void()> run;                  // kernel / memset / memcpy
+  unsigned long long handle = 0;              // IF node: its condition ...
+  simt_graph_* body = nullptr;                // ... and body
+  simt_graph_* body_out[1] = {nullptr};       // storage behind cudaConditionalNodeParams::phGraph_out
+};
+struct simt_graph_ { std::vector<simt_graph_node_*> nodes; };
+typedef simt_graph_* cudaGraph_t;
+typedef simt_graph_* cudaGraphExec_t;
+typedef simt_graph_node_* cudaGraphNode_t;
 typedef unsigned long long cudaGraphConditionalHandle;
 enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone, cudaStreamCaptureStatusActive };
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
@@ -120,16 +137,115 @@ enum cudaGraphConditionalNodeType { cudaGraphCondTypeIf };
 struct cudaConditionalNodeParams { cudaGraphConditionalHandle handle; cudaGraphConditionalNodeType type; unsigned size; cudaGraph_t* phGraph_out; };
 struct cudaGraphNodeParams { cudaGraphNodeType type; cudaConditionalNodeParams conditional; };
 struct cudaGraphEdgeData;
-inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) { *s = cudaStreamCaptureStatusNone; return cudaSuccess; }
-inline cudaError_t cudaStreamGetCaptureInfo(cudaStream_t, cudaStreamCaptureStatus* s, unsigned long long* = nullptr, cudaGraph_t* = nullptr, const cudaGraphNode_t** = nullptr, size_t* = nullptr) { *s = cudaStreamCaptureStatusNone; return cudaSuccess; }
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t, cudaGraph_t, const cudaGraphNode_t*, const cudaGraphEdgeData*, size_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t, cudaGraphNode_t*, size_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle*, cudaGraph_t, unsigned, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphAddNode(cudaGraphNode_t*, cudaGraph_t, const cudaGraphNode_t*, size_t, cudaGraphNodeParams*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+namespace simt_stub {
+struct Cond { unsigned value, def; bool reset; };
+struct State {
+  std::map<cudaStream_t, simt_graph_*> capture;   // streams that are capturing, and into which graph
+  std::map<cudaStream_t, cudaStream_t> origin;    // a joined stream -> the stream whose capture it joined
+  std::map<cudaEvent_t, cudaStream_t> event_in;   // events recorded in a capturing stream -> that stream
+  std::vector<Cond> conds{Cond{0, 0, false}};     // handle = index (0 is "no handle")
+  long long graph_launches = 0, bodies_run = 0, bodies_skipped = 0;  // what the replays did (simt_lib.cpp exports them)
+};
+inline State& state() { static State s; return s; }
+inline bool capturing(cudaStream_t st) { return state().capture.count(st) != 0; }
+inline void record(cudaStream_t st, std::function<void()> fn) {
+  simt_graph_node_* n = new simt_graph_node_;
+  n->run = std::move(fn);
+  state().capture[st]->nodes.push_back(n);
+}
+inline void run_graph(simt_graph_* g) {
+  for (simt_graph_node_* n : g->nodes) {
+    if (n->body) {
+      if (state().conds[n->handle].value) { state().bodies_run++; run_graph(n->body); }
+      else state().bodies_skipped++;
+    }
+    else n->run();
+  }
+}
+}  // namespace simt_stub
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+  if (simt_stub::capturing(st)) simt_stub::record(st, [=]() { memmove(d, s, n); });
+  else memmove(d, s, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
+  if (simt_stub::capturing(st)) simt_stub::record(st, [=]() { memset(d, v, n); });
+  else memset(d, v, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st) {
+  if (simt_stub::capturing(st)) simt_stub::state().event_in[e] = st;
+  else simt_stub::state().event_in.erase(e);
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned) {
+  auto& S = simt_stub::state();
+  auto it = S.event_in.find(e);
+  if (it != S.event_in.end() && !simt_stub::capturing(st) && simt_stub::capturing(it->second)) {
+    S.capture[st] = S.capture[it->second];  // fork: the waiting stream records into the same graph
+    S.origin[st] = it->second;
+  }
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamIsCapturing(cudaStream_t st, cudaStreamCaptureStatus* s) {
+  *s = simt_stub::capturing(st) ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamGetCaptureInfo(cudaStream_t st, cudaStreamCaptureStatus* s, unsigned long long* = nullptr, cudaGraph_t* g = nullptr,
+                                            const cudaGraphNode_t** deps = nullptr, size_t* ndeps = nullptr) {
+  const bool on = simt_stub::capturing(st);
+  *s = on ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+  if (g) *g = on ? simt_stub::state().capture[st] : nullptr;
+  if (deps) *deps = nullptr;
+  if (ndeps) *ndeps = 0;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) {
+  if (simt_stub::capturing(st)) return cudaErrorNotSupported;
+  simt_stub::state().capture[st] = new simt_graph_;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t st, cudaGraph_t g, const cudaGraphNode_t*, const cudaGraphEdgeData*, size_t, cudaStreamCaptureMode) {
+  if (simt_stub::capturing(st) || !g) return cudaErrorNotSupported;
+  simt_stub::state().capture[st] = g;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g) {
+  auto& S = simt_stub::state();
+  if (!simt_stub::capturing(st)) return cudaErrorNotSupported;
+  *g = S.capture[st];
+  S.capture.erase(st);
+  for (auto it = S.origin.begin(); it != S.origin.end();)  // streams that joined this capture leave it with it
+    if (it->second == st) { S.capture.erase(it->first); it = S.origin.erase(it); } else ++it;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t st, cudaGraphNode_t*, size_t, unsigned) {
+  return simt_stub::capturing(st) ? cudaSuccess : cudaErrorNotSupported;  // (program order already is the dependency order)
+}
+inline cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle* h, cudaGraph_t, unsigned def, unsigned flags) {
+  auto& c = simt_stub::state().conds;
+  c.push_back(simt_stub::Cond{def, def, (flags & cudaGraphCondAssignDefault) != 0});
+  *h = c.size() - 1;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphAddNode(cudaGraphNode_t* node, cudaGraph_t g, const cudaGraphNode_t*, size_t, cudaGraphNodeParams* p) {
+  if (!g || p->type != cudaGraphNodeTypeConditional || p->conditional.type != cudaGraphCondTypeIf || p->conditional.size != 1 || !p->conditional.handle)
+    return cudaErrorNotSupported;
+  simt_graph_node_* n = new simt_graph_node_;
+  n->handle = p->conditional.handle;
+  n->body = n->body_out[0] = new simt_graph_;
+  p->conditional.phGraph_out = n->body_out;
+  g->nodes.push_back(n);
+  *node = n;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = g; return g ? cudaSuccess : cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+  simt_stub::state().graph_launches++;
+  simt_stub::run_graph(e);
+  for (auto& c : simt_stub::state().conds) if (c.reset) c.value = c.def;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }      // (leaked: test processes are short-lived)
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle h, unsigned v) { simt_stub::state().conds[h].value = v; }

@@ -25,8 +25,9 @@ VARIANTS = {  # tag -> defines; every interpreter build the tests use (built tog
     "": [],
     "_cull": ["BT_CULL=1"],
     "_paired": ["BT_CULL=1", "BT_PAIRED=1"],
+    "_graph": ["TMD_COND_NODE=1"],  # the device-side switch of the rebuild's conditional node compiled in
     # every opt-in path as the default (what round 2 switches on once the B200 has confirmed it)
-    "_r2": ["BT_CULL=1", "BT_PAIRED=1", "TMD_DEFAULT_FX=2", "TMD_DEFAULT_OVERLAP=1", "TMD_DEFAULT_FUSEPREP=1"],
+    "_r2": ["BT_CULL=1", "BT_PAIRED=1", "TMD_COND_NODE=1", "TMD_DEFAULT_FX=2", "TMD_DEFAULT_OVERLAP=1", "TMD_DEFAULT_FUSEPREP=1", "TMD_DEFAULT_GRAPH=1"],
     "_t2": ["FX_SMALLT_MAX_N=2"],
     "_fxu4": ["PAIR_FX_UNROLL=4"],
     "_fx2u2": ["PAIR_FX2_UNROLL=2"],
@@ -374,6 +375,52 @@ def test_integrate_and_prepare_in_one_kernel_is_bit_identical(simt, extra):
     assert st[0].rebuilds == st[1].rebuilds and st[0].rebuilds >= 2  # the list is rebuilt on the way
     # one launch fewer per step (k_prepare), two with the overlapped bonded kernel (k_add_bonded folded into k_vv_second)
     assert (st[0].kernel_launches - l0[0]) - (st[1].kernel_launches - l0[1]) == total * (2 if "TMD_B200_OVERLAP" in extra else 1)
+    Fa, Ea = a.forces(pos=a.posw)
+    Fb, Eb = b.forces(pos=b.posw)
+    assert np.array_equal(Fa, Fb) and repr(Ea) == repr(Eb)
+    a.close()
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def simt_graph():
+    return load(build_simt("_graph", VARIANTS["_graph"]))
+
+
+@pytest.mark.parametrize("extra", [{}, {"TMD_B200_OVERLAP": "1", "TMD_B200_FX": "2", "TMD_B200_FUSEPREP": "1"}])
+def test_captured_step_with_conditional_rebuild_replays_the_stream_path(simt_graph, extra):
+    """TMD_B200_GRAPH=1 (the interpreter's record-and-replay model of stream capture, tests/simt/stub): tmd_md_steps
+    captures one step twice (with / without energy outputs), the rebuild kernels go into the body of an IF node that
+    the preparing kernel switches on, and replaying gives the trajectory of the plain stream path bit for bit -- with
+    the rebuild kernels launched only on the steps that rebuild."""
+    from torchmd_b200 import _lib
+
+    L = simt_graph
+    g, t, a = md_setup(L, env=dict(extra))
+    _, _, b = md_setup(L, env=dict(extra, TMD_B200_GRAPH="1"))
+    gamma = 0.1 / (1000.0 / TIMEFACTOR)
+    vcoeff = np.sqrt(2.0 * gamma / a.masses.astype(np.float64) * BOLTZMAN * 300.0 * a.dt).astype(np.float32)
+    st = [_lib.Stats(), _lib.Stats()]
+    for k, c in enumerate((a, b)):
+        assert L.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
+    l0, r0 = [s.kernel_launches for s in st], [s.rebuilds for s in st]
+    total = 0
+    for niter in (1, 2, 17):
+        for c in (a, b):
+            md_steps(L, c, niter, gamma=gamma, vcoeff=vcoeff, seed=5)
+        total += niter
+        assert np.array_equal(a.posw, b.posw) and np.array_equal(a.vel, b.vel) and np.array_equal(a.F, b.F)
+        assert np.array_equal(a.ene, b.ene) and np.array_equal(a.ke, b.ke)
+    for k, c in enumerate((a, b)):
+        assert L.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
+    rebuilds = st[0].rebuilds - r0[0]
+    assert st[1].rebuilds - r0[1] == rebuilds and 2 <= rebuilds < total
+    counters = (C.c_longlong * 3)()
+    L.simt_graph_counters(counters)
+    assert counters[0] >= total and counters[1] + counters[2] == counters[0]  # every replay met its IF node ...
+    assert counters[1] >= rebuilds and counters[2] >= total - rebuilds - 3    # ... and skipped the body unless a rebuild was due
+    # a step that keeps its list launches none of the five rebuild kernels: the library's launch count is the captured
+    # step's node count (body included), so the check is on what actually ran -- the rebuild counter -- and on the results
     Fa, Ea = a.forces(pos=a.posw)
     Fb, Eb = b.forces(pos=b.posw)
     assert np.array_equal(Fa, Fb) and repr(Ea) == repr(Eb)

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -76,8 +77,12 @@ static int env_switch(const char* name, int def) {
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
 #if defined(TMD_SIMT_HOST)
-  (void)st;
-  simt::run_grid(grid, block, [&]() { kernel(args...); });
+  // (a capturing stream records the launch -- arguments by value, like a kernel node -- and the graph replays it)
+  auto run = [kernel, grid, block, held = std::make_tuple(std::decay_t<Args>(args)...)]() {
+    simt::run_grid(grid, block, [&]() { std::apply(kernel, held); });
+  };
+  if (simt_stub::capturing(st)) simt_stub::record(st, run);
+  else run();
 #else
   kernel<<<grid, block, 0, st>>>(std::forward<Args>(args)...);
 #endif
