@@ -14,3 +14,11 @@ extern "C" void simt_graph_counters(long long* out) {
   out[1] = simt_stub::state().bodies_run;
   out[2] = simt_stub::state().bodies_skipped;
 }
+
+// stream capture driven from Python (the tests' stand-in for torch.cuda.graph around library calls)
+extern "C" int simt_capture_begin(void* stream) { return (int)cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeGlobal); }
+extern "C" void* simt_capture_end(void* stream) {
+  cudaGraph_t g = nullptr;
+  return cudaStreamEndCapture((cudaStream_t)stream, &g) == cudaSuccess ? (void*)g : nullptr;
+}
+extern "C" int simt_graph_replay(void* graph) { return graph ? (int)cudaGraphLaunch((cudaGraphExec_t)graph, nullptr) : -1; }

@@ -135,9 +135,52 @@ def test_gated_peer_to_peer_test_runs_as_written(hostsim, monkeypatch):
     monkeypatch.setenv("MASTER_PORT", str(T_free_port()))
     try:
         P.test_p2p_world1_matches_integrator_bitwise(False)
+        _fake_torch_graphs(monkeypatch, hostsim)
+        launched = _graph_counters(hostsim)[0]
+        P.test_p2p_world1_matches_integrator_bitwise(True)  # one captured step per (energy outputs, buffer parity)
+        assert _graph_counters(hostsim)[0] - launched >= sum(P.SIZE["steps"]) + 3  # the steps really were replays
     finally:
         if dist.is_initialized():
             dist.destroy_process_group()
+
+
+def _graph_counters(handle):
+    import ctypes as C
+
+    out = (C.c_longlong * 3)()
+    handle.simt_graph_counters(out)
+    return list(out)
+
+
+def _fake_torch_graphs(monkeypatch, handle):
+    """torch.cuda.CUDAGraph / torch.cuda.graph on the interpreter's record-and-replay capture (tests/simt/stub): what
+    the library enqueues inside the `with` block is recorded on the null stream and `replay()` runs it again.  (A
+    collective issued inside the block runs at capture time only -- fine for one rank, where it is the identity.)"""
+    import ctypes as C
+
+    handle.simt_capture_end.restype = C.c_void_p
+    handle.simt_capture_begin.argtypes = handle.simt_capture_end.argtypes = handle.simt_graph_replay.argtypes = [C.c_void_p]
+
+    class Graph:
+        g = None
+
+        def replay(self):
+            assert handle.simt_graph_replay(self.g) == 0
+
+    class Capture:
+        def __init__(self, graph, **kw):
+            assert kw.get("capture_error_mode", "global") in ("global", "relaxed", "thread_local")
+            self.graph = graph
+
+        def __enter__(self):
+            assert handle.simt_capture_begin(None) == 0
+
+        def __exit__(self, *exc):
+            self.graph.g = handle.simt_capture_end(None)
+            return False
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
+    monkeypatch.setattr(torch.cuda, "graph", Capture)
 
 
 def T_free_port():
@@ -303,3 +346,37 @@ def test_the_references_own_integrator_tests_pass_against_this_package(hostsim, 
     assert len(names) == 11
     for n in names:
         getattr(mod, n)()
+
+
+def test_decomposed_integrator_replays_captured_steps(hostsim, monkeypatch):
+    """DecomposedIntegrator with its default exchange and use_graph=True (one rank): the step it captures -- half-kick,
+    exchange, force call with the gated rebuild, second half-kick -- replays to the trajectory of Integrator.step."""
+    import torch.distributed as dist
+
+    import test_gpu_zzz_p2p as P
+    from torchmd_b200 import Integrator
+    from torchmd_b200.domain import DecomposedIntegrator
+
+    monkeypatch.setattr(P, "DEV", "cpu")
+    monkeypatch.setattr(P, "SIZE", dict(waters=64, cutoff=5.0, switch=4.0, skin=0.3, steps=(1, 2, 7), backend="gloo"))
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("MASTER_PORT", str(T_free_port()))
+    _fake_torch_graphs(monkeypatch, hostsim)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        sa, fa = P._setup()
+        torch.manual_seed(9)
+        ia = Integrator(sa, fa, 1.0, "cpu", gamma=0.1, T=300.0)
+        sb, fb = P._setup()
+        torch.manual_seed(9)
+        ib = DecomposedIntegrator(sb, fb, 1.0, "cpu", gamma=0.1, T=300.0, use_graph=True)
+        assert ib.exchange == "allgather"
+        launched = _graph_counters(hostsim)[0]
+        for niter in (1, 2, 7):
+            ea, eb = ia.step(niter=niter), ib.step(niter=niter)
+            assert torch.equal(sa.pos, sb.pos) and torch.equal(sa.vel, sb.vel)
+            np.testing.assert_allclose(ea[1], eb[1], rtol=1e-9, atol=1e-6)
+        assert ib.use_graph and len(ib._graphs) == 2 and _graph_counters(hostsim)[0] - launched == 10
+        assert fb.stats()["rebuilds"] >= 2
+    finally:
+        dist.destroy_process_group()
