@@ -404,6 +404,8 @@ def test_captured_step_with_conditional_rebuild_replays_the_stream_path(simt_gra
     for k, c in enumerate((a, b)):
         assert L.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
     l0, r0 = [s.kernel_launches for s in st], [s.rebuilds for s in st]
+    before = (C.c_longlong * 3)()
+    L.simt_graph_counters(before)  # (the model's counters are per process: other tests replay graphs too)
     total = 0
     for niter in (1, 2, 17):
         for c in (a, b):
@@ -415,10 +417,11 @@ def test_captured_step_with_conditional_rebuild_replays_the_stream_path(simt_gra
         assert L.tmd_get_stats(c.h, C.byref(st[k]), None) == 0
     rebuilds = st[0].rebuilds - r0[0]
     assert st[1].rebuilds - r0[1] == rebuilds and 2 <= rebuilds < total
-    counters = (C.c_longlong * 3)()
-    L.simt_graph_counters(counters)
-    assert counters[0] >= total and counters[1] + counters[2] == counters[0]  # every replay met its IF node ...
-    assert counters[1] >= rebuilds and counters[2] >= total - rebuilds - 3    # ... and skipped the body unless a rebuild was due
+    after = (C.c_longlong * 3)()
+    L.simt_graph_counters(after)
+    replays, ran, skipped = (after[k] - before[k] for k in range(3))
+    assert replays == total and ran + skipped == total  # every step was a replay and met its IF node ...
+    assert ran == rebuilds                               # ... whose body ran exactly on the steps that rebuilt
     # a step that keeps its list launches none of the five rebuild kernels: the library's launch count is the captured
     # step's node count (body included), so the check is on what actually ran -- the rebuild counter -- and on the results
     Fa, Ea = a.forces(pos=a.posw)
