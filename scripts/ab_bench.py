@@ -90,6 +90,9 @@ def main(argv=None):
             print("%-44s %9.0f %9.4f %9.4f %8.1f %7.1f   [pair kernel %d, %d rebuilds]" % (
                 label, 1e3 / ms, ms, pair_ms.value / max(1, pair_n.value), (st1["kernel_launches"] - st0["kernel_launches"]) / args.steps,
                 float(T[0]), L.tmd_pair_kernel(forces._ctx), st1["rebuilds"] - st0["rebuilds"]), flush=True)
+            # the context goes with the library build that made it (the next variant may load another build)
+            L.tmd_destroy(forces._ctx)
+            forces._ctx = None
             del integ, eq, forces, system
         except Exception as err:  # one broken variant must not cost the others their measurement
             print("%-44s failed: %s" % (label, err), flush=True)
