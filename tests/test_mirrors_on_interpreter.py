@@ -380,3 +380,26 @@ def test_decomposed_integrator_replays_captured_steps(hostsim, monkeypatch):
         assert fb.stats()["rebuilds"] >= 2
     finally:
         dist.destroy_process_group()
+
+
+def _fuzz_module():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("fuzz_interpreter", os.path.join(T.ROOT, "scripts", "fuzz_interpreter.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("build", ["default", "round2"])
+def test_differential_fuzz_sample(request, build):
+    """A seeded sample of scripts/fuzz_interpreter.py (random non-cubic boxes, atoms a box away, replicas, exclusions,
+    switching / reaction field / no cutoff) on the default build and on the build with every opt-in path on."""
+    request.getfixturevalue("hostsim" if build == "default" else "hostsim_r2")
+    fuzz = _fuzz_module()
+    bad = []
+    for seed in range(2000, 2016):
+        ok, desc = fuzz.one_case(seed)
+        if not ok:
+            bad.append(desc)
+    assert not bad, "\n".join(bad)
