@@ -58,11 +58,11 @@ def one_case(seed):
         pos[r] = np.array(pts)
         if periodic:
             far = rng.random(n) < 0.15
-            # one box either way: image counts of a pair stay in -2..2, for which fl(L * count) is exact.  (For counts
-            # of 3, 5, 6 ... the float kernel keeps the reference's rounding error of L * count in its VALUES -- it only
-            # restores the bits fl(p_i - p_j) drops -- and is then no better than the reference's fp32; the fixed-point
-            # kernels do not have the problem.  FAR=1 in the environment fuzzes that regime.)
-            reach = 3 if os.environ.get("FAR") == "1" else 1
+            # one box either way by default; FAR=<k> in the environment moves atoms up to k boxes away (image counts of
+            # 3, 5, 6, 7 ... for which fl(L * count) is inexact: the float kernel's VALUES use the unrounded product,
+            # physics.cuh straddle_value, so its forces stay at the 1e-4 yardstick where the reference's fp32 does not;
+            # STRICT=1 drops the allowance for the reference's own fp32 deviation from the tolerance below)
+            reach = int(os.environ.get("FAR", "1"))
             pos[r][far] += L * rng.integers(-reach, reach + 1, size=(int(far.sum()), 3))
     ntypes = int(rng.integers(1, 5))
     types = rng.integers(0, ntypes, size=n)
@@ -104,7 +104,9 @@ def one_case(seed):
     F32 = torch.zeros_like(p32)
     of32f.compute(p32, box, F32)
     dev = float((F32.double() - F64).abs().max())
-    tol = max(1e-4 * max(1.0, fmax / 100.0), 1.2 * dev)
+    tol = 1e-4 * max(1.0, fmax / 100.0)
+    if os.environ.get("STRICT") != "1":
+        tol = max(tol, 1.2 * dev)
     ok = err < tol
     for r in range(nrep):
         for k in terms:

@@ -194,16 +194,17 @@ void hc_pair_forces(int variant, int natoms, int npairs, const int* pairs, const
       s = fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0]));
     } else {
       bool straddle = false;
-      float d0[3];
+      float d0[3], img[3];
       for (int k = 0; k < 3; ++k) {
         float r;
         d0[k] = sub_rn(pos[3 * i + k], pos[3 * j + k]);
         w[k] = min_image_exact(d0[k], box[k], iL[k], r);
+        img[k] = r;
         straddle |= (r != 0.f);
       }
       s = norm2_ref(w[0], w[1], w[2]);
       if (straddle) {
-        for (int k = 0; k < 3; ++k) w[k] += sub_err(pos[3 * i + k], pos[3 * j + k], d0[k]);
+        for (int k = 0; k < 3; ++k) w[k] = straddle_value(pos[3 * i + k], pos[3 * j + k], d0[k], box[k], img[k]);
         s = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
       }
     }

@@ -105,10 +105,11 @@ k_pair(DeviceState S, float* __restrict__ forces, double* __restrict__ energies)
       float s = norm2_ref(wx, wy, wz);  // the reference's own rounding: decides in/out
       if (s <= pp.s_max) {
         if (PERIODIC && (rx != 0.f || ry != 0.f || rz != 0.f)) {
-          // straddles the box: give the VALUES the bits fl(pi-pj) dropped (sub_err)
-          wx += sub_err(pi.x, pj.x, dx0);
-          wy += sub_err(pi.y, pj.y, dy0);
-          wz += sub_err(pi.z, pj.z, dz0);
+          // straddles the box: the VALUES get the bits fl(pi-pj) dropped and the unrounded image
+          // shift L*n (physics.cuh, straddle_value)
+          wx = straddle_value(pi.x, pj.x, dx0, Lx, rx);
+          wy = straddle_value(pi.y, pj.y, dy0, Ly, ry);
+          wz = straddle_value(pi.z, pj.z, dz0, Lz, rz);
           s = wx * wx + wy * wy + wz * wz;
         }
         float2 ab = make_float2(0.f, 0.f);

@@ -130,6 +130,11 @@ TMD_HD float sub_err(float a, float b, float d) {
   return sub_rn(da, add_rn(b, c1));
 }
 
+// Separation of a pair that straddles the box, for the force VALUES: one fused multiply-add  fl(d - L * n)  on the
+// unrounded product (the decision path's fl(d - fl(L * n)) carries the rounding of L * n, up to ulp(L * n) / 2, for the
+// image counts 3, 5, 6, 7 ...; for 0, +-1, +-2, +-4 both are the same bits), plus the bits fl(a - b) dropped.
+TMD_HD float straddle_value(float a, float b, float d, float L, float n) { return add_rn(fmaf(-L, n, d), sub_err(a, b, d)); }
+
 TMD_HD float rcp_refined(float a) {
 #if defined(__CUDA_ARCH__)
   float y;
