@@ -68,6 +68,7 @@ def test_forces_api_formats_errors_replicas_and_skin(hostsim):
     G.test_api_errors_and_formats()
     G.test_forces_deterministic_and_replicas_identical()
     G.test_results_do_not_depend_on_skin(0.3)
+    G.test_molecules_several_boxes_away_meet_the_plain_yardstick()  # (gated on the GPU until its first B200 run)
 
 
 def test_repulsion_terms(hostsim):
