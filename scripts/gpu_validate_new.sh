@@ -50,7 +50,7 @@ fi
 if has 2; then
   TMD_B200_VALIDATE=1 timeout -s KILL 500 python -m pytest tests/test_gpu_zzz_fixedpoint.py -q -s > gpurun_out/validate_fx.log 2>&1; echo "fixed-point / packed kernels rc=$?"
   grep -E "max\|dF\||NVE|drifted|passed|failed|Error|error" gpurun_out/validate_fx.log | tail -40
-  TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_trajectory.py tests/test_gpu_zzz_p2p.py tests/test_gpu_forces.py -k "not test_gpu_forces or new_reference" -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap / autograd / trajectory / p2p-world1 rc=$?"
+  TMD_B200_VALIDATE=1 timeout -s KILL 400 python -m pytest tests/test_wrapper.py tests/test_autograd_path.py tests/test_trajectory.py tests/test_gpu_zzz_p2p.py tests/test_gpu_forces.py -k "not test_gpu_forces or new_reference or several_boxes" -m gpu -q -s > gpurun_out/validate_rows.log 2>&1; echo "wrap / autograd / trajectory / p2p-world1 rc=$?"
   grep -E "passed|failed|Error|error" gpurun_out/validate_rows.log | tail -12
 fi
 if has 3; then
