@@ -76,13 +76,52 @@ def one_case(seed):
     if len(bonds):
         terms.append("bonds")
         bonded = (bonds, np.stack([np.arange(len(bonds)), np.zeros(len(bonds), int)], 1), np.array([[30.0, 2.5]]))
+    # BONDED=1 in the environment: random angles, multi-term dihedrals (AMBER cosine series, or a harmonic CHARMM term
+    # where every period of the list is zero), impropers of either kind and scaled 1-4 pairs over random atom tuples
+    angles = dihedrals = impropers = pairs14 = None
+    if os.environ.get("BONDED") == "1" and n >= 6:
+
+        def tuples(count, k):
+            out = [rng.choice(n, size=k, replace=False) for _ in range(count)]
+            return np.unique(np.array(out, dtype=np.int64), axis=0)
+
+        if rng.random() < 0.8:
+            idx = tuples(int(rng.integers(1, n)), 3)
+            prm = np.stack([rng.uniform(10.0, 60.0, 3), rng.uniform(1.6, 2.2, 3)], 1)
+            angles = (idx, np.stack([np.arange(len(idx)), rng.integers(0, 3, len(idx))], 1), prm)
+            terms.append("angles")
+
+        def torsion_set(count):
+            idx = tuples(count, 4)
+            harmonic = rng.random() < 0.35  # the reference switches on `all periods > 0` for the WHOLE list
+            if harmonic:
+                prm = np.stack([rng.uniform(5.0, 50.0, 3), rng.uniform(-np.pi, np.pi, 3), np.zeros(3)], 1)
+                mp = np.stack([np.arange(len(idx)), rng.integers(0, 3, len(idx))], 1)
+            else:
+                prm = np.stack([rng.uniform(0.05, 2.0, 5), rng.choice([0.0, np.pi], 5), rng.integers(1, 5, 5).astype(float)], 1)
+                rows = np.repeat(np.arange(len(idx)), rng.integers(1, 4, len(idx)))  # up to three series terms per dihedral
+                mp = np.stack([rows, rng.integers(0, 5, len(rows))], 1)
+            return idx, mp, prm
+
+        if rng.random() < 0.8:
+            dihedrals = torsion_set(int(rng.integers(1, n)))
+            terms.append("dihedrals")
+            if rng.random() < 0.7:
+                idx = np.unique(np.sort(dihedrals[0][:, [0, 3]], axis=1), axis=0)
+                prm = np.stack([rng.uniform(1e4, 6e5, 3), rng.uniform(50.0, 700.0, 3), np.full(3, 2.0), np.full(3, 1.2)], 1)
+                pairs14 = (idx, np.stack([np.arange(len(idx)), rng.integers(0, 3, len(idx))], 1), prm)
+                terms.append("1-4")
+        if rng.random() < 0.6:
+            impropers = torsion_set(int(rng.integers(1, max(2, n // 3))))
+            terms.append("impropers")
     switch = float(rng.uniform(0.5 * cutoff, 0.95 * cutoff)) if cutoff and rng.random() < 0.6 else None
     rfa = bool(cutoff and rng.random() < 0.6)
     skin = float(rng.choice([0.0, 0.3, 1.0, 2.0]))
 
     def params(prec):
         return TopologyParameters(atom_types=types, type_sigma=sigma, type_epsilon=eps, charges=charges.astype(np.float32),
-                                  masses=np.full(n, 12.0, np.float32), bonds=bonded, precision=prec, device="cpu")
+                                  masses=np.full(n, 12.0, np.float32), bonds=bonded, angles=angles, dihedrals=dihedrals,
+                                  impropers=impropers, pairs14=pairs14, precision=prec, device="cpu")
 
     cfg = dict(cutoff=cutoff, rfa=rfa, switch_dist=switch)
     f = Forces(params(torch.float32), terms=terms, skin=skin, **cfg)
@@ -117,7 +156,11 @@ def one_case(seed):
         got = f.neighbour_pairs(p32, box, replica=r).cpu().numpy() if "replica" in f.neighbour_pairs.__code__.co_varnames else None
         if got is not None:
             ok = ok and got.shape == want.shape and np.array_equal(got, want)
-    desc = f"seed {seed}: n={n} R={nrep} periodic={periodic} L={np.round(L, 2)} cutoff={cutoff} switch={switch} rfa={rfa} skin={skin} bonds={len(bonds)}"
+    if len(terms) > 3:
+        desc_terms = " terms=" + ",".join(terms[2:])
+    else:
+        desc_terms = ""
+    desc = f"seed {seed}:{desc_terms} n={n} R={nrep} periodic={periodic} L={np.round(L, 2)} cutoff={cutoff} switch={switch} rfa={rfa} skin={skin} bonds={len(bonds)}"
     return ok, desc + f" | max|dF| {err:.2e} (tol {tol:.1e}, max|F| {fmax:.1f})"
 
 
@@ -134,5 +177,7 @@ if __name__ == "__main__":
         if not ok:
             bad += 1
             print("FAIL", desc, flush=True)
+        elif os.environ.get("VERBOSE") == "1":
+            print("ok  ", desc, flush=True)
     print(f"{ncases - bad} of {ncases} cases passed")
     sys.exit(1 if bad else 0)

@@ -420,3 +420,18 @@ def test_differential_fuzz_far_images_strict(request, monkeypatch):
         if not ok:
             bad.append(desc)
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("build", ["default", "round2"])
+def test_differential_fuzz_bonded_terms(request, monkeypatch, build):
+    """The fuzzer with random angles, multi-term dihedrals (cosine series or the all-periods-zero harmonic form), impropers
+    and scaled 1-4 pairs over random atom tuples, periodic and not, several replicas."""
+    request.getfixturevalue("hostsim" if build == "default" else "hostsim_r2")
+    monkeypatch.setenv("BONDED", "1")
+    fuzz = _fuzz_module()
+    bad = []
+    for seed in range(3000, 3012):
+        ok, desc = fuzz.one_case(seed)
+        if not ok:
+            bad.append(desc)
+    assert not bad, "\n".join(bad)
