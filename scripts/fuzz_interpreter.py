@@ -4,6 +4,10 @@ switching / reaction field / cutoff, several replicas with different configurati
 (the real host path) on the interpreter build.  Pairs must be bit-exact, forces within the parity tolerance.
 
     python scripts/fuzz_interpreter.py [ncases] [first_seed] [variant-tag]     # e.g. 200 0 _r2
+
+Environment switches (each leaves the default sequence of cases unchanged): BONDED=1 random angles / dihedrals / impropers /
+1-4 pairs; FAR=<k> atoms up to k boxes away (default 1); STRICT=1 plain 1e-4 yardstick; REPBOX=1 every replica in its own box;
+NOCUT=1 periodic boxes without a cutoff; VERBOSE=1 print passing cases too.
 """
 import os
 import sys
@@ -42,11 +46,21 @@ def one_case(seed):
     has_cut = periodic or rng.random() < 0.6
     cutoff = float(rng.uniform(3.5, 9.0)) if has_cut else None
     L = rng.uniform(2.05 * (cutoff or 5.0), 2.05 * (cutoff or 5.0) + 25.0, size=3) if periodic else np.zeros(3)
+    if os.environ.get("NOCUT") == "1":  # periodic boxes without a cutoff: every pair at its minimum image
+        cutoff = None
     extent = L if periodic else np.full(3, rng.uniform(8.0, 30.0))
     n = max(2, min(n, int(np.prod(extent) / 80.0)))  # room for the minimum distance below
     # positions: minimum distance 2.6 A (contacts down to 0.7 sigma) inside the extent, then some atoms moved whole box lengths away
     pos = np.zeros((nrep, n, 3))
+    # REPBOX=1 in the environment: every replica in its own box (up to 15 % longer per axis; own generator, so that the
+    # default sequence of cases does not move)
+    Ls = np.tile(L, (nrep, 1))
+    if periodic and os.environ.get("REPBOX") == "1":
+        Ls[1:] *= 1.0 + 0.15 * np.random.default_rng(seed + 10**6).random((nrep - 1, 3))
     for r in range(nrep):
+        L = Ls[r]
+        if periodic:
+            extent = L
         pts = []
         while len(pts) < n:
             p = rng.uniform(0, extent)
@@ -127,8 +141,10 @@ def one_case(seed):
     f = Forces(params(torch.float32), terms=terms, skin=skin, **cfg)
     p32 = torch.tensor(pos, dtype=torch.float32)
     box = torch.zeros(nrep, 3, 3)
-    for k in range(3):
-        box[:, k, k] = float(L[k])
+    for r in range(nrep):
+        for k in range(3):
+            box[r, k, k] = float(Ls[r, k])
+    L = Ls[0]
     F = torch.zeros_like(p32)
     E = f.compute(p32, box, F, returnDetails=True)
     of = refmd.OracleForces(params(torch.float64), terms, decision_dtype=torch.float32, **cfg)

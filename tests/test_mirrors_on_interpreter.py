@@ -435,3 +435,19 @@ def test_differential_fuzz_bonded_terms(request, monkeypatch, build):
         if not ok:
             bad.append(desc)
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("env", [{"REPBOX": "1", "BONDED": "1"}, {"NOCUT": "1", "REPBOX": "1", "FAR": "3"}], ids=["replica-boxes", "periodic-no-cutoff"])
+def test_differential_fuzz_box_variants(request, monkeypatch, env):
+    """Every replica in its own box (own cell grid per replica), and periodic boxes without a cutoff (every pair at its
+    minimum image: the guarded minimum-image variant of the pair kernel over the all-pairs list)."""
+    request.getfixturevalue("hostsim")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fuzz = _fuzz_module()
+    bad = []
+    for seed in range(4000, 4010):
+        ok, desc = fuzz.one_case(seed)
+        if not ok:
+            bad.append(desc)
+    assert not bad, "\n".join(bad)
