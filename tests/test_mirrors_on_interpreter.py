@@ -95,6 +95,12 @@ def test_wrapper_wrap(hostsim, name):
     getattr(W.test_gpu_wrap_matches_reference_golden, "__wrapped__", W.test_gpu_wrap_matches_reference_golden)(name)
 
 
+def test_wrapper_wrap_random_topologies(hostsim):
+    import test_wrapper as W
+
+    W.test_gpu_wrap_random_topologies()
+
+
 def test_autograd_path(hostsim):
     import test_autograd_path as A
 

@@ -94,3 +94,53 @@ def test_gpu_wrap_matches_reference_golden(name):
     p = torch.tensor(pos, device=DEV)
     w.wrap(p, torch.tensor(box, device=DEV))
     assert np.array_equal(p.cpu().numpy(), after)
+
+
+def random_wrap_case(seed):
+    """Random bond graph (chains, branched groups, lone atoms), one to three replicas each in its own box, atoms up to four
+    boxes outside; returns (natoms, bonds, pos, box, oracle result)."""
+    rng = np.random.default_rng(seed)
+    natoms = int(rng.integers(1, 200))
+    nb = int(rng.integers(0, natoms))
+    bonds = None
+    if nb and natoms > 1:
+        a = rng.integers(0, natoms - 1, nb)
+        b = np.minimum(natoms - 1, a + rng.integers(1, 4, nb))  # short-range partners: groups of a few to a few dozen atoms
+        bonds = np.stack([a, b], 1)
+    nrep = int(rng.integers(1, 4))
+    box = np.zeros((nrep, 3, 3), np.float32)
+    for r in range(nrep):
+        box[r][np.eye(3, dtype=bool)] = rng.uniform(10.0, 40.0, 3)
+    diag = box[:, np.eye(3, dtype=bool)]
+    pos = (rng.uniform(-3.0, 4.0, (nrep, natoms, 3)) * diag[:, None, :]).astype(np.float32)
+    groups, single = refmd.molecule_groups(natoms, bonds)
+    want = torch.tensor(pos.copy())
+    refmd.wrap_positions(want, torch.tensor(box), groups, single)
+    return natoms, bonds, pos, box, want.numpy()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_kernel_arithmetic_on_host_matches_oracle_on_random_topologies(seed):
+    """The kernel's arithmetic (hostcheck build of csrc/wrap.cuh) against the oracle on random_wrap_case, bit for bit."""
+    from torchmd_b200.wrapper import Wrapper
+
+    hc = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so"))
+    natoms, bonds, pos, box, want = random_wrap_case(seed)
+    w = Wrapper(natoms, bonds, "cpu")
+    p = np.ascontiguousarray(pos).copy()
+    hc.hc_wrap(natoms, len(w._ptr) - 1, w._ptr.ctypes.data_as(C.c_void_p), w._atoms.ctypes.data_as(C.c_void_p),
+               p.shape[0], p.ctypes.data_as(C.c_void_p), np.ascontiguousarray(box).ctypes.data_as(C.c_void_p))
+    assert np.array_equal(p, want), f"max diff {np.abs(p - want).max()}"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
+                    reason="wrap kernel: host-checked, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
+def test_gpu_wrap_random_topologies():
+    from torchmd_b200.wrapper import Wrapper
+
+    for seed in range(24):
+        natoms, bonds, pos, box, want = random_wrap_case(seed)
+        p = torch.tensor(pos, device=DEV)
+        Wrapper(natoms, bonds, DEV).wrap(p, torch.tensor(box, device=DEV))
+        assert np.array_equal(p.cpu().numpy(), want), f"seed {seed}: max diff {np.abs(p.cpu().numpy() - want).max()}"
