@@ -457,3 +457,37 @@ def test_differential_fuzz_box_variants(request, monkeypatch, env):
         if not ok:
             bad.append(desc)
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("n,periodic,cutoff,coords,npairs", [
+    (1, True, 9.0, [[1.0, 2.0, 3.0]], 0),  # a single atom: empty list, zero force (the force buffer is overwritten)
+    (1, False, None, [[1.0, 2.0, 3.0]], 0),
+    (2, True, 9.0, [[1.0, 2.0, 3.0], [20.0, 2.0, 3.0]], 1),  # the only pair is across the boundary
+    (2, True, 9.0, [[1.0, 2.0, 3.0], [12.0, 14.0, 3.0]], 0),  # no pair inside the cutoff
+    (2, False, None, [[1.0, 2.0, 3.0], [4.0, 2.0, 3.0]], 1),
+    (3, False, 4.0, [[0.0, 0.0, 0.0], [100.0, 0.0, 0.0], [0.0, 300.0, 0.0]], 0),  # sparse, no box: empty cells everywhere
+])
+def test_smallest_systems(hostsim, n, periodic, cutoff, coords, npairs):
+    from oracle import refmd
+    from torchmd_b200 import Forces
+    from torchmd_b200.parameters import TopologyParameters
+
+    def par(prec):
+        return TopologyParameters(atom_types=np.zeros(n, int), type_sigma=[3.0], type_epsilon=[0.1], charges=np.full(n, 0.3, np.float32),
+                                  masses=np.full(n, 12.0, np.float32), precision=prec, device="cpu")
+
+    cfg = dict(cutoff=cutoff, rfa=cutoff is not None)
+    terms = ["lj", "electrostatics"]
+    f = Forces(par(torch.float32), terms=terms, **cfg)
+    p = torch.tensor(coords, dtype=torch.float32)[None]
+    box = torch.zeros(1, 3, 3)
+    if periodic:
+        box[0] = torch.eye(3) * 25.0
+    F = torch.full_like(p, 3.0)
+    E = f.compute(p, box, F, returnDetails=True)
+    F64 = torch.zeros(1, n, 3, dtype=torch.float64)
+    E64 = refmd.OracleForces(par(torch.float64), terms, decision_dtype=torch.float32, **cfg).compute(p.double(), box.double(), F64)
+    assert tuple(f.neighbour_pairs(p, box).shape) == (npairs, 2)
+    assert float((F.double() - F64).abs().max()) < 1e-5
+    for k in terms:
+        assert abs(E[0][k] - E64[0][k]) < 1e-5
