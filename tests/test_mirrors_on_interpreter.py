@@ -491,3 +491,44 @@ def test_smallest_systems(hostsim, n, periodic, cutoff, coords, npairs):
     assert float((F.double() - F64).abs().max()) < 1e-5
     for k in terms:
         assert abs(E[0][k] - E64[0][k]) < 1e-5
+
+
+def test_md_steps_two_replicas_in_different_boxes(hostsim):
+    """Fused MD steps with two replicas that differ in configuration AND box (own cell grid, own rebuild moments; thin
+    skin so that lists are rebuilt inside the run): positions and velocities after 20 NVE steps against the oracle's
+    integrator run in fp64 on the reference's fp32 in/out decisions."""
+    from conftest import golden_cfg, load_golden, params_from_golden
+    from oracle import refmd
+    from torchmd_b200 import Forces, Integrator, System
+
+    g, t = load_golden("water291_rf_switch"), load_golden("water291_traj")
+    terms = [str(x) for x in g["terms"]]
+    cfg = golden_cfg(g)
+    n = len(g["coords"])
+    L0 = np.asarray(g["box"], np.float64).reshape(-1)[:3]
+    scale = np.array([1.0, 1.04])
+    coords = np.stack([g["coords"].astype(np.float64) * s for s in scale])  # replica 1: the same waters 4 % further apart
+    system = System(n, 2, torch.float32, "cpu")
+    system.pos[:] = torch.tensor(coords, dtype=torch.float32)
+    for r in range(2):
+        system.box[r] = torch.diag(torch.tensor(L0 * scale[r], dtype=torch.float32))
+    system.set_velocities(torch.tensor(t["vel0_f32"]))
+    forces = Forces(params_from_golden(g, device="cpu"), terms=terms, skin=0.3, **cfg)
+    forces.compute(system.pos, system.box, system.forces)
+    pos0, vel0, box = system.pos.clone(), system.vel.clone(), system.box.clone()
+    integ = Integrator(system, forces, 1.0, "cpu")
+    ek, ep, T = integ.step(niter=20)
+    assert forces.stats()["rebuilds"] >= 2
+
+    o = refmd.OracleForces(params_from_golden(g, precision=torch.float64), terms, decision_dtype=torch.float32, **cfg)
+    p64, v64, F64 = pos0.double(), vel0.double(), torch.zeros(2, n, 3, dtype=torch.float64)
+    o.compute(p64, box.double(), F64)
+    oi = refmd.OracleIntegrator(p64, v64, box.double(), F64, params_from_golden(g, precision=torch.float64).masses.double(),
+                                lambda p, b, f: o.compute(p, b, f), 1.0)
+    oek, oep, oT = oi.step(niter=20)
+    dp = float((system.pos.double() - p64).abs().max())
+    dv = float((system.vel.double() - v64).abs().max())
+    print(f"two boxes, 20 NVE steps: dpos {dp:.2e} A, dvel {dv:.2e}")
+    assert dp < 1e-4 and dv < 5e-4
+    np.testing.assert_allclose(ek, oek, rtol=2e-4)
+    assert abs(float(T[0]) - float(T[1])) > 1e-3  # the replicas really ran different trajectories
