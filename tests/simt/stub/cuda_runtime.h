@@ -22,6 +22,7 @@ inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct dim3 {
   unsigned x, y, z;
@@ -64,6 +65,7 @@ inline void __nanosleep(unsigned) { simt::yield(); }
 inline long long clock64() { return simt::fake_clock(); }
 template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }  // fibers of one OS thread: no races
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 
 // ---- runtime: "device" memory is host memory, streams execute immediately ----------------------

@@ -151,8 +151,6 @@ def test_external_potential_in_both_force_modes(cpu_forces):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                    reason="autograd path on the kernels: plumbing checked on CPU, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 def test_gpu_energy_backward_and_vmap():
     from torchmd_b200 import Forces
 
@@ -237,8 +235,6 @@ def test_kernel_switch_term_in_exact_gradient_form():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                    reason="exact-gradient force convention: host-checked, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 def test_gpu_autograd_mode_returns_the_reference_autograd_forces():
     from torchmd_b200 import Forces
 

@@ -106,14 +106,12 @@ def test_golden_neighbour_pairs_bit_exact(name):
     assert hashlib.sha256(np.ascontiguousarray(pairs.astype(np.int32)).tobytes()).hexdigest() == str(g["pairs_sha256_f32"])
 
 
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1", reason="new parity cases: not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 @pytest.mark.parametrize("name", NEW_CASES)
 def test_new_reference_fixtures(name):
     test_golden_forces_energies(name)
     test_golden_neighbour_pairs_bit_exact(name)
 
 
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1", reason="added after round 1's GPU time was spent (green on the interpreter build)")
 def test_molecules_several_boxes_away_meet_the_plain_yardstick():
     """Whole waters moved up to seven box lengths away (image counts for which fl(L * count) is inexact): the same pair set
     as the fp32 reference, and forces within the plain 1e-4 yardstick of the fp64 values on that pair set -- the float

@@ -1,10 +1,8 @@
 """Parity of the fixed-point pair kernel (k_pair_fx, TMD_B200_FX=1) with the oracle and
 with the default float kernel.
 
-STATUS: the kernel was written after the round's GPU budget was spent.  Its arithmetic
-is checked on the host (tests/test_physics_host.py, hostcheck shim) but it has not run on
-a B200 yet, so it is opt-in in the library and these tests only run with
-TMD_B200_VALIDATE=1 (scripts/gpu_validate_new.sh).  Same tolerances as
+STATUS: first run on a B200 in round 2 (26 passed; profiles/r02_validation_call1.txt); part of
+the standing GPU suite since.  Same tolerances as
 test_gpu_forces.py: pairs bit-exact, forces < 1e-4 kcal/mol/A against the fp64 oracle on
 the fp32 pair set.
 """
@@ -19,8 +17,6 @@ from oracle import refmd
 
 pytestmark = [
     pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                       reason="fixed-point pair kernel: not yet validated on a B200 (set TMD_B200_VALIDATE=1)"),
 ]
 DEV = "cuda:0"
 PERIODIC_CASES = ["water291_rf_switch", "water291_plain", "argon100_cut", "water999_eq", "chain_amber_periodic",

@@ -3,7 +3,7 @@ single rank: the double-buffered positions, the push kernel, the flag wait and t
 replay per parity must reproduce the plain Integrator bit for bit.  Multi-rank:
 scripts/p2p_check.py under torchrun (scripts/gpu_validate_p2p.sh).
 
-STATUS: written after the round's GPU budget was spent; runs only with TMD_B200_VALIDATE=1.
+STATUS: first run on a B200 in round 2 (green); part of the standing GPU suite since.
 """
 import os
 
@@ -14,8 +14,6 @@ import torch.distributed as dist
 
 pytestmark = [
     pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                       reason="peer-to-peer exchange: not yet validated on a B200 (set TMD_B200_VALIDATE=1)"),
 ]
 DEV = "cuda:0"
 # (tests/test_mirrors_on_interpreter.py runs this test on the host interpreter with a smaller system)

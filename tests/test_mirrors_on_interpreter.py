@@ -317,7 +317,7 @@ def test_ab_bench_script_dry_run(hostsim, monkeypatch, capsys):
     monkeypatch.setattr(mod, "DEVICE", "cpu")
     monkeypatch.setattr(bench, "N_WATERS", 64)
     monkeypatch.setattr(bench, "CFG", dict(bench.CFG, cutoff=5.0, switch_dist=4.0))
-    mod.main(["default|SKIN=0.3", "packed+overlap+fused|TMD_B200_FX=2,TMD_B200_OVERLAP=1,TMD_B200_FUSEPREP=1,SKIN=0.3", "--steps", "6", "--equil", "10", "--warmup", "2"])
+    mod.main(["default|TMD_B200_FX=0,TMD_B200_OVERLAP=0,TMD_B200_FUSEPREP=0,SKIN=0.3", "packed+overlap+fused|TMD_B200_FX=2,TMD_B200_OVERLAP=1,TMD_B200_FUSEPREP=1,SKIN=0.3", "--steps", "6", "--equil", "10", "--warmup", "2"])
     out = capsys.readouterr().out
     rows = [l for l in out.splitlines() if l.startswith(("default", "packed"))]
     assert len(rows) == 2 and "failed" not in out, out

@@ -54,8 +54,6 @@ def test_log_writer_layout(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                    reason="asynchronous frame sink: checked with CPU tensors, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 def test_frame_sink_on_cuda(tmp_path):
     n, nrep = 2000, 2
     dev = "cuda:0"

@@ -82,8 +82,6 @@ def test_wrap_index_branch_leaves_caller_tensor_alone():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                    reason="wrap kernel: host-checked, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 @pytest.mark.parametrize("name", CASES)
 def test_gpu_wrap_matches_reference_golden(name):
     from torchmd_b200.wrapper import Wrapper
@@ -134,8 +132,6 @@ def test_kernel_arithmetic_on_host_matches_oracle_on_random_topologies(seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMD_B200_VALIDATE") != "1",
-                    reason="wrap kernel: host-checked, not yet run on a B200 (set TMD_B200_VALIDATE=1)")
 def test_gpu_wrap_random_topologies():
     from torchmd_b200.wrapper import Wrapper
 

@@ -127,6 +127,13 @@ k_bonded(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, cons
       o[0] = f.x;
       o[1] = f.y;
       o[2] = f.z;
+    } else if (S.cl.on) {
+      // cluster path: the pair forces sit in slot order; this kernel brings them home and adds its own sums
+      const float4 pf = S.cl.f[(size_t)r * (S.cl.slots + 1) + S.cl.inv[base + a]];
+      float* out = forces + (base + a) * 3;
+      out[0] = (float)((double)pf.x + f.x);
+      out[1] = (float)((double)pf.y + f.y);
+      out[2] = (float)((double)pf.z + f.z);
     } else if (T.atom_ptr[a + 1] > T.atom_ptr[a]) {
       float* out = forces + (base + a) * 3;
       out[0] = (float)((double)out[0] + f.x);

@@ -38,7 +38,31 @@ enum {
   F_FARPOS = 5,    // a position was further than 2000 box lengths from the origin
   F_PMAX = 6,      // bits of the largest |coordinate| seen since the box was set (+inf if one was not finite)
   F_PEERWAIT = 7,  // (replica 0) the wait for the peers' position stores timed out
-  F_COUNT = 8
+  F_CLFAIL = 8,    // cluster path: a cluster grew past the size the single image count per (cluster, partner) allows,
+                   // or an exclusion set / segment table overflowed -> the host falls back to the full Verlet rows
+  F_CLMAXA = 9,    // cluster path: most masked / plain entries any cluster wanted at the last builds
+  F_CLMAXB = 10,
+  F_COUNT = 12
+};
+
+// Cluster half-list path (cluster.cuh).  Slots: atoms sorted by cell row and x, rows padded to whole clusters.
+struct ClusterState {
+  int on;              // cluster path in use
+  int slots;           // slot capacity per replica (a multiple of the cluster size); record `slots` is the dummy
+  int nclusters_cap;   // slots / cluster size
+  int ecap, mcap;      // plain / masked entries reserved per cluster (multiples of 32)
+  float max_extent;    // largest bounding-box edge a cluster may have (periodic boxes)
+  float4* xq;          // [rep*(slots+1) + s] raw x, y, z + scaled charge (every step)
+  float4* f;           // [rep*(slots+1) + s] force accumulators (zeroed every step)
+  float4* xw;          // coordinates folded into the box at the last build; .w = atom type (bits)
+  int4* xf;            // fixed-point records (physics.cuh, fx_encode) of a periodic box: X, Y, Z + charge bits (every step)
+  int* perm;           // slot -> atom (-1: padding)
+  int* tmp;            // scratch of the sort
+  int* inv;            // [rep*natoms + i] atom -> slot
+  int* nslots;         // [rep] slots in use after the last build
+  int2* meta;          // [rep*nclusters_cap + c] (masked entries | mask of real atoms << 24, plain entries), counts padded to 32
+  unsigned* entries;   // [(rep*nclusters_cap + c) * (mcap + ecap)] masked region, then plain region
+  unsigned char* masks;  // [(rep*nclusters_cap + c) * mcap] which atoms of the cluster a masked entry interacts with
 };
 
 struct DeviceState {
@@ -81,6 +105,7 @@ struct DeviceState {
   float rlist;           // cutoff + skin
   float trigger2;        // (skin/2 - margin)^2 ; +inf without cutoff
   PairParams pp;
+  ClusterState cl;
 };
 
 struct BondedSet {
@@ -122,6 +147,7 @@ struct tmd_ctx {
   int last_pair_kernel = 0;          // tmd_pair_kernel(): 0 float (k_pair), 1 k_pair_fx, 2 k_pair_fx2, 3 k_pair2_open
   bool fx_packed = false;            // TMD_B200_FX=2: k_pair_fx2 (packed fp32x2 arithmetic) where it applies
   int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
+  bool cluster_failed = false;       // the cluster path reported F_CLFAIL once: this context stays on the full rows
   // peer-to-peer position exchange (tmd_dd_*): one cudaMalloc holding [pos0 | pos1 | flags | sync]
   int dd_rank = -1, dd_world = 0;
   bool dd_connected = false;

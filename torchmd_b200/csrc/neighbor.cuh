@@ -90,6 +90,21 @@ __device__ __forceinline__ void prepare_atom(const DeviceState& S, int r, int i,
     if (!(fabsf(x) < 2000.f * g->L[0]) || !(fabsf(y) < 2000.f * g->L[1]) || !(fabsf(z) < 2000.f * g->L[2]))
       fl[F_FARPOS] = 1;
   }
+  if (S.cl.on) {  // cluster path (cluster.cuh): slot record refreshed, force accumulator of the slot cleared
+    const size_t s = (size_t)r * (S.cl.slots + 1) + S.cl.inv[a];
+    S.cl.xq[s] = make_float4(x, y, z, S.q[i]);
+    S.cl.f[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (S.cl.xf) {  // periodic box: fixed-point record + largest |coordinate| for the decision band
+      const Grid* g = S.grid + r;
+      S.cl.xf[s] = make_int4(fx_encode(x, g->fx_inv[0]), fx_encode(y, g->fx_inv[1]), fx_encode(z, g->fx_inv[2]), __float_as_int(S.q[i]));
+      float m = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+      if (!(fabsf(x) < INFINITY) || !(fabsf(y) < INFINITY) || !(fabsf(z) < INFINITY)) m = INFINITY;
+      const unsigned am = __activemask();
+      const int mb = __reduce_max_sync(am, __float_as_int(m));
+      if ((threadIdx.x & 31) == __ffs(am) - 1 && mb > fl[F_PMAX]) atomicMax(fl + F_PMAX, mb);
+    }
+    return;
+  }
   const int k = S.inv[a];
   S.xq_s[(size_t)r * (S.natoms + 1) + k] = make_float4(x, y, z, S.q[i]);
   if (S.xf_s) {  // fixed-point records of the periodic pair kernel (physics.cuh, fx_encode)
@@ -366,9 +381,9 @@ struct Run {
 // BT_CULL=1: every 32-candidate chunk of the tile gets a bounding box; an atom only walks
 // the chunks whose box comes within the list radius (the sweep volume is ~5x the list
 // sphere, so most chunks cannot contribute).  Skipped chunks hold no accepted candidate,
-// so the rows are identical to the unculled build.  Off until validated on a B200.
+// so the rows are identical to the unculled build (GPU suite green with it on a B200, round 2).
 #ifndef BT_CULL
-#define BT_CULL 0
+#define BT_CULL 1
 #endif
 constexpr int BT_CHUNKS = BT_TILE / 32;
 static_assert(BT_CHUNKS <= 64, "the per-atom chunk mask is 64 bits");
@@ -568,7 +583,7 @@ __device__ __forceinline__ void build_process_tile(const DeviceState& S, const G
 // list radius, so visiting it adds nothing to that atom's row.  Rows come out in the same order as in the one-atom
 // loop.  Off until measured on a B200.
 #ifndef BT_PAIRED
-#define BT_PAIRED 0
+#define BT_PAIRED 1
 #endif
 #if BT_CULL && BT_PAIRED
 struct BuildAtom {

@@ -338,7 +338,7 @@ k_pair_fx(DeviceState S, float* __restrict__ forces, double* __restrict__ energi
 // operation costs one issue slot for two results.  Decisions, band handling and list layout are
 // those of k_pair_fx; a partner that is not taken contributes through a zeroed coefficient.
 #ifndef PAIR_FX2_MINBLOCKS
-#define PAIR_FX2_MINBLOCKS 4
+#define PAIR_FX2_MINBLOCKS 4  // measured on B200 (profiles/r02_validation_call1.txt): 5 CTAs/SM 136.9 us with spills in the loop, 4 CTAs/SM 138.8 us without
 #endif
 #ifndef PAIR_FX2_UNROLL
 #define PAIR_FX2_UNROLL 1  // packed evaluations (pairs of list entries) per lane and loop iteration: 1 or 2

@@ -72,6 +72,44 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+// ---- bulk (TMA) copies global -> shared with an mbarrier, fire-and-forget vector reductions ----
+// One elected lane announces the bytes and starts the copy; the warp then waits on the barrier's phase.
+__device__ __forceinline__ void mbar_init(smem_addr bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(smem_addr bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// size and both addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(smem_addr dst, const void* src, unsigned bytes, smem_addr bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(smem_addr bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(smem_addr a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+// f[0..2] += (x, y, z) as one 16-byte reduction at L2 (the fourth component adds zero)
+__device__ __forceinline__ void red_add_f32x4(float4* p, float x, float y, float z) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
 #else
 #define TMD_PIN_R(x) ((void)0)
 #define TMD_PIN_F(x) ((void)0)
@@ -101,6 +139,18 @@ inline unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long lon
 inline void stg_u32(unsigned long long addr, int v) { *reinterpret_cast<int*>(addr) = v; }
 inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+
+inline void mbar_init(smem_addr, unsigned) {}
+inline void fence_mbar_init() {}
+inline void mbar_expect_tx(smem_addr, unsigned) {}
+inline void bulk_g2s(smem_addr dst, const void* src, unsigned bytes, smem_addr) { memcpy(const_cast<char*>(dst), src, bytes); }
+inline void mbar_wait(smem_addr, unsigned) {}  // (the host copy above is synchronous)
+inline unsigned lds_u32(smem_addr a) { return *reinterpret_cast<const unsigned*>(a); }
+inline void red_add_f32x4(float4* p, float x, float y, float z) {  // (interpreter threads run one at a time)
+  p->x += x;
+  p->y += y;
+  p->z += z;
+}
 #endif
 
 }  // namespace tmd

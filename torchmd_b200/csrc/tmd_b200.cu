@@ -19,6 +19,7 @@
 #include "wrap.cuh"
 #include "neighbor.cuh"
 #include "pair.cuh"
+#include "cluster.cuh"
 
 using namespace tmd;
 
@@ -46,16 +47,17 @@ int fail(int code, const std::string& msg) {
       return fail(TMD_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
-// Run-time switches: the environment decides ("0" off, "1"/"2" on), otherwise the default below.  Everything is off
-// until it has run on a B200; flipping a default is this one line (or -DTMD_DEFAULT_<NAME>=... for an A/B build).
+// Run-time switches: the environment decides ("0" off, "1"/"2" on), otherwise the default below
+// (-DTMD_DEFAULT_<NAME>=... for an A/B build).  FX=2, OVERLAP and FUSEPREP went through the whole GPU suite and the
+// A/B benches on a B200 in round 2 (profiles/r02_validation_call1.txt, r02_validation_call2.txt) and are on.
 #ifndef TMD_DEFAULT_FX
-#define TMD_DEFAULT_FX 0        // TMD_B200_FX: 1 fixed-point pair kernel, 2 + packed fp32x2 arithmetic
+#define TMD_DEFAULT_FX 2        // TMD_B200_FX: 1 fixed-point pair kernel, 2 + packed fp32x2 arithmetic
 #endif
 #ifndef TMD_DEFAULT_COOP
 #define TMD_DEFAULT_COOP 0      // TMD_B200_COOP: rebuild as one cooperative launch
 #endif
 #ifndef TMD_DEFAULT_OVERLAP
-#define TMD_DEFAULT_OVERLAP 0   // TMD_B200_OVERLAP: bonded kernel on a second stream
+#define TMD_DEFAULT_OVERLAP 1   // TMD_B200_OVERLAP: bonded kernel on a second stream
 #endif
 #ifndef TMD_DEFAULT_COND
 #define TMD_DEFAULT_COND 0      // TMD_B200_COND: rebuild as a conditional node when captured (needs TMD_COND_NODE)
@@ -64,7 +66,10 @@ int fail(int code, const std::string& msg) {
 #define TMD_DEFAULT_GRAPH 0     // TMD_B200_GRAPH: tmd_md_steps replays a captured step
 #endif
 #ifndef TMD_DEFAULT_FUSEPREP
-#define TMD_DEFAULT_FUSEPREP 0  // TMD_B200_FUSEPREP: integrate + prepare in one kernel, bonded fold in the second kick
+#define TMD_DEFAULT_FUSEPREP 1  // TMD_B200_FUSEPREP: integrate + prepare in one kernel, bonded fold in the second kick
+#endif
+#ifndef TMD_DEFAULT_CLUSTER
+#define TMD_DEFAULT_CLUSTER 1   // TMD_B200_CLUSTER: cluster half-list pair path (cluster.cuh) where it applies
 #endif
 static int env_switch(const char* name, int def) {
   const char* e = getenv(name);
@@ -85,6 +90,16 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t
   else run();
 #else
   kernel<<<grid, block, 0, st>>>(std::forward<Args>(args)...);
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+#if defined(TMD_SIMT_HOST)
+  (void)smem;
+  launch(kernel, grid, block, st, std::forward<Args>(args)...);
+#else
+  kernel<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
 #endif
 }
 
@@ -159,6 +174,10 @@ struct CtxPriv {
   cudaGraphConditionalHandle prepared_cond = 0; // and this handle already handed to the kernel
   bool dirty = true;
   size_t nbr_entries = 0;
+  // cluster path: owned buffers behind ctx->d.cl
+  std::vector<void*> cl_bufs;
+  int cl_blocks = 0;        // CTAs of k_cpair per replica
+  size_t cl_smem = 0;       // its dynamic shared memory
   std::vector<cudaEvent_t> ev;  // pair-kernel timing samples (begin,end interleaved)
   int ev_used = 0;
   bool profiling = false;
@@ -256,6 +275,7 @@ int tmd_destroy(tmd_ctx* ctx) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   dd_release(ctx);
+  for (void* b : priv(ctx).cl_bufs) cudaFree(b);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
   for (int k = 0; k < 2; ++k) {
     if (priv(ctx).exec[k]) cudaGraphExecDestroy(priv(ctx).exec[k]);
@@ -442,6 +462,29 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   d.rlist2 = has_cut ? (float)(rl * rl) : INFINITY;
   d.trigger2 = has_cut ? (float)(0.25 * ctx->skin * ctx->skin) : INFINITY;
 
+  // Cluster half-list path (cluster.cuh): a cutoff, pair terms out of {lj, electrostatics}, explicit-force
+  // convention, few atom types, the whole system on this context; in a periodic box additionally every pair a list
+  // can hold must have ONE image within reach (size condition below).  Otherwise: full Verlet rows.
+  ClusterState& cl = d.cl;
+  const double cl_extent = 8.0;  // a periodic box must leave room for clusters at least this long (A)
+  bool use_cluster = env_switch("TMD_B200_CLUSTER", TMD_DEFAULT_CLUSTER) == 1 && !ctx->cluster_failed && has_cut &&
+                     ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0 && !ctx->exact_gradient &&
+                     d.ntypes <= CL_MAXT && d.own_all && N < (1 << 24) - 4096 * CL;
+  double cl_max_extent = INFINITY;
+  if (use_cluster && ctx->periodic) {
+    // pair (i, j) of a list: |x_i - x_j| <= rl + (cluster extent) + skin along every axis, and that must stay below
+    // 0.45 L for the image count of the pair to be the one taken from the cluster's centre (cluster.cuh)
+    float lmin = INFINITY;
+    for (int e = 0; e < R * 3; ++e) lmin = std::min(lmin, ctx->box_host[e]);
+    cl_max_extent = 0.45 * (double)lmin - rl - ctx->skin - 0.01;
+    use_cluster = cl_max_extent >= cl_extent;
+  }
+  {
+    double cellw = 4.0;
+    if (const char* e = getenv("TMD_B200_CELLW")) cellw = std::max(1.0, atof(e));
+    d.nsub = use_cluster ? std::max(1, (int)floor(rl / cellw + 0.5)) : 2;
+  }
+
   // cell grid per replica
   std::vector<Grid> grids(R);
   long long max_cells = 1;
@@ -495,11 +538,13 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   {
     const int fx = env_switch("TMD_B200_FX", TMD_DEFAULT_FX);
     ctx->fx_packed = fx == 2;
-    if ((fx == 1 || fx == 2) && ctx->safe_image && ctx->pair_mask) {
-      const size_t n = (size_t)R * N + R;
-      if ((rc = device_alloc(&ctx->xf_buf, n))) return rc;
-      TMD_CUDA(cudaMemset(ctx->xf_buf, 0, n * sizeof(int4)));
-      d.xf_s = ctx->xf_buf;
+    if ((((fx == 1 || fx == 2) && ctx->safe_image) || (use_cluster && ctx->periodic)) && ctx->pair_mask) {
+      if (!use_cluster) {
+        const size_t n = (size_t)R * N + R;
+        if ((rc = device_alloc(&ctx->xf_buf, n))) return rc;
+        TMD_CUDA(cudaMemset(ctx->xf_buf, 0, n * sizeof(int4)));
+        d.xf_s = ctx->xf_buf;
+      }
       const double rmax = ctx->cutoff + 2.0 * ctx->skin + 2.0 * margin;  // no listed pair is further apart
       for (int r = 0; r < R; ++r) {
         Grid& g = grids[r];
@@ -531,7 +576,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     if (N >= (1 << 24) || d.ntypes > 128)
       return fail(TMD_ERR_UNSUPPORTED, "neighbour entries pack a 24-bit atom index and a 7-bit atom type: "
                                        "at most 16,777,216 atoms per replica and 128 atom types");
-    const size_t need = (size_t)R * N * d.row_cap + 256;  // slack: the pair loop prefetches past a row's end
+    const size_t need = use_cluster ? 256 : (size_t)R * N * d.row_cap + 256;  // slack: the pair loop prefetches past a row's end
     if (need * sizeof(int) > (size_t)96 << 30)
       return fail(TMD_ERR_UNSUPPORTED, "neighbour list would exceed 96 GiB (no cutoff on a large system?)");
     if (need != priv(ctx).nbr_entries) {
@@ -542,6 +587,74 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     if ((rc = device_alloc(&d.cell_start, (size_t)R * (max_cells + 1)))) return rc;
     TMD_CUDA(cudaMemset(d.cell_count, 0, (size_t)R * (max_cells + 1) * sizeof(int)));
     TMD_CUDA(cudaMemset(d.cell_start, 0, (size_t)R * (max_cells + 1) * sizeof(int)));
+  }
+  // cluster path: slot arrays and lists
+  {
+    CtxPriv& pv = priv(ctx);
+    const int keep_ecap = cl.ecap, keep_mcap = cl.mcap;
+    for (void* b : pv.cl_bufs) cudaFree(b);
+    pv.cl_bufs.clear();
+    memset(&cl, 0, sizeof(cl));
+    if (use_cluster) {
+      long long rows = 1;
+      for (int r = 0; r < R; ++r) rows = std::max<long long>(rows, (long long)grids[r].n[1] * grids[r].n[2]);
+      if (!ctx->periodic) rows = 64 * 64;  // the device sizes that grid
+      const long long slots = ((long long)N + rows * (CL - 1) + CL - 1) / CL * CL;
+      cl.on = 1;
+      cl.slots = (int)slots;
+      cl.nclusters_cap = (int)(slots / CL);
+      cl.max_extent = (float)cl_max_extent;
+      // entries per cluster: half of the atoms within rl of a box of about (2.5, w, w) A, with head room
+      const double w = rl / d.nsub, a = 2.5, rho = std::max(max_density, 0.11);
+      const double vol = a * w * w + 2.0 * (a * w + w * w + a * w) * rl + M_PI * (a + 2 * w) * rl * rl + 4.0 / 3.0 * M_PI * rl * rl * rl;
+      long long ecap = (long long)(0.5 * rho * vol * 1.3) + 64;
+      if (const char* e = getenv("TMD_B200_CLUSTER_ECAP")) ecap = std::max(32, atoi(e));  // (tests: start too small, grow)
+      ecap = std::max<long long>(ecap, keep_ecap);
+      ecap = std::min<long long>((ecap + 31) / 32 * 32, ((long long)N + 31) / 32 * 32);
+      cl.ecap = (int)std::max<long long>(ecap, 32);
+      cl.mcap = std::max(64, keep_mcap);
+      auto grab = [&](auto** ptr, size_t n) {
+        void* b = nullptr;
+        if (cudaMalloc(&b, n * sizeof(**ptr)) != cudaSuccess) return false;
+        pv.cl_bufs.push_back(b);
+        *ptr = reinterpret_cast<std::remove_reference_t<decltype(**ptr)>*>(b);
+        return true;
+      };
+      const size_t S1 = (size_t)R * (slots + 1), C1 = (size_t)R * cl.nclusters_cap;
+      const size_t ne = C1 * (size_t)(cl.mcap + cl.ecap);
+      if (ne * 4 > ((size_t)64 << 30)) return fail(TMD_ERR_UNSUPPORTED, "cluster lists would exceed 64 GiB");
+      bool ok = grab(&cl.xq, S1) && grab(&cl.f, S1) && grab(&cl.xw, S1) && (!ctx->periodic || grab(&cl.xf, S1)) &&
+                grab(&cl.perm, S1) && grab(&cl.tmp, S1) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
+                grab(&cl.meta, C1) && grab(&cl.entries, ne + 64) && grab(&cl.masks, C1 * (size_t)cl.mcap + 64);
+      if (!ok) return fail(TMD_ERR_CUDA, "cudaMalloc of the cluster lists failed");
+      TMD_CUDA(cudaMemset(cl.xq, 0, S1 * sizeof(float4)));
+      TMD_CUDA(cudaMemset(cl.f, 0, S1 * sizeof(float4)));
+      if (cl.xf) TMD_CUDA(cudaMemset(cl.xf, 0, S1 * sizeof(int4)));
+      TMD_CUDA(cudaMemset(cl.perm, 0xFF, S1 * sizeof(int)));
+      TMD_CUDA(cudaMemset(cl.nslots, 0, (size_t)R * sizeof(int)));
+      TMD_CUDA(cudaMemset(cl.meta, 0, C1 * sizeof(int2)));
+      {
+        std::vector<int> ident((size_t)R * N);
+        for (int r = 0; r < R; ++r)
+          for (int i = 0; i < N; ++i) ident[(size_t)r * N + i] = i;
+        TMD_CUDA(cudaMemcpy(cl.inv, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      // launch shape of k_cpair: persistent CTAs, as many as fit
+      pv.cl_smem = (size_t)CL_WARPS * 2 * (cl.mcap + cl.ecap) * sizeof(unsigned) + (size_t)CL_WARPS * d.ntypes * CL_H * sizeof(ClTab);
+#if !defined(TMD_SIMT_HOST)
+      if (pv.cl_smem > (size_t)180 * 1024) return fail(TMD_ERR_UNSUPPORTED, "cluster lists too long for the shared-memory staging");
+      int nsm = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+      const void* kernels[4] = {(const void*)k_cpair<false, false>, (const void*)k_cpair<false, true>,
+                                (const void*)k_cpair<true, false>, (const void*)k_cpair<true, true>};
+      for (const void* k : kernels) TMD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pv.cl_smem));
+      TMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cpair<false, true>, CL_WARPS * 32, pv.cl_smem));
+      pv.cl_blocks = std::max(1, std::min(nsm * std::max(per_sm, 1), (cl.nclusters_cap + CL_WARPS - 1) / CL_WARPS));
+#else
+      if (cl.mcap + cl.ecap > CL_SIMT_MAX_ENTRIES || d.ntypes > CL_SIMT_MAX_TYPES) return fail(TMD_ERR_UNSUPPORTED, "interpreter build: cluster list too long");
+      pv.cl_blocks = std::max(1, std::min(16, (cl.nclusters_cap + CL_WARPS - 1) / CL_WARPS));
+#endif
+    }
   }
   TMD_CUDA(cudaMemcpy(d.grid, grids.data(), (size_t)R * sizeof(Grid), cudaMemcpyHostToDevice));
   TMD_CUDA(cudaMemset(d.pos_ref, 0xFF, (size_t)R * N * sizeof(float4)));  // NaN: forces a build
@@ -731,7 +844,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   }
   // fork: the bonded terms need only the positions, so they run on a second stream while the
   // list check and the pair kernel run here; joined by k_add_bonded below
-  const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr;
+  const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr && !d.cl.on;
   if (overlap) {
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaEventRecord(pv.ev_fork, st));
@@ -783,7 +896,27 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       rs = priv(ctx).helper;
       in_body = true;
     }
-    if (ctx->coop_blocks > 0 && !in_body) {
+    if (d.cl.on) {
+      // cluster path: cell binning as before, then the row-padded sort and the cluster lists (cluster.cuh)
+      if (need_bounds) {
+        launch(k_bounds, atoms_grid(ctx, 256), 256, rs, d, pos);
+        TMD_LAUNCHED(ctx, "k_bounds");
+        launch(k_grid, (R + 63) / 64, 64, rs, d);
+        TMD_LAUNCHED(ctx, "k_grid");
+      }
+      launch(k_bin, atoms_grid(ctx, 256), 256, rs, d, pos);
+      TMD_LAUNCHED(ctx, "k_bin");
+      launch(k_cscan, R, 1024, rs, d);
+      TMD_LAUNCHED(ctx, "k_cscan");
+      launch(k_cplace, dim3(std::min((N + 255) / 256, 148 * 8), R), 256, rs, d);
+      TMD_LAUNCHED(ctx, "k_cplace");
+      launch(k_csort, dim3(std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8)), R), 256, rs, d);
+      TMD_LAUNCHED(ctx, "k_csort");
+      launch(k_cfinish_sort, dim3(std::min((d.cl.slots + 256) / 256, 148 * 8), R), 256, rs, d);
+      TMD_LAUNCHED(ctx, "k_cfinish_sort");
+      launch(k_cbuild, dim3(std::max(1, std::min((d.cl.nclusters_cap + CLB_WARPS - 1) / CLB_WARPS, 148 * 16)), R), CLB_WARPS * 32, rs, d);
+      TMD_LAUNCHED(ctx, "k_cbuild");
+    } else if (ctx->coop_blocks > 0 && !in_body) {
       // the whole (gated) rebuild in one cooperative launch
       const float* pos_arg = pos;
       int nb_arg = need_bounds;
@@ -822,7 +955,18 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     CtxPriv& pv = priv(ctx);
     const bool sample = pv.profiling && (size_t)(pv.ev_used + 2) <= pv.ev.size();
     if (sample) TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used], st));
-    launch_pair(ctx, pg, st, forces, energies);
+    if (d.cl.on) {
+      ctx->last_pair_kernel = 4;
+      const SwitchConsts sc = make_switch_consts(d.pp);
+      const dim3 cg(pv.cl_blocks, R);
+      const bool e = energies != nullptr;
+      if (e && ctx->periodic) launch_smem(k_cpair<true, true>, cg, CL_WARPS * 32, pv.cl_smem, st, d, sc, energies);
+      else if (e) launch_smem(k_cpair<true, false>, cg, CL_WARPS * 32, pv.cl_smem, st, d, sc, energies);
+      else if (ctx->periodic) launch_smem(k_cpair<false, true>, cg, CL_WARPS * 32, pv.cl_smem, st, d, sc, energies);
+      else launch_smem(k_cpair<false, false>, cg, CL_WARPS * 32, pv.cl_smem, st, d, sc, energies);
+    } else {
+      launch_pair(ctx, pg, st, forces, energies);
+    }
     TMD_LAUNCHED(ctx, "k_pair");
     if (sample) {
       TMD_CUDA(cudaEventRecord(pv.ev[pv.ev_used + 1], st));
@@ -842,8 +986,12 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_add_bonded");
     }
   } else if (have_bonded) {
+    // (cluster path: this kernel also brings the pair forces home from slot order)
     launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, d, T, ctx->q, pos, forces, energies, nullptr);
     TMD_LAUNCHED(ctx, "k_bonded");
+  } else if (d.cl.on && ctx->pair_mask) {
+    launch(k_cunsort, atoms_grid(ctx, 256), 256, st, d, forces);
+    TMD_LAUNCHED(ctx, "k_cunsort");
   }
   return TMD_OK;
 }
@@ -1056,8 +1204,12 @@ int tmd_export_pairs(tmd_ctx* ctx, const float* pos, int replica, int32_t* pairs
   DeviceGuard guard(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   TMD_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st));
-  launch(k_export_pairs, (ctx->natoms + 3) / 4, 128, st, ctx->d, replica, pairs, (long long)capacity,
-                                                       reinterpret_cast<unsigned long long*>(count));
+  if (ctx->d.cl.on)
+    launch(k_cexport_pairs, (ctx->d.cl.nclusters_cap + 3) / 4, 128, st, ctx->d, replica, pairs, (long long)capacity,
+           reinterpret_cast<unsigned long long*>(count));
+  else
+    launch(k_export_pairs, (ctx->natoms + 3) / 4, 128, st, ctx->d, replica, pairs, (long long)capacity,
+           reinterpret_cast<unsigned long long*>(count));
   TMD_LAUNCHED(ctx, "k_export_pairs");
   return TMD_OK;
 }
@@ -1296,6 +1448,34 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
       return fail(TMD_ERR_UNSUPPORTED,
                   "a position is more than 2000 box lengths from the origin: wrap the coordinates "
                   "(torchmd Wrapper) -- results since the last check are not reliable");
+  if (ctx->d.cl.on) {
+    int maxa = 0, maxb = 0;
+    bool clfail = false;
+    for (int r = 0; r < ctx->nrep; ++r) {
+      maxa = std::max(maxa, fl[r * F_COUNT + F_CLMAXA]);
+      maxb = std::max(maxb, fl[r * F_COUNT + F_CLMAXB]);
+      clfail |= fl[r * F_COUNT + F_CLFAIL] != 0;
+    }
+    if (getenv("TMD_B200_DEBUG")) {
+      fprintf(stderr, "[tmd] cluster flags:");
+      for (int k = 0; k < F_COUNT; ++k) fprintf(stderr, " %d", fl[k]);
+      fprintf(stderr, "  (slots %d, ecap %d, mcap %d)\n", ctx->d.cl.slots, ctx->d.cl.ecap, ctx->d.cl.mcap);
+    }
+    if (clfail) {
+      // a cluster too large for one image count per partner, or an exclusion set / segment table overflow:
+      // this context continues on the full Verlet rows
+      ctx->cluster_failed = true;
+      priv(ctx).dirty = true;
+      return fail(TMD_ERR_OVERFLOW, "cluster lists do not fit this system; switched to full neighbour rows, recompute required");
+    }
+    if (overflow) {
+      if (maxb > ctx->d.cl.ecap) ctx->d.cl.ecap = (int)(((long long)(maxb * 1.25) + 32 + 31) / 32 * 32);
+      if (maxa > ctx->d.cl.mcap) ctx->d.cl.mcap = (int)(((long long)(maxa * 1.25) + 32 + 31) / 32 * 32);
+      priv(ctx).dirty = true;
+      return fail(TMD_ERR_OVERFLOW, "cluster list capacity exceeded; capacity grown, recompute required");
+    }
+    return TMD_OK;
+  }
   if (overflow) {
     // grow the rows, invalidate the list; the caller recomputes (standalone force call)
     // or reports the run as invalid (fused multi-step call)
