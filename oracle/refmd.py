@@ -387,6 +387,71 @@ class OracleForces:
 # ----------------------------------------------------------------------------
 # integrator  (integrator.py:8-125)
 # ----------------------------------------------------------------------------
+
+# ----------------------------------------------------------------------------
+# row-sampled evaluation for systems the all-pairs table cannot hold
+# ----------------------------------------------------------------------------
+def sampled_rows(par, terms, pos, box_diag, atoms, cutoff, rfa=False, solventDielectric=78.5, switch_dist=None,
+                 exclusions=("bonds", "angles", "1-4"), chunk=256):
+    """Non-bonded force on each atom of ``atoms`` from ALL its partners, and its in-cutoff partner sets.
+
+    The reference's pair arithmetic (forces.py:264-319 with 360-372, 381-415, 453-491) restricted to the
+    rows of the all-pairs table that contain a sampled atom: 1,000 atoms x 99,999 partners is 1e8 distances,
+    where the full table (forces.py:348-357) would need 5e9.  Decisions ``dist <= cutoff`` in fp32 on fp32
+    positions like the reference's fp32 path; values in the dtype of ``pos`` (fp64: the yardstick).
+    ``pos`` (N,3), ``box_diag`` (3,).  Returns (forces (len(atoms),3), list of sorted partner index arrays)."""
+    terms = [t.lower() for t in terms]
+    N = pos.shape[0]
+    excl = {}
+    for i, j in par.get_exclusions(exclusions):
+        excl.setdefault(int(i), set()).add(int(j))
+        excl.setdefault(int(j), set()).add(int(i))
+    if "lj" in terms:
+        A, B = par.get_AB()
+        A, B = A.to(pos.dtype), B.to(pos.dtype)
+    types = par.mapped_atom_types
+    q = par.charges.to(pos.dtype)
+    pos32, bd32 = pos.to(torch.float32), box_diag.to(torch.float32)
+    allj = torch.arange(N)
+    out_f = torch.zeros((len(atoms), 3), dtype=pos.dtype)
+    out_p = []
+    for c0 in range(0, len(atoms), chunk):
+        sel = torch.as_tensor(atoms[c0 : c0 + chunk], dtype=torch.long)
+        ii = sel.repeat_interleave(N)
+        jj = allj.repeat(len(sel))
+        keep = ii != jj
+        # the reference's table holds (min, max): its difference is pos[min] - pos[max] (forces.py:369)
+        lo, hi = torch.minimum(ii, jj), torch.maximum(ii, jj)
+        pairs = torch.stack([lo, hi], dim=1)
+        d32, _, _ = pair_geometry(pos32, pairs, bd32)
+        inside = (d32 <= cutoff) & keep
+        for k, a in enumerate(sel.tolist()):  # exclusions of the sampled atoms
+            ex = excl.get(a)
+            if ex:
+                inside[k * N + torch.as_tensor(sorted(ex), dtype=torch.long)] = False
+        idx = pairs[inside]
+        dist, unit, _ = pair_geometry(pos, idx, box_diag)
+        dedr = torch.zeros_like(dist)
+        if "lj" in terms:
+            a_ = A[types[idx[:, 0]], types[idx[:, 1]]]
+            b_ = B[types[idx[:, 0]], types[idx[:, 1]]]
+            dedr += lj_pair(dist, a_, b_, 1, switch_dist, cutoff)[1]
+        if "electrostatics" in terms:
+            dedr += coulomb_pair(dist, q[idx[:, 0]], q[idx[:, 1]], 1, cutoff, rfa, solventDielectric)[1]
+        fvec = unit * dedr.unsqueeze(1)  # forces.py:316-319: f[idx0] -= fvec ; f[idx1] += fvec
+        row = ii[inside]  # the sampled atom of each kept pair
+        sign = torch.where(idx[:, 0] == row, -1.0, 1.0).to(pos.dtype).unsqueeze(1)
+        local = torch.searchsorted(sel, row) if bool(torch.all(sel[1:] > sel[:-1])) else None
+        if local is None:
+            lut = {a: k for k, a in enumerate(sel.tolist())}
+            local = torch.as_tensor([lut[a] for a in row.tolist()], dtype=torch.long)
+        out_f[c0 : c0 + len(sel)].index_add_(0, local, sign * fvec)
+        partner = jj[inside]
+        for k in range(len(sel)):
+            out_p.append(torch.sort(partner[local == k]).values)
+    return out_f, out_p
+
+
 def kinetic_energy(masses, vel):
     """0.5 m v^2 summed per replica -> (R,1)  (integrator.py:8-30)."""
     return torch.sum(0.5 * masses * torch.sum(vel * vel, dim=2, keepdim=True), dim=1)

@@ -39,7 +39,9 @@ def make_forces(g, fx, **kw):
     from torchmd_b200 import Forces
 
     old = os.environ.get("TMD_B200_FX")
+    old_cl = os.environ.get("TMD_B200_CLUSTER")
     os.environ["TMD_B200_FX"] = str(int(fx))
+    os.environ["TMD_B200_CLUSTER"] = "0"  # these tests are about the full-row kernels
     try:
         par = params_from_golden(g, precision=torch.float32, device=DEV)
         f = Forces(par, terms=[str(t) for t in g["terms"]], **golden_cfg(g), **kw)
@@ -52,6 +54,10 @@ def make_forces(g, fx, **kw):
             os.environ.pop("TMD_B200_FX", None)
         else:
             os.environ["TMD_B200_FX"] = old
+        if old_cl is None:
+            os.environ.pop("TMD_B200_CLUSTER", None)
+        else:
+            os.environ["TMD_B200_CLUSTER"] = old_cl
     return f, pos, box, F, E
 
 

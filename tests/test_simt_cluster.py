@@ -53,11 +53,11 @@ TERMS = ["lj", "electrostatics", "bonds", "angles"]
 CFG = dict(cutoff=5.0, rfa=True, switch_dist=4.0)
 
 
-def _compute(sysd, coords, handle, **kw):
+def _compute(sysd, coords, handle, dev="cpu", **kw):
     from torchmd_b200 import Forces, System, testsystems
 
-    par = testsystems.water_parameters(sysd, device="cpu")
-    system = System(len(coords), 1, torch.float32, "cpu")
+    par = testsystems.water_parameters(sysd, device=dev)
+    system = System(len(coords), 1, torch.float32, dev)
     system.set_positions(coords)
     system.set_box(sysd["box"])
     forces = Forces(par, terms=TERMS, **CFG, **kw)
@@ -70,11 +70,11 @@ def _oracle(sysd, system):
 
     par64 = testsystems.water_parameters(sysd, precision=torch.float64)
     of = refmd.OracleForces(par64, TERMS, decision_dtype=torch.float32, **CFG)
-    pos64 = system.pos.double()
+    pos64 = system.pos.cpu().double()
     f64 = torch.zeros_like(pos64)
-    e_ref = of.compute(pos64, system.box.double(), f64)[0]
+    e_ref = of.compute(pos64, system.box.cpu().double(), f64)[0]
     par32 = testsystems.water_parameters(sysd, precision=torch.float32)
-    pairs = refmd.OracleForces(par32, TERMS, **CFG).neighbour_pairs(system.pos[0], torch.diagonal(system.box[0])).numpy()
+    pairs = refmd.OracleForces(par32, TERMS, **CFG).neighbour_pairs(system.pos[0].cpu(), torch.diagonal(system.box[0]).cpu()).numpy()
     return f64, e_ref, pairs
 
 

@@ -545,50 +545,67 @@ struct ClPairShared {
 };
 
 // Pairs of cluster c inside the decision band of a periodic box: the reference's own decision on the raw
-// positions, scalar arithmetic, forces straight to the accumulators.  Rare (about one cluster in a hundred).
+// positions, one pair at a time, forces straight to the accumulators.  Rare (about one cluster in a hundred).
+// (Arguments by value: a reference to the kernel's parameter block would force a local copy of it.)
+struct ClExactArgs {
+  const int4* xf;        // slot records of this replica
+  const float4* xq;
+  const float4* xw;
+  float4* f;
+  const unsigned* ent;   // this cluster's entries / masks
+  const unsigned char* msk;
+  const Grid* g;
+  const float2* AB;
+  int mcap, slots, c, ntypes;
+  unsigned terms;
+  float s_lo, s_hi, s_max;
+};
 template <bool ENERGY>
-__device__ __noinline__ void cl_exact_pass(const DeviceState& S, int r, int c, int2 mt, float s_lo, float s_hi, float& e_lj, float& e_el) {
-  const ClusterState& C = S.cl;
+__device__ __noinline__ float2 cl_exact_pass(ClExactArgs a, int2 mt, SwitchConsts sc) {
   const int lane = threadIdx.x & 31;
-  const size_t sb = (size_t)r * (C.slots + 1), cb = (size_t)r * C.nclusters_cap;
-  const Grid* g = S.grid + r;
+  const Grid* g = a.g;
   const unsigned imask = (unsigned)mt.x >> 24;
   const int nA = mt.x & 0xffffff, nB = mt.y;
-  const unsigned* ent = C.entries + (cb + c) * (size_t)(C.mcap + C.ecap);
-  const unsigned char* msk = C.masks + (cb + c) * (size_t)C.mcap;
   const float ux = g->fx_unit[0], uy = g->fx_unit[1], uz = g->fx_unit[2];
-  float e_rep = 0.f, e_cg = 0.f;
+  float e_lj = 0.f, e_el = 0.f;
   for (int region = 0; region < 2; ++region) {
     const int n = region == 0 ? nA : nB;
-    const unsigned* e = region == 0 ? ent : ent + C.mcap;
+    const unsigned* e = region == 0 ? a.ent : a.ent + a.mcap;
     for (int k = lane; k < n; k += 32) {
       const unsigned en = e[k];
       const int sj = (int)(en & 0xffffffu);
-      if (sj >= C.slots) continue;
-      const unsigned m = (region == 0 ? (unsigned)msk[k] : 0xffu) & imask;
-      const int4 pj = C.xf[sb + sj];
+      if (sj >= a.slots) continue;
+      const unsigned m = (region == 0 ? (unsigned)a.msk[k] : 0xffu) & imask;
+      const int4 pj = a.xf[sj];
       for (int i = 0; i < CL; ++i) {
         if (!((m >> i) & 1u)) continue;
-        const int4 pi = C.xf[sb + c * CL + i];
+        const int si = a.c * CL + i;
+        const int4 pi = a.xf[si];
         const float wx = fx_delta(pi.x, pj.x, ux), wy = fx_delta(pi.y, pj.y, uy), wz = fx_delta(pi.z, pj.z, uz);
         const float s = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
-        if (!(s < s_lo) && s <= s_hi) {
-          const float4 a = C.xq[sb + c * CL + i], b = C.xq[sb + sj];
-          if (ref_inside(a.x, a.y, a.z, b.x, b.y, b.z, g->L[0], g->L[1], g->L[2], g->invL[0], g->invL[1], g->invL[2], S.pp.s_max)) {
-            const int ti = __float_as_int(C.xw[sb + c * CL + i].w);
+        if (!(s < a.s_lo) && s <= a.s_hi) {
+          const float4 ri = a.xq[si], rj = a.xq[sj];
+          if (ref_inside(ri.x, ri.y, ri.z, rj.x, rj.y, rj.z, g->L[0], g->L[1], g->L[2], g->invL[0], g->invL[1], g->invL[2], a.s_max)) {
             float2 ab = make_float2(0.f, 0.f);
-            if (S.pp.terms & T_LJ) ab = S.AB[ti * S.ntypes + (int)(en >> 24)];
-            float rinv;
-            const float dedr = pair_terms<0>(S.pp, s, __int_as_float(pi.w) * __int_as_float(pj.w), ab.x, ab.y, e_el, e_lj, e_rep, e_cg, rinv);
-            const float cc = dedr * rinv;
-            red_add_f32x4(C.f + sb + c * CL + i, -wx * cc, -wy * cc, -wz * cc);
-            red_add_f32x4(C.f + sb + sj, wx * cc, wy * cc, wz * cc);
+            if (a.terms & T_LJ) ab = a.AB[__float_as_int(a.xw[si].w) * a.ntypes + (int)(en >> 24)];
+            ClTab tb;
+            tb.ab = make_float4(ab.x, ab.x, ab.y, ab.y);
+            tb.dab = make_float4(12.0f * ab.x, 12.0f * ab.x, 6.0f * ab.y, 6.0f * ab.y);
+            const float nqq = (a.terms & T_ELEC) ? -(__int_as_float(pi.w) * __int_as_float(pj.w)) : 0.f;
+            F2 elj, neel;
+            const F2 nc = cl_coef2<ENERGY>(sc, f2(s), f2(nqq), tb, elj, neel);
+            red_add_f32x4(a.f + si, wx * nc.x, wy * nc.x, wz * nc.x);
+            red_add_f32x4(a.f + sj, -wx * nc.x, -wy * nc.x, -wz * nc.x);
+            if (ENERGY) {
+              e_lj += elj.x;
+              e_el -= neel.x;
+            }
           }
         }
       }
     }
   }
-  (void)ENERGY;
+  return make_float2(e_lj, e_el);
 }
 
 // dynamic shared memory: per warp two entry buffers of (mcap + ecap) words, then per warp the LJ table (ntypes x CL_H)
@@ -640,6 +657,9 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
     s_in = S.pp.s_max - margin;
     s_hi = S.pp.s_max + margin;
   }
+  // s >= +0 always, so its bit pattern orders like its value: u = bits(s) - bits(s_in) wraps to >= 2^31 exactly for the
+  // pairs inside (s < s_in), and the pairs in the band are those with u <= bits(s_hi) - bits(s_in)
+  const unsigned b_in = __float_as_uint(fmaxf(s_in, 0.f)), b_band = __float_as_uint(fmaxf(s_hi, 0.f)) - b_in;
 
   auto issue = [&](int c, int which, int2 mt) {  // lane 0: bulk copies of the cluster's two regions into buffer `which`
     const int nA = mt.x & 0xffffff;
@@ -721,7 +741,15 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
     const unsigned char* __restrict__ mrow = C.masks + (cb + c) * (size_t)C.mcap;
     if (nb) mbar_wait(bar_s + 8u * which, (phase >> which) & 1u);
     __syncwarp();
-    bool band = false;
+    unsigned u_min = 0xffffffffu;  // smallest u of a pair not taken (see b_band)
+    // base addresses the loop uses, kept in registers (otherwise re-derived from the parameter block per entry)
+    unsigned long long rec_base = PERIODIC ? reinterpret_cast<unsigned long long>(xf) : reinterpret_cast<unsigned long long>(xq);
+    unsigned long long f_base = reinterpret_cast<unsigned long long>(fout);
+    unsigned long long m_base = reinterpret_cast<unsigned long long>(mrow);
+    TMD_PIN_L(rec_base);
+    TMD_PIN_L(f_base);
+    TMD_PIN_L(m_base);
+    const unsigned nslots_cap = (unsigned)C.slots;
 
     // one partner (record rj: float x, y, z, q or fixed-point X, Y, Z, q bits) against the cluster
     auto body = [&](unsigned entry, unsigned mask, const int4 rj) {
@@ -747,9 +775,10 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
         const bool m0 = (mask >> (2 * p)) & 1u, m1 = (mask >> (2 * p + 1)) & 1u;
         bool in0, in1;
         if (PERIODIC) {
-          in0 = m0 && s.x < s_in;
-          in1 = m1 && s.y < s_in;
-          band |= (m0 && !(s.x < s_in) && s.x <= s_hi) || (m1 && !(s.y < s_in) && s.y <= s_hi);
+          const unsigned u0 = __float_as_uint(s.x) - b_in, u1 = __float_as_uint(s.y) - b_in;
+          in0 = m0 && (int)u0 < 0;
+          in1 = m1 && (int)u1 < 0;
+          u_min = min(u_min, min(m0 ? u0 : 0xffffffffu, m1 ? u1 : 0xffffffffu));
         } else {
           in0 = m0 && s.x <= s_in;
           in1 = m1 && s.y <= s_in;
@@ -773,29 +802,31 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
         }
       }
       const float gx = -(GX.x + GX.y), gy = -(GY.x + GY.y), gz = -(GZ.x + GZ.y);
-      if (gx != 0.f || gy != 0.f || gz != 0.f) red_add_f32x4(fout + jslot, gx, gy, gz);
+      if (gx != 0.f || gy != 0.f || gz != 0.f) red_add_f32x4(reinterpret_cast<float4*>(mad_wide_u32(jslot, 16u, f_base)), gx, gy, gz);
     };
-    auto record_of = [&](unsigned en) {
-      if (PERIODIC) return xf[en & 0xffffffu];
-      const float4 v = xq[en & 0xffffffu];
-      return make_int4(__float_as_int(v.x), __float_as_int(v.y), __float_as_int(v.z), __float_as_int(v.w));
+    // (float4 and int4 records alike: 16 bytes at slot * 16)
+    auto record_of = [&](unsigned en) { return ldg_s32x4(mad_wide_u32(en & 0xffffffu, 16u, rec_base)); };
+    auto mask_of = [&](int e) {
+      unsigned v;
+      v = *reinterpret_cast<const unsigned char*>(m_base + (unsigned)e);
+      return v;
     };
 
     // batches: entries from shared memory, partner records gathered one batch ahead
     if (nb) {
       unsigned en = lds_u32(ebuf + 4u * lane);
-      unsigned mk = 0 < nbA ? (unsigned)mrow[lane] : 0xffu;
+      unsigned mk = 0 < nbA ? mask_of(lane) : 0xffu;
       int4 rj = record_of(en);
       for (int b = 0; b < nb; ++b) {
         unsigned en_n = en, mk_n = 0xffu;
         int4 rj_n = rj;
         if (b + 1 < nb) {
           en_n = lds_u32(ebuf + 4u * ((b + 1) * 32 + lane));
-          if (b + 1 < nbA) mk_n = (unsigned)mrow[(b + 1) * 32 + lane];
+          if (b + 1 < nbA) mk_n = mask_of((b + 1) * 32 + lane);
           rj_n = record_of(en_n);
         }
         unsigned m = mk & imask;
-        if ((en & 0xffffffu) >= (unsigned)C.slots) m = 0;  // padding entry: the dummy record interacts with nothing
+        if ((en & 0xffffffu) >= nslots_cap) m = 0;  // padding entry: the dummy record interacts with nothing
         body(en, m, rj);
         en = en_n;
         mk = mk_n;
@@ -813,7 +844,28 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
         if ((imask >> (2 * p + 1)) & 1u) red_add_f32x4(fout + s0 + 2 * p + 1, bx, by, bz);
       }
     }
-    if (PERIODIC && __any_sync(0xffffffffu, band)) cl_exact_pass<ENERGY>(S, r, c, mt_cur, s_in, s_hi, ex_lj, ex_el);
+    if (PERIODIC && __any_sync(0xffffffffu, u_min <= b_band)) {
+      ClExactArgs a;
+      a.xf = xf;
+      a.xq = xq;
+      a.xw = C.xw + sb;
+      a.f = fout;
+      a.ent = C.entries + (cb + c) * (size_t)stride_e;
+      a.msk = mrow;
+      a.g = S.grid + r;
+      a.AB = S.AB;
+      a.mcap = C.mcap;
+      a.slots = C.slots;
+      a.c = c;
+      a.ntypes = S.ntypes;
+      a.terms = S.pp.terms;
+      a.s_lo = s_in;
+      a.s_hi = s_hi;
+      a.s_max = S.pp.s_max;
+      const float2 ee = cl_exact_pass<ENERGY>(a, mt_cur, sc);
+      ex_lj += ee.x;
+      ex_el += ee.y;
+    }
     which ^= 1;
   }
   if (ENERGY) {

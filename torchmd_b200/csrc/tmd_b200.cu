@@ -607,7 +607,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       // entries per cluster: half of the atoms within rl of a box of about (2.5, w, w) A, with head room
       const double w = rl / d.nsub, a = 2.5, rho = std::max(max_density, 0.11);
       const double vol = a * w * w + 2.0 * (a * w + w * w + a * w) * rl + M_PI * (a + 2 * w) * rl * rl + 4.0 / 3.0 * M_PI * rl * rl * rl;
-      long long ecap = (long long)(0.5 * rho * vol * 1.3) + 64;
+      long long ecap = (long long)(0.5 * rho * vol * 1.6) + 128;
       if (const char* e = getenv("TMD_B200_CLUSTER_ECAP")) ecap = std::max(32, atoi(e));  // (tests: start too small, grow)
       ecap = std::max<long long>(ecap, keep_ecap);
       ecap = std::min<long long>((ecap + 31) / 32 * 32, ((long long)N + 31) / 32 * 32);

@@ -134,24 +134,31 @@ class Integrator:
             f = self.forces
             f._ensure_box(s.box)
             ene = torch.empty((nrep, _lib.NUM_ENERGIES), dtype=torch.float64, device=s.pos.device)
-            _lib.check(
-                L.tmd_md_steps(
-                    ctx, niter, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), self.masses.data_ptr(),
-                    self.dt, gamma, vcoeff, _lib.ptr(noise), self.seed, 0,
-                    ene.data_ptr(), ke.data_ptr(), stream,
+            # A neighbour list that outgrows its reserved capacity inside the fused call invalidates the call (the
+            # kernels truncate, the library grows the capacity at the stats() check).  The state is three small
+            # tensors: keep a copy and run the call again from it instead of giving up.
+            saved = (s.pos.clone(), s.vel.clone(), s.forces.clone())
+            for attempt in range(6):
+                _lib.check(
+                    L.tmd_md_steps(
+                        ctx, niter, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), self.masses.data_ptr(),
+                        self.dt, gamma, vcoeff, _lib.ptr(noise), self.seed, 0,
+                        ene.data_ptr(), ke.data_ptr(), stream,
+                    )
                 )
-            )
+                try:
+                    f.stats()
+                    break
+                except _lib.TmdError as err:
+                    if err.code != _lib.ERR_OVERFLOW:
+                        raise
+                    if attempt == 5:
+                        raise RuntimeError("the neighbour lists kept overflowing during Integrator.step") from err
+                    s.pos.copy_(saved[0])
+                    s.vel.copy_(saved[1])
+                    s.forces.copy_(saved[2])
+                    ctx = self._ctx()  # (re-finalised with the grown capacity on the next call)
             self._step_index += niter
-            try:
-                f.stats()
-            except _lib.TmdError as err:
-                if err.code == _lib.ERR_OVERFLOW:
-                    raise RuntimeError(
-                        "a neighbour row overflowed during Integrator.step: the trajectory of this call is invalid. "
-                        "Call forces.compute() once before dynamics (as torchmd/run.py does) so rows are sized from "
-                        "the real neighbour counts, or raise TMD_B200_SKIN headroom."
-                    ) from err
-                raise
             pot = f._format(ene, None, s.pos.dtype, False, True)
         else:
             for it in range(niter):
