@@ -38,24 +38,50 @@ GAMMA_PS = 0.1
 TEMPERATURE = 300.0
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
+# BASELINE.json configs as bench workloads.  The headline (and the default) is water100k.
+WORKLOADS = {
+    "water100k": "synthetic TIP3P water box, 33333 waters = 99999 atoms, L=99.93 A, LJ(switch 7.5)+RF electrostatics cutoff 9 A, "
+                 "flexible bonds+angles, Langevin 300 K gamma 0.1/ps, dt 1 fs, 1 replica (BASELINE config 4)",
+    "water10k": "synthetic TIP3P water box, 3333 waters = 9999 atoms, L=46.39 A, same settings as water100k: the largest size "
+                "the reference's all-pairs path runs in seconds per step, so BOTH arms are timed on it",
+    "water291": "the reference's tests/water fixture: 97 waters = 291 atoms, L=16.9 A, 2 replicas, LJ(switch 6.0)+RF cutoff 7.3 A, "
+                "bonds+angles, Langevin 300 K (BASELINE config 2)",
+    "ala2": "the reference's tests/prod_alanine_dipeptide_amber: 688 atoms in a 19.8 A box, AMBER bonds/angles/dihedrals/impropers/1-4 + "
+            "LJ(switch 7.5)+RF cutoff 9 A, Langevin 300 K (BASELINE config 3)",
+    "thrombin16": "the reference's tests/thrombin-ligand-amber: 4676 atoms, no box, all AMBER terms, RF cutoff 7.3 A, 16 replicas "
+                  "(sharded over the GPUs when --gpus > 1), Langevin 300 K (BASELINE config 5)",
+}
+
+
+def build_workload(name, device, precision=None, nrep=None):
+    """(par, coords (N,3), box (3,), terms, cfg, nrep, needs_equilibration) of a workload."""
+    import numpy as np
+    import torch
+
+    from torchmd_b200 import testsystems
+
+    precision = precision or torch.float32
+    if name in ("water100k", "water10k"):
+        sysd = testsystems.water_box(N_WATERS if name == "water100k" else 3333, seed=0)
+        par = testsystems.water_parameters(sysd, precision=precision, device=device)
+        return par, np.asarray(sysd["coords"], np.float32), np.asarray(sysd["box"], np.float32), list(TERMS), dict(CFG), nrep or 1, True
+    golden = {"water291": ("water291_rf_switch", 2), "ala2": ("ala2_xsc_rf", 1), "thrombin16": ("thrombin_nobox_rf", 16)}[name]
+    par, coords, box, terms, cfg = testsystems.golden_system(golden[0], precision=precision, device=device)
+    return par, coords, box, terms, cfg, nrep or golden[1], False
+
 
 # ------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's CPU path
 # ------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, budget_s=150.0):
-    """Time the reference algorithm (all-pairs + mask, torch CPU ops, all host threads)
-    on a bounded sample: the same generator/settings at a box size whose (warmup+steps)
-    steps fit the budget; scaled to the 99,999-atom metric with the O(N^2) law the
-    all-pairs evaluation follows (100k atoms are infeasible for
-    the reference -- 80 GB pair table)."""
+def _probe_threads():
+    """ATen's elementwise kernels stop scaling (and degrade) on very wide hosts: probe a few thread counts on a
+    3,000-atom box and give the reference the fastest one."""
     import torch
 
     from oracle import refmd
     from torchmd_b200 import testsystems
 
     ncores = os.cpu_count() or 1
-    # ATen's elementwise kernels stop scaling (and degrade) on very wide hosts: probe a few thread
-    # counts on a 3,000-atom box and give the reference the fastest one
     best = (float("inf"), ncores)
     try:
         probe = testsystems.water_box(1000, seed=0)
@@ -76,27 +102,56 @@ def cpu_reference_run(steps, warmup, budget_s=150.0):
                 best = (dt, nt)
     except Exception:
         pass
-    nthreads = best[1]
-    torch.set_num_threads(nthreads)
-    est = {3333: 1.6, 1000: 0.22, 333: 0.05}  # s/step measured on 8 cores
-    scale = 8.0 / max(1, min(ncores, 32))
-    nw = 333
-    for cand in (3333, 1000, 333):
-        if (steps + warmup) * est[cand] * max(scale, 0.25) <= budget_s:
-            nw = cand
-            break
-    sysd = testsystems.water_box(nw, seed=0)
-    par = testsystems.water_parameters(sysd, precision=torch.float32)
-    n = len(sysd["coords"])
+    torch.set_num_threads(best[1])
+    return best[1], ncores
+
+
+def cpu_reference_run(workload, steps, warmup, budget_s=150.0):
+    """Time the reference algorithm (all-pairs table + cutoff mask, torch CPU ops, all useful host threads) through the
+    oracle port.  water100k cannot run there at all (the pair table alone is 80 GB): the arm then
+    times a BOUNDED SAMPLE -- the same generator and settings at a box size whose steps fit the budget -- and
+    reports what it MEASURED at that size; an O(N^2) extrapolation to 99,999 atoms is given separately and labelled.
+    Every other workload is timed as it is (thrombin16: fewer replicas if 16 do not fit the budget)."""
+    import numpy as np
+    import torch
+
+    from oracle import refmd
+
+    nthreads, ncores = _probe_threads()
+    sample_note = ""
+    name = workload
+    nrep_full = None
+    if workload == "water100k":
+        est = {3333: 1.6, 1000: 0.22, 333: 0.05}  # s/step measured on 8 cores (BASELINE.md)
+        scale = 8.0 / max(1, min(ncores, 32))
+        nw = 333
+        for cand in (3333, 1000, 333):
+            if (steps + warmup) * est[cand] * max(scale, 0.25) <= budget_s:
+                nw = cand
+                break
+        from torchmd_b200 import testsystems
+
+        sysd = testsystems.water_box(nw, seed=0)
+        par = testsystems.water_parameters(sysd, precision=torch.float32)
+        coords, boxd, terms, cfg, nrep = np.asarray(sysd["coords"], np.float32), np.asarray(sysd["box"], np.float32), list(TERMS), dict(CFG), 1
+        sample_note = f"bounded sample of water100k: the same generator and settings at {3 * nw} atoms; "
+    else:
+        par, coords, boxd, terms, cfg, nrep, _ = build_workload(workload, "cpu")
+        if workload == "thrombin16":
+            nrep_full = nrep
+            nrep = 2 if (steps + warmup) * 16 * 2.0 > budget_s else 16
+            if nrep != nrep_full:
+                sample_note = f"bounded sample of thrombin16: {nrep} of the {nrep_full} replicas (the reference loops over replicas serially, forces.py:116); "
+    n = len(coords)
     t0 = time.perf_counter()
-    of = refmd.OracleForces(par, TERMS, **CFG)
+    of = refmd.OracleForces(par, terms, **cfg)
     t_init = time.perf_counter() - t0
-    pos = torch.tensor(sysd["coords"])[None].clone()
-    box = torch.zeros(1, 3, 3)
+    pos = torch.tensor(coords)[None].repeat(nrep, 1, 1).contiguous()
+    box = torch.zeros(nrep, 3, 3)
     for k in range(3):
-        box[0, k, k] = float(sysd["box"][k])
+        box[:, k, k] = float(boxd[k])
     torch.manual_seed(1)
-    vel = refmd.maxwell_boltzmann(par.masses, TEMPERATURE, 1)
+    vel = refmd.maxwell_boltzmann(par.masses, TEMPERATURE, nrep)
     F = torch.zeros_like(pos)
     fn = lambda p, b, f: [sum(e.values()) for e in of.compute(p, b, f)]  # noqa: E731
     fn(pos, box, F)
@@ -106,24 +161,26 @@ def cpu_reference_run(steps, warmup, budget_s=150.0):
     integ.step(steps)
     dt = time.perf_counter() - t0
     measured = steps / dt
-    target_n = 3 * N_WATERS
-    value = measured * (n / target_n) ** 2
-    return {
-        "value": value,
+    out = {
+        "value": measured,
         "unit": "steps/s",
         "cores": nthreads,
         "kind": "port",
         "sample": (
-            f"oracle/refmd.py (torch-CPU restatement of the reference; {nthreads} torch threads, the fastest of a probe "
-            f"over 8..{ncores} on this {ncores}-core host) on a {n}-atom water box, "
-            f"{steps} steps after {warmup} warm-up: measured {measured:.4g} steps/s ({dt / steps:.3f} s/step, "
-            f"pair-table init {t_init:.1f} s); value = measured x ({n}/{target_n})^2 (all-pairs O(N^2)); "
-            f"99,999 atoms are infeasible for the reference (O(N^2) memory)"
+            f"{sample_note}oracle/refmd.py (torch-CPU restatement of the reference; {nthreads} torch threads, the fastest of a probe "
+            f"over 8..{ncores} on this {ncores}-core host), {n} atoms x {nrep} replica(s), {steps} steps after {warmup} warm-up: "
+            f"{measured:.4g} steps/s measured ({dt / steps:.3f} s/step, pair-table init {t_init:.1f} s)"
         ),
-        "measured_steps_per_s": measured,
         "measured_natoms": n,
+        "measured_replicas": nrep,
         "ms_per_step_measured": 1e3 * dt / steps,
     }
+    if workload == "water100k":
+        out["extrapolated_99999_atoms_steps_per_s"] = measured * (n / (3.0 * N_WATERS)) ** 2
+        out["extrapolation_note"] = "measured x (natoms/99999)^2, the all-pairs O(N^2) law; NOT a measurement: 99,999 atoms are infeasible for the reference (O(N^2) memory)"
+    if nrep_full and nrep != nrep_full:
+        out["extrapolated_16_replicas_steps_per_s"] = measured * nrep / nrep_full
+    return out
 
 
 def reference_arm(args):
@@ -131,10 +188,16 @@ def reference_arm(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    base = cpu_reference_run(steps, max(0, args.warmup))
+    base = cpu_reference_run(args.workload, steps, max(0, args.warmup))
+    cfg = workload_config(args.gpus, args.workload)
+    cfg["natoms"] = base["measured_natoms"]  # what this arm actually ran
+    cfg["replicas"] = base["measured_replicas"]
+    if args.workload == "water100k":
+        cfg["workload"] = ("REFERENCE ARM SAMPLE of: " + cfg["workload"] + f" -- timed at {base['measured_natoms']} atoms "
+                           "(the reference cannot hold the 99,999-atom pair table); `value` is the measured steps/s at that size")
     line = {
         "impl": "reference",
-        "metric": "MD steps/sec (100k-atom water, fp32)",
+        "metric": METRICS[args.workload],
         "value": base["value"],
         "unit": "steps/s",
         "n_gpus": args.gpus,
@@ -146,7 +209,7 @@ def reference_arm(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -154,17 +217,28 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(ngpus):
+METRICS = {
+    "water100k": "MD steps/sec (100k-atom water, fp32)",
+    "water10k": "MD steps/sec (9,999-atom water, fp32)",
+    "water291": "MD steps/sec (tests/water fixture, 291 atoms x 2 replicas, fp32)",
+    "ala2": "MD steps/sec (alanine dipeptide in water, 688 atoms, AMBER, fp32)",
+    "thrombin16": "MD steps/sec (thrombin-ligand, 4676 atoms x 16 replicas, fp32)",
+}
+
+
+def workload_config(ngpus, workload="water100k"):
+    replicated = workload in ("thrombin16", "water291")
     return {
-        "workload": "synthetic TIP3P water box, 33333 waters = 99999 atoms, L=99.93 A, LJ(switch 7.5)+RF electrostatics cutoff 9 A, "
-        "flexible bonds+angles, Langevin 300 K gamma 0.1/ps, dt 1 fs, 1 replica",
-        "natoms": 3 * N_WATERS,
-        "pair_kernel": {"1": "fixed-point separations (TMD_B200_FX=1)", "2": "fixed-point separations + packed fp32x2 arithmetic (TMD_B200_FX=2)"}.get(
-            os.environ.get("TMD_B200_FX", "")[:1], "float separations (default)"),
-        "parallelism": "single GPU" if ngpus == 1 else (f"spatial slabs over {ngpus} GPUs, " + ("positions pushed to all ranks over NVLink peer memory by the integration kernel"
+        "workload": WORKLOADS[workload],
+        "natoms": {"water100k": 3 * N_WATERS, "water10k": 9999, "water291": 291, "ala2": 688, "thrombin16": 4676}[workload],
+        "pair_kernel": "cluster half list, packed fp32x2 arithmetic on fixed-point separations (cluster.cuh) where it applies; "
+                       "TMD_B200_CLUSTER=0: full Verlet rows",
+        "parallelism": "single GPU" if ngpus == 1 else (
+            f"replicas sharded over {ngpus} GPUs, no per-step collective" if replicated else
+            f"spatial slabs over {ngpus} GPUs, " + ("positions pushed to all ranks over NVLink peer memory by the integration kernel"
                                                    if os.environ.get("TMD_B200_EXCHANGE", "").lower() == "p2p" else "position all-gather")),
-        "l2": "no flush between steps: consecutive MD steps are data-dependent; the neighbour list streamed by the "
-        "pair kernel (>150 MB) exceeds the 126 MB L2",
+        "l2": "no flush between steps: consecutive MD steps are data-dependent (each step's positions are the previous step's "
+        "output); the state is re-read from L2/HBM as a real run does",
     }
 
 
@@ -229,51 +303,66 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from torchmd_b200 import Forces, Integrator, System, _lib, maxwell_boltzmann, testsystems
+    from torchmd_b200 import Forces, Integrator, System, _lib, maxwell_boltzmann
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload
+    replicated = wl in ("thrombin16", "water291")
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # (NCCL's own log, if NCCL_DEBUG is set, goes to stderr / NCCL_DEBUG_FILE; rank 0 prints the JSON line last)
+        if not dist.is_initialized():  # (tests/test_domain_host.py brings its own gloo group)
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = DEVICE_OVERRIDE or f"cuda:{local}"
     if DEVICE_OVERRIDE is None:
         torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not replicated:
+        if wl != "water100k":
+            raise SystemExit(f"--gpus > 1 runs water100k (spatial decomposition) or the replicated workloads, not {wl}")
         from torchmd_b200 import domain  # spatial decomposition driver
 
         try:
-            return domain.bench_decomposed(args, world, rank, local, workload_config(world))
+            return domain.bench_decomposed(args, world, rank, local, workload_config(world, wl))
         finally:
             dist.destroy_process_group()
 
-    sysd = testsystems.water_box(N_WATERS, seed=0)
-    n = len(sysd["coords"])
-    par = testsystems.water_parameters(sysd, device=dev)
-    system = System(n, 1, torch.float32, dev)
-    system.set_positions(sysd["coords"])
-    system.set_box(sysd["box"])
-    torch.manual_seed(1)
-    system.set_velocities(maxwell_boltzmann(par.masses, TEMPERATURE, 1))
-    forces = Forces(par, terms=TERMS, **CFG)
+    par, coords, boxd, terms, cfg, nrep_total, needs_eq = build_workload(wl, dev)
+    # replicas are independent (forces.py:116 loops over them): shard them over the ranks, no per-step collective
+    if nrep_total % world:
+        raise SystemExit(f"{nrep_total} replicas do not divide over {world} ranks")
+    nrep = nrep_total // world
+    n = len(coords)
+    system = System(n, nrep, torch.float32, dev)
+    system.set_positions(coords)
+    system.set_box(boxd)
+    torch.manual_seed(1 + rank)
+    system.set_velocities(maxwell_boltzmann(par.masses, TEMPERATURE, nrep))
+    forces = Forces(par, terms=terms, **cfg)
     forces.compute(system.pos, system.box, system.forces)
 
-    # relax the lattice start into a liquid: strong coupling, then the production thermostat
-    eq = Integrator(system, forces, TIMESTEP_FS, dev, gamma=10.0, T=TEMPERATURE)
-    for _ in range(args.equil // 100):
-        eq.step(niter=100)
+    # relax a lattice start into a liquid: strong coupling, then the production thermostat
+    equil_done = 0
+    if needs_eq:
+        eq = Integrator(system, forces, TIMESTEP_FS, dev, gamma=10.0, T=TEMPERATURE)
+        for _ in range(args.equil // 100):
+            eq.step(niter=100)
+            equil_done += 100
     integ = Integrator(system, forces, TIMESTEP_FS, dev, gamma=GAMMA_PS, T=TEMPERATURE)
-    sampler = ClockSampler(local)  # runs through the warm-up too (same load), so short runs still get samples
+    sampler = ClockSampler(local) if rank == 0 else None  # runs through the warm-up too (same load)
     t_w = time.perf_counter()
+    chunk = 50 if n > 20000 else 500
+    nwarm = max(3, args.warmup, chunk if world == 1 else 4 * chunk)
     done = 0
-    while done < max(3, args.warmup) or time.perf_counter() - t_w < 0.6:  # >= 0.6 s under load for the sampler
-        ekin, pot, T = integ.step(niter=50)
-        done += 50
+    while done < nwarm or (world == 1 and time.perf_counter() - t_w < 0.6):  # >= 0.6 s under load for the sampler
+        ekin, pot, T = integ.step(niter=chunk)
+        done += chunk
 
     L = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
     st0 = forces.stats()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     _lib.check(L.tmd_profile_begin(forces._ctx, args.steps))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,19 +374,27 @@ def gpu_arm(args):
 
     pair_ms, pair_n = C.c_double(), C.c_int()
     _lib.check(L.tmd_profile_end(forces._ctx, C.byref(pair_ms), C.byref(pair_n), stream))
-    clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        ms_total = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
     st1 = forces.stats()
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
+    pair_kernel_id = int(L.tmd_pair_kernel(forces._ctx))
 
-    # exact number of in-cutoff pairs of the final configuration (reference predicate)
-    count = torch.zeros(1, dtype=torch.int64, device=dev)
-    dummy = torch.zeros(2, dtype=torch.int32, device=dev)
-    scratch = torch.empty_like(system.pos)
-    forces.compute(system.pos, system.box, scratch)
-    _lib.check(L.tmd_export_pairs(forces._ctx, system.pos.data_ptr(), 0, dummy.data_ptr(), 0, count.data_ptr(), stream))
-    p_rc = int(count.item())
+    # exact number of in-cutoff pairs of the final configuration (reference predicate), replica 0
+    p_rc = 0
+    if forces.require_distances:
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        dummy = torch.zeros(2, dtype=torch.int32, device=dev)
+        scratch = torch.empty_like(system.pos)
+        forces.compute(system.pos, system.box, scratch)
+        _lib.check(L.tmd_export_pairs(forces._ctx, system.pos.data_ptr(), 0, dummy.data_ptr(), 0, count.data_ptr(), stream))
+        p_rc = int(count.item())
 
     peaks = {}
     try:
@@ -306,10 +403,16 @@ def gpu_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
     pair_avg_ms = pair_ms.value / max(1, pair_n.value)
-    alg_bytes = 32.0 * n + 4.0 * p_rc
+    alg_bytes = nrep * (32.0 * n + 4.0 * p_rc)  # SURVEY.md 8d, per force evaluation and replica
     achieved = alg_bytes / (pair_avg_ms * 1e-3) / 1e9 if pair_avg_ms > 0 else 0.0
+    kname = {0: "k_pair (full rows, float separations)", 1: "k_pair_fx (full rows, fixed-point separations)",
+             2: "k_pair_fx2 (full rows, packed fp32x2)", 3: "k_pair2_open (full rows, packed fp32x2, no box)",
+             4: "k_cpair (cluster half list, TMA-staged entries, packed fp32x2)"}.get(pair_kernel_id, str(pair_kernel_id))
+    # the pair kernel's other roof: packed or not, the SM issues 128 fp32 FMA lanes per clock
+    flops_per_pair = 60.0
+    fp32_peak_tflops = 148 * 128 * 2 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0) * 1e6 / 1e12
     roofline = {
-        "kernel": "k_pair<false,true> (non-bonded pair kernel)",
+        "kernel": kname,
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
@@ -322,11 +425,16 @@ def gpu_arm(args):
         "launches_sampled": pair_n.value,
         "share_of_step": pair_avg_ms / ms_per_step,
         "traffic": None,
+        "fp32_useful_tflops": nrep * p_rc * flops_per_pair / (pair_avg_ms * 1e-3) / 1e12 if pair_avg_ms > 0 else 0.0,
+        "fp32_peak_tflops": fp32_peak_tflops,
+        "note": "the pair loop is bound by the fp32 pipe, not by HBM (DESIGN.md 4): ~60 flop per in-cutoff pair; "
+                "fp32_useful_tflops / fp32_peak_tflops is its fraction of that roof",
     }
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")))
-        roofline["traffic"] = prof.get("dram_bytes_per_launch")
-        roofline["traffic_source"] = prof.get("source")
+        if prof.get("kernel_id") == pair_kernel_id and wl == "water100k":
+            roofline["traffic"] = prof.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = prof.get("source")
     except Exception:
         pass
 
@@ -336,8 +444,8 @@ def gpu_arm(args):
     hvel = torch.empty(system.vel.shape, dtype=torch.float32, pin_memory=True)
     hpos.copy_(system.pos)
     hvel.copy_(system.vel)
-    hene = np.zeros((1, _lib.NUM_ENERGIES), dtype=np.float64)
-    hke = np.zeros(1, dtype=np.float64)
+    hene = np.zeros((nrep, _lib.NUM_ENERGIES), dtype=np.float64)
+    hke = np.zeros(nrep, dtype=np.float64)
     gamma_int = GAMMA_PS / (1000.0 / 48.88821)
 
     def host_step(k):
@@ -351,49 +459,71 @@ def gpu_arm(args):
 
     for k in range(5):
         host_step(k)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         host_step(5 + k)
     t_e2e = time.perf_counter() - t0
-    bytes_each_way = 2 * system.pos.numel() * 4
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    bytes_each_way = 2 * system.pos.numel() * 4 * world
     e2e = {
         "value": e2e_steps / t_e2e,
         "unit": "steps/s",
         "h2d_bytes_per_step": bytes_each_way,
-        "d2h_bytes_per_step": bytes_each_way + hene.nbytes + hke.nbytes,
+        "d2h_bytes_per_step": bytes_each_way + (hene.nbytes + hke.nbytes) * world,
         "steps": e2e_steps,
         "api": "tmd_md_steps_host (C ABI, pinned host positions+velocities in and out every step)",
     }
-
-    base = cpu_reference_run(3, 1, budget_s=40.0) if not args.no_cpu_baseline else None
+    # replica sharding: the per-replica results gathered once, after the run (run.py:211-216 logs them per replica)
+    launches = int(st1["kernel_launches"] - st0["kernel_launches"])
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (np.asarray(ekin).tolist(), [float(x) for x in pot], np.asarray(T).tolist()))
+        T = np.concatenate([np.asarray(g[2]) for g in gathered])
+        pot = sum((g[1] for g in gathered), [])
+        t = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        launches = int(t.item())
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    base = cpu_reference_run(wl, 3, 1, budget_s=40.0) if not args.no_cpu_baseline else None
 
     line = {
-        "metric": "MD steps/sec (100k-atom water, fp32)",
+        "metric": METRICS[wl],
         "value": value,
         "unit": "steps/s",
-        "n_gpus": 1,
+        "n_gpus": world,
         "steps": args.steps,
-        "warmup": max(3, args.warmup),
+        "warmup": done,
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
-        "data": "synthetic",
-        "config": workload_config(1),
+        "data": "synthetic" if wl.startswith("water1") else "the reference's own test system (coordinates and parameters from its fixtures), random velocities",
+        "config": workload_config(world, wl),
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+        "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": base,
         "state": {
-            "temperature_K": float(T[0]),
+            "temperature_K": float(np.mean(T)),
             "epot": float(pot[0]),
+            "replicas": nrep_total,
+            "replicas_per_gpu": nrep,
             "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
             "max_neighbours": int(st1["max_neighbours"]),
             "row_capacity": int(st1["row_capacity"]),
             "skin_A": forces.skin,
-            "equilibration_steps": args.equil,
+            "equilibration_steps": equil_done,
+            "warmup_steps_run": done,
+            "pair_kernel_id": pair_kernel_id,
         },
     }
     print(json.dumps(line), flush=True)
@@ -408,6 +538,8 @@ def main():
     ap.add_argument("--equil", type=int, default=600, help="relaxation steps before warm-up (lattice start)")
     ap.add_argument("--e2e-steps", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="water100k", choices=sorted(WORKLOADS),
+                    help="water100k is BASELINE.json's headline; the others are its configs 2, 3, 5 and the 9,999-atom box both arms can run")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -263,3 +263,92 @@ def test_bench_decomposed_dry_run_gloo():
         assert key in line, key
     assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
     assert line["roofline"]["pair_entries_counted"] > 0 and line["scaling"] == "strong"
+
+
+def _worker_replicas(rank, world, port, out):
+    """bench.py's replica-sharded arm (BASELINE config 5 pattern: R replicas over the ranks, no per-step collective, results
+    gathered once) with two gloo ranks on the interpreter build, on the two-replica water fixture."""
+    import argparse
+    import contextlib
+    import io
+    import json
+    import sys
+    import time
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK="0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import bench
+    import test_simt_kernels as T
+    from torchmd_b200 import _lib
+
+    class _Stream:
+        cuda_stream = None
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, *a):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    class _NoSampler:
+        def __init__(self, *a):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+    real_empty = torch.empty
+
+    def empty(*a, **k):
+        k.pop("pin_memory", None)
+        return real_empty(*a, **k)
+
+    _lib._lib = T.load(os.path.join(T.SIMT_DIR, "libtmd_simt.so"))
+    _lib.on_device = lambda t: True
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.current_device = lambda: 0
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = _Event
+    torch.empty = empty
+    bench.DEVICE_OVERRIDE = "cpu"
+    bench.ClockSampler = _NoSampler
+    args = argparse.Namespace(gpus=world, steps=4, warmup=3, equil=0, e2e_steps=2, no_cpu_baseline=True, impl="ours", workload="water291")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+        bench.gpu_arm(args)
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    out.put((rank, json.loads(lines[-1]) if lines else None))
+
+
+def test_bench_replica_sharding_dry_run_gloo():
+    """Two replicas over two ranks: one replica each, no collective inside the steps, one gather at the end; rank 0 prints the
+    line with the per-replica temperatures of both ranks folded in."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_simt_kernels as T
+
+    T.build_simt()
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_replicas, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    results = dict(out.get(timeout=10) for _ in range(world))
+    assert results[1] is None
+    line = results[0]
+    assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
+    assert line["state"]["replicas"] == 2 and line["state"]["replicas_per_gpu"] == 1
+    assert "replicas sharded over 2 GPUs" in line["config"]["parallelism"]

@@ -260,7 +260,7 @@ def test_bench_single_gpu_arm_dry_run(hostsim, monkeypatch, capsys):
     monkeypatch.setattr(bench, "CFG", dict(bench.CFG, cutoff=5.0, switch_dist=4.0))
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.setattr(bench, "DEVICE_OVERRIDE", "cpu")
-    args = argparse.Namespace(gpus=1, steps=6, warmup=3, equil=100, e2e_steps=3, no_cpu_baseline=True, impl="ours")
+    args = argparse.Namespace(gpus=1, steps=6, warmup=3, equil=100, e2e_steps=3, no_cpu_baseline=True, impl="ours", workload="water100k")
     bench.gpu_arm(args)
     line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -269,6 +269,34 @@ def test_bench_single_gpu_arm_dry_run(hostsim, monkeypatch, capsys):
     assert line["gpu_launches"] > 0 and line["value"] > 0 and line["e2e"]["value"] > 0
     assert line["roofline"]["pairs_in_cutoff"] > 0 and line["roofline"]["launches_sampled"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    # the reference's own small test systems as workloads (BASELINE configs 2 and 3), two replicas included
+    for wl in ("water291", "ala2"):
+        args = argparse.Namespace(gpus=1, steps=4, warmup=3, equil=0, e2e_steps=2, no_cpu_baseline=True, impl="ours", workload=wl)
+        bench.gpu_arm(args)
+        line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+        assert line["value"] > 0 and line["metric"] == bench.METRICS[wl] and line["state"]["replicas"] == (2 if wl == "water291" else 1)
+
+
+def test_bench_reference_arm_reports_what_it_measured(monkeypatch, capsys):
+    """--impl reference: `value` is the steps/s measured at the size that ran, `config.natoms` says that size, the O(N^2)
+    extrapolation to 99,999 atoms sits in its own labelled field."""
+    import argparse
+    import json
+
+    import bench
+
+    monkeypatch.setattr(bench, "_probe_threads", lambda: (2, 2))
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="water100k")
+    bench.reference_arm(args)
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    n = line["cpu_baseline"]["measured_natoms"]
+    assert line["config"]["natoms"] == n < 99999 and line["impl"] == "reference"
+    assert abs(line["value"] - 1e3 / line["cpu_baseline"]["ms_per_step_measured"]) < 1e-6 * line["value"]
+    assert line["cpu_baseline"]["extrapolated_99999_atoms_steps_per_s"] < line["value"]
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="ala2")
+    bench.reference_arm(args)
+    line = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    assert line["config"]["natoms"] == 688 and "extrapolated_99999_atoms_steps_per_s" not in line["cpu_baseline"]
 
 
 def test_round2_default_configuration_passes_the_gpu_tests(hostsim_r2, capsys):

@@ -13,6 +13,7 @@ Both return a plain dict of numpy arrays plus a ``TopologyParameters`` factory,
 so neither moleculekit nor the reference checkout is needed.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -169,3 +170,33 @@ def argon_parameters(sysd, precision=torch.float32, device="cpu"):
         precision=precision,
         device=device,
     )
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def golden_system(name, precision=torch.float32, device="cpu"):
+    """A system of the committed parity fixtures (``tests/golden/<name>.npz``: coordinates, box, run settings and the
+    parameter tables the reference's ``Parameters`` held when the fixture was made) as
+    ``(TopologyParameters, coords (N,3) float32, box (3,) float32, terms, cfg)`` -- the reference's own test systems
+    (alanine dipeptide, thrombin-ligand, the water fixture) for ``bench.py --workload`` without the reference checkout."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+
+    def term(key):
+        if "par_" + key + "_idx" not in g:
+            return None
+        return (g["par_" + key + "_idx"], g["par_" + key + "_map"], g["par_" + key + "_params"])
+
+    se = g["par_lj_sigma_eps"]
+    par = TopologyParameters(
+        atom_types=g["par_types"], type_sigma=se[:, 0], type_epsilon=se[:, 1], charges=g["par_charges"], masses=g["par_masses"],
+        bonds=term("bond"), angles=term("angle"), dihedrals=term("dihedral"), impropers=term("improper"),
+        pairs14=term("nonbonded_14"), precision=precision, device=device,
+    )
+
+    def opt(k):
+        v = float(g["cfg_" + k])
+        return None if np.isnan(v) else v
+
+    cfg = dict(cutoff=opt("cutoff"), rfa=bool(g["cfg_rfa"]), switch_dist=opt("switch_dist"))
+    return par, np.asarray(g["coords"], dtype=np.float32), np.asarray(g["box"], dtype=np.float32), [str(t) for t in g["terms"]], cfg
