@@ -333,4 +333,9 @@ def test_nonperiodic_cutoff_with_distinct_replicas():
     F2 = torch.empty_like(pos)
     f.compute(pos2, box, F2)
     assert (F2[1] - F[1]).abs().max().item() < 0.5
-    assert torch.equal(F2[0], F[0]) and torch.equal(F2[2], F[2])
+    from torchmd_b200 import _lib
+    if _lib.lib().tmd_pair_kernel(f._ctx) == 4:
+        # cluster half list: the partners' forces are summed by reductions at L2, in no fixed order
+        assert (F2[0] - F[0]).abs().max().item() < 2e-5 and (F2[2] - F[2]).abs().max().item() < 2e-5
+    else:
+        assert torch.equal(F2[0], F[0]) and torch.equal(F2[2], F[2])

@@ -50,7 +50,7 @@ constexpr int CL_XCAP = 192;   // excluded-partner entries of one cluster the li
 #endif
 constexpr int CL_WARPS = CL_WARPS_N;
 #ifndef CL_MINBLOCKS
-#define CL_MINBLOCKS 3
+#define CL_MINBLOCKS 2  // 120 registers, no spills: 205 us against 217 us at 3 CTAs/SM with spills (B200, profiles/r02_cluster_call5.txt)
 #endif
 constexpr int CLB_WARPS = 4;   // list build: warps per CTA
 constexpr int CLB_MAXSEG = 160;
@@ -227,6 +227,7 @@ __global__ void k_cfinish_sort(DeviceState S) {
 struct ClSeg {
   int begin, len;      // slots [begin, begin + len)
   float sx, sy, sz;    // image shift of these candidates into the cluster's frame
+  int own;             // segment of the cluster's own row: partners chosen per cluster (cyclic half of the row)
 };
 struct ClBuildShared {
   ClSeg seg[CLB_WARPS][CLB_MAXSEG];
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
     if (lane == 0 && g.periodic &&
         (hi[0] - lo[0] > C.max_extent || hi[1] - lo[1] > C.max_extent || hi[2] - lo[2] > C.max_extent))
       atomicOr(fl + F_CLFAIL, 1);
-    // ---- excluded partners of the cluster's atoms (slots >= s0): (slot, bit of the cluster atom)
+    // ---- excluded partners of the cluster's atoms: (slot, bit of the cluster atom)
     int nx = 0;
     if (S.excl_ptr) {
       for (int k = 0; k < CL; ++k) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
           const int e = e0 + lane;
           int sj = -1;
           if (e < e1) sj = C.inv[base + S.excl_idx[e]];
-          const bool keep = sj >= s0;
+          const bool keep = sj >= 0;  // (any slot: with the cyclic half-shell rule a listed partner may sit before the cluster)
           const unsigned bal = __ballot_sync(0xffffffffu, keep);
           if (keep) {
             const int p = nx + __popc(bal & lt);
@@ -347,6 +348,9 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
     const int row_c = S.cell_of[base + C.perm[sb + s0 + first]] / n0;
     const int cy = row_c % n1, cz = row_c / n1;
     const int ry = n1 > 1 ? g.reach[1] : 0, rz = n2 > 1 ? g.reach[2] : 0;
+    const int nrows_total = n1 * n2;
+    const int row_s = start[row_c * n0], row_ncl = (start[(row_c + 1) * n0] - row_s) / CL;  // the own row's clusters
+    const int ci_row = (s0 - row_s) / CL;
     const int nry = 2 * ry + 1, nrows_c = nry * (2 * rz + 1);
     int nseg = 0;
     for (int q0 = 0; q0 < nrows_c; q0 += 32) {
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       // up to three segments per row (x images -1, 0, +1)
       int sbeg[3] = {0, 0, 0}, slen[3] = {0, 0, 0};
       float shx[3] = {0.f, 0.f, 0.f}, shy = 0.f, shz = 0.f;
+      bool own_row = false;
       if (q < nrows_c) {
         const int dy = q % nry - ry, dz = q / nry - rz;
         int yy = cy + dy, zz = cz + dz;
@@ -369,7 +374,15 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
           ok = yy >= 0 && yy < n1 && zz >= 0 && zz < n2;
         }
         const int rr = zz * n1 + yy;
-        if (ok && rr >= row_c) {
+        // Which of two clusters lists the pair?  The one from which the other lies in the NEXT half of the cyclic row
+        // order (the own row: of the cyclic cluster order inside it, see the sweep).  Antisymmetric, and every
+        // cluster gets about half of its surroundings wherever it sits -- a plain "later slots" rule gives the first
+        // planes of a periodic box twice the work of the middle ones and the last planes none.
+        int dr = rr - row_c;
+        if (dr < 0) dr += nrows_total;
+        const bool mine = rr == row_c || 2 * dr < nrows_total || (2 * dr == nrows_total && rr > row_c);
+        own_row = ok && rr == row_c;
+        if (ok && mine) {
           // distance in y, z between the box and the row's slab (with a margin for the binning's rounding)
           const float ylo = g.origin[1] + yy * wy + shy - 1.0e-3f, yhi = ylo + wy + 2.0e-3f;
           const float zlo = g.origin[2] + zz * wz + shz - 1.0e-3f, zhi = zlo + wz + 2.0e-3f;
@@ -400,15 +413,6 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
                 }
               }
             }
-            // later clusters only: in the cluster's own row skip everything up to its last slot
-            if (rr == row_c) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                const int cut = max(sbeg[k], s0 + CL);
-                slen[k] = max(0, sbeg[k] + slen[k] - cut);
-                sbeg[k] = cut;
-              }
-            }
           }
         }
       }
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
         const unsigned bal = __ballot_sync(0xffffffffu, has);
         if (has) {
           const int p = nseg + __popc(bal & lt);
-          if (p < CLB_MAXSEG) sh.seg[w][p] = ClSeg{sbeg[k], slen[k], shx[k], shy, shz};
+          if (p < CLB_MAXSEG) sh.seg[w][p] = ClSeg{sbeg[k], slen[k], shx[k], shy, shz, own_row ? 1 : 0};
         }
         nseg += __popc(bal);
       }
@@ -459,6 +463,12 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
         const float ex = fmaxf(fmaxf(lo[0] - x, x - hi[0]), 0.f), ey = fmaxf(fmaxf(lo[1] - y, y - hi[1]), 0.f),
                     ez = fmaxf(fmaxf(lo[2] - z, z - hi[2]), 0.f);
         take = ex * ex + ey * ey + ez * ez < rl2;  // (padding records are 1e30 away)
+        if (sgm.own) {  // own row: the clusters in the next half of the row's cyclic order
+          const int cj = (sj - row_s) / CL;
+          int dd = cj - ci_row;
+          if (dd < 0) dd += row_ncl;
+          take = take && dd != 0 && (2 * dd < row_ncl || (2 * dd == row_ncl && cj > ci_row));
+        }
         tj = (unsigned)__float_as_int(p.w);
       }
       unsigned xb = 0;
