@@ -28,7 +28,7 @@ VARIANTS = {  # tag -> defines; every interpreter build the tests use (built tog
     "_graph": ["TMD_COND_NODE=1"],  # the device-side switch of the rebuild's conditional node compiled in
     # every opt-in path as the default (what round 2 switches on once the B200 has confirmed it)
     "_r2": ["BT_CULL=1", "BT_PAIRED=1", "TMD_COND_NODE=1", "TMD_DEFAULT_FX=2", "TMD_DEFAULT_OVERLAP=1", "TMD_DEFAULT_FUSEPREP=1", "TMD_DEFAULT_GRAPH=1", "TMD_DEFAULT_CLUSTER=1"],
-    "_cl": ["TMD_DEFAULT_CLUSTER=1"],  # the cluster half-list path (cluster.cuh) over the plain kernels
+    "_cl": ["TMD_DEFAULT_CLUSTER=1", "TMD_COND_NODE=1", "TMD_DEFAULT_GRAPH=1", "TMD_DEFAULT_FUSEPREP=1"],  # the cluster half-list path (cluster.cuh) over the plain kernels
     "_t2": ["FX_SMALLT_MAX_N=2"],
     "_fxu4": ["PAIR_FX_UNROLL=4"],
     "_fx2u2": ["PAIR_FX2_UNROLL=2"],
@@ -43,7 +43,8 @@ def _simt_command(out, defines):
     # the interpreter builds start from the plain kernels (every round-1 opt-in off) so that a variant is compared
     # with the same baseline whatever the product's defaults are; a variant's own defines come later and win
     keys = {d.split("=")[0] for d in defines}
-    base = [d for d in ("TMD_DEFAULT_FX=0", "TMD_DEFAULT_OVERLAP=0", "TMD_DEFAULT_FUSEPREP=0", "BT_CULL=0", "BT_PAIRED=0", "TMD_DEFAULT_CLUSTER=0")
+    base = [d for d in ("TMD_DEFAULT_FX=0", "TMD_DEFAULT_OVERLAP=0", "TMD_DEFAULT_FUSEPREP=0", "BT_CULL=0", "BT_PAIRED=0", "TMD_DEFAULT_CLUSTER=0",
+                        "TMD_DEFAULT_GRAPH=0", "TMD_COND_NODE=0")
             if d.split("=")[0] not in keys]
     return cmd + [f"-D{d}" for d in base + list(defines)] + ["-o", out, os.path.join(SIMT_DIR, "simt_lib.cpp")]
 

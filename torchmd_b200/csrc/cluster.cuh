@@ -49,6 +49,9 @@ constexpr int CL_XCAP = 192;   // excluded-partner entries of one cluster the li
 #define CL_WARPS_N 8
 #endif
 constexpr int CL_WARPS = CL_WARPS_N;
+#ifndef CL_BRANCHFREE
+#define CL_BRANCHFREE 1  // evaluate every packed pair (no per-pair branch): the two pairs of a lane interleave
+#endif
 #ifndef CL_MINBLOCKS
 #define CL_MINBLOCKS 2  // 120 registers, no spills: 205 us against 217 us at 3 CTAs/SM with spills (B200, profiles/r02_cluster_call5.txt)
 #endif
@@ -623,7 +626,7 @@ template <bool ENERGY, bool PERIODIC>
 __global__ void __launch_bounds__(CL_WARPS * 32, CL_MINBLOCKS)
 k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
 #if defined(TMD_SIMT_HOST)
-  __shared__ __attribute__((aligned(128))) unsigned char cl_dyn[CL_WARPS * 2 * CL_SIMT_MAX_ENTRIES * 4 + CL_WARPS * CL_SIMT_MAX_TYPES * CL_H * sizeof(ClTab)];  // (interpreter build: no dynamic window)
+  __shared__ __attribute__((aligned(128))) unsigned char cl_dyn[CL_WARPS * 2 * CL_SIMT_MAX_ENTRIES * 5 + CL_WARPS * CL_SIMT_MAX_TYPES * CL_H * sizeof(ClTab)];  // (interpreter build: no dynamic window)
 #else
   extern __shared__ __align__(128) unsigned char cl_dyn[];
 #endif
@@ -634,8 +637,9 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
   const size_t sb = cl_slot_base(C, r), cb = cl_cluster_base(C, r);
   const int stride_e = C.mcap + C.ecap;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
-  unsigned* buf0 = reinterpret_cast<unsigned*>(cl_dyn) + (size_t)w * 2 * stride_e;
-  ClTab* tab = reinterpret_cast<ClTab*>(cl_dyn + (size_t)CL_WARPS * 2 * stride_e * 4) + (size_t)w * S.ntypes * CL_H;
+  const size_t buf_bytes_h = (size_t)stride_e * 4 + C.mcap;  // entry words + mask bytes of one buffer
+  unsigned char* buf0 = cl_dyn + (size_t)w * 2 * buf_bytes_h;
+  ClTab* tab = reinterpret_cast<ClTab*>(cl_dyn + (size_t)CL_WARPS * 2 * buf_bytes_h) + (size_t)w * S.ntypes * CL_H;
   const smem_addr buf_s = smem_address(buf0);
   const smem_addr bar_s = smem_address(&sh.bar[w][0]);
   if (lane == 0) {
@@ -651,7 +655,8 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
   // consecutive clusters per CTA: chunk of the cluster range, warps interleaved inside it
   const int per_cta = (ncl + gridDim.x - 1) / gridDim.x;
   const int c_begin = blockIdx.x * per_cta, c_end = min(ncl, c_begin + per_cta);
-  F2 ELJ = f2(0.f), NEEL = f2(0.f);
+  F2 ELJ = f2(0.f), NEEL = f2(0.f);   // energies of the current cluster (fp32), folded into fp64 per cluster
+  double acc_lj = 0.0, acc_el = 0.0;
   float ex_lj = 0.f, ex_el = 0.f;  // energies of the pairs decided by cl_exact_pass
   const bool lj_on = (S.pp.terms & T_LJ) != 0, el_on = (S.pp.terms & T_ELEC) != 0;
   // decision thresholds: without a box the reference's s <= s_max itself; in a periodic box the band around it
@@ -671,13 +676,18 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
   // pairs inside (s < s_in), and the pairs in the band are those with u <= bits(s_hi) - bits(s_in)
   const unsigned b_in = __float_as_uint(fmaxf(s_in, 0.f)), b_band = __float_as_uint(fmaxf(s_hi, 0.f)) - b_in;
 
-  auto issue = [&](int c, int which, int2 mt) {  // lane 0: bulk copies of the cluster's two regions into buffer `which`
+  // one buffer: (mcap + ecap) entry words, then mcap mask bytes
+  const unsigned buf_bytes = (unsigned)stride_e * 4u + (unsigned)C.mcap;
+  auto issue = [&](int c, int which, int2 mt) {  // lane 0: bulk copies of the cluster's regions into buffer `which`
     const int nA = mt.x & 0xffffff;
-    const unsigned bytes = (unsigned)(nA + mt.y) * 4u;
-    const smem_addr dst = buf_s + (unsigned)which * (unsigned)stride_e * 4u, bar = bar_s + 8u * which;
+    const unsigned bytes = (unsigned)(nA + mt.y) * 4u + (unsigned)nA;
+    const smem_addr dst = buf_s + (unsigned)which * buf_bytes, bar = bar_s + 8u * which;
     const unsigned* src = C.entries + (cb + c) * (size_t)stride_e;
     mbar_expect_tx(bar, bytes);
-    if (nA) bulk_g2s(dst, src, (unsigned)nA * 4u, bar);
+    if (nA) {
+      bulk_g2s(dst, src, (unsigned)nA * 4u, bar);
+      bulk_g2s(dst + (unsigned)stride_e * 4u, C.masks + (cb + c) * (size_t)C.mcap, (unsigned)nA, bar);
+    }
     if (mt.y) bulk_g2s(dst + (unsigned)nA * 4u, src + C.mcap, (unsigned)mt.y * 4u, bar);
   };
   auto entries_of = [](int2 mt) { return (mt.x & 0xffffff) + mt.y; };
@@ -747,7 +757,8 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
     for (int p = 0; p < CL_H; ++p) FX[p] = FY[p] = FZ[p] = f2(0.f);
 
     const int nbA = (mt_cur.x & 0xffffff) >> 5, nb = entries_of(mt_cur) >> 5;
-    const smem_addr ebuf = buf_s + (unsigned)which * (unsigned)stride_e * 4u;
+    const smem_addr ebuf = buf_s + (unsigned)which * buf_bytes;
+    const smem_addr mbuf = ebuf + (unsigned)stride_e * 4u;
     const unsigned char* __restrict__ mrow = C.masks + (cb + c) * (size_t)C.mcap;
     if (nb) mbar_wait(bar_s + 8u * which, (phase >> which) & 1u);
     __syncwarp();
@@ -755,10 +766,8 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
     // base addresses the loop uses, kept in registers (otherwise re-derived from the parameter block per entry)
     unsigned long long rec_base = PERIODIC ? reinterpret_cast<unsigned long long>(xf) : reinterpret_cast<unsigned long long>(xq);
     unsigned long long f_base = reinterpret_cast<unsigned long long>(fout);
-    unsigned long long m_base = reinterpret_cast<unsigned long long>(mrow);
     TMD_PIN_L(rec_base);
     TMD_PIN_L(f_base);
-    TMD_PIN_L(m_base);
     const unsigned nslots_cap = (unsigned)C.slots;
 
     // one partner (record rj: float x, y, z, q or fixed-point X, Y, Z, q bits) against the cluster
@@ -788,12 +797,14 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
           const unsigned u0 = __float_as_uint(s.x) - b_in, u1 = __float_as_uint(s.y) - b_in;
           in0 = m0 && (int)u0 < 0;
           in1 = m1 && (int)u1 < 0;
-          u_min = min(u_min, min(m0 ? u0 : 0xffffffffu, m1 ? u1 : 0xffffffffu));
+          // (pairs a mask switches off are not filtered here: one of them inside the band only costs a pass that
+          //  re-checks the masks)
+          u_min = min(u_min, min(u0, u1));
         } else {
           in0 = m0 && s.x <= s_in;
           in1 = m1 && s.y <= s_in;
         }
-        if (in0 || in1) {
+        if (CL_BRANCHFREE || in0 || in1) {
           const ClTab tb = tab[tj * CL_H + p];
           const F2 nqq = f2_mul(NQI[p], f2(qj));
           F2 elj, neel;
@@ -816,11 +827,7 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
     };
     // (float4 and int4 records alike: 16 bytes at slot * 16)
     auto record_of = [&](unsigned en) { return ldg_s32x4(mad_wide_u32(en & 0xffffffu, 16u, rec_base)); };
-    auto mask_of = [&](int e) {
-      unsigned v;
-      v = *reinterpret_cast<const unsigned char*>(m_base + (unsigned)e);
-      return v;
-    };
+    auto mask_of = [&](int e) { return (unsigned)lds_u8(mbuf + (unsigned)e); };
 
     // batches: entries from shared memory, partner records gathered one batch ahead
     if (nb) {
@@ -876,13 +883,21 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
       ex_lj += ee.x;
       ex_el += ee.y;
     }
+    if (ENERGY) {
+      acc_lj += (double)(ELJ.x + ELJ.y) + (double)ex_lj;
+      acc_el += (double)ex_el - (double)(NEEL.x + NEEL.y);
+      ELJ = f2(0.f);
+      NEEL = f2(0.f);
+      ex_lj = 0.f;
+      ex_el = 0.f;
+    }
     which ^= 1;
   }
   if (ENERGY) {
     double* E = energies + (size_t)r * TMD_NUM_ENERGIES;
     __syncthreads();
-    if (el_on) block_accumulate<CL_WARPS>((double)ex_el - (double)(NEEL.x + NEEL.y), E + TMD_E_ELECTROSTATICS, sh.red);
-    if (lj_on) block_accumulate<CL_WARPS>((double)ex_lj + (double)(ELJ.x + ELJ.y), E + TMD_E_LJ, sh.red);
+    if (el_on) block_accumulate<CL_WARPS>(acc_el, E + TMD_E_ELECTROSTATICS, sh.red);
+    if (lj_on) block_accumulate<CL_WARPS>(acc_lj, E + TMD_E_LJ, sh.red);
   }
 }
 

@@ -1,0 +1,60 @@
+// fused.cuh -- integrator kernels fused with the force assembly (cluster path, tmd_md_steps).
+//
+// After the pair kernel of a step the per-atom work of the reference's loop body
+// (integrator.py:115-120: forces.compute's bonded part, langevin, _second_VV) is one pass over the atoms:
+// bring the atom's pair force home from slot order, add its bonded terms (fp64, atom-centric: bonded.cuh),
+// store the total force, kick.  One launch and one round trip of the forces through memory instead of two.
+#pragma once
+#include "bonded.cuh"
+#include "cluster.cuh"
+#include "integrate.cuh"
+
+namespace tmd {
+
+template <bool THERMOSTAT, bool KINETIC>
+__global__ void __launch_bounds__(BONDED_THREADS)
+k_bonded_vv_second(DeviceState S, BondedTables T, const float* __restrict__ q_scaled, const float* __restrict__ pos,
+                   float* __restrict__ forces, double* __restrict__ energies, float* __restrict__ vel,
+                   const float* __restrict__ masses, float dt, float hdt, float neg_gamma, const float* __restrict__ vcoeff,
+                   const float* __restrict__ noise, uint64_t seed, uint64_t step_offset, double* __restrict__ ke) {
+  const int r = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // whole system (cluster path)
+  const uint64_t step = step_offset + S.counters[1];
+  BondedEnergies E;
+  double ek = 0.0;
+  if (i < S.natoms) {
+    const size_t slot = (size_t)r * S.natoms + i;
+    const size_t a = slot * 3;
+    Vec3d fb = {0., 0., 0.};
+    if (T.atom_ptr && T.atom_ptr[i + 1] > T.atom_ptr[i]) fb = bonded_force_on_atom(S, T, q_scaled, pos, r, i, E);
+    const float4 pf = S.cl.f[(size_t)r * (S.cl.slots + 1) + S.cl.inv[slot]];
+    const float f[3] = {(float)((double)pf.x + fb.x), (float)((double)pf.y + fb.y), (float)((double)pf.z + fb.z)};
+    const float m = masses[i];
+    float xi[3] = {0.f, 0.f, 0.f};
+    float vc = 0.f;
+    if (THERMOSTAT) {
+      vc = vcoeff[i];
+      if (noise) {
+        xi[0] = noise[a]; xi[1] = noise[a + 1]; xi[2] = noise[a + 2];
+      } else {
+        normal3(seed, step, slot, xi);
+      }
+    }
+    float v2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      forces[a + d] = f[d];
+      float v = vel[a + d];
+      if (THERMOSTAT) v = add_rn(v, add_rn(mul_rn(mul_rn(neg_gamma, v), dt), mul_rn(xi[d], vc)));
+      v = add_rn(v, mul_rn(hdt, div_rn(f[d], m)));
+      vel[a + d] = v;
+      v2 += v * v;
+    }
+    if (KINETIC) ek = 0.5 * (double)m * (double)v2;
+  }
+  __shared__ double red[BONDED_THREADS / 32];
+  if (KINETIC) block_accumulate<BONDED_THREADS / 32>(ek, ke + r, red);
+  if (energies && T.atom_ptr) bonded_energy_reduce(S, T, r, E, energies, red);
+}
+
+}  // namespace tmd

@@ -62,10 +62,9 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, float x, float y, fl
 // ---- every call ---------------------------------------------------------------
 // -DTMD_COND_NODE=1 compiles the device-side switch of the rebuild's CUDA-graph conditional node
 // (cudaGraphSetConditional, a driver-resolved builtin: the module then carries an undefined symbol
-// that is bound at load time).  Off in the default build until a B200 has loaded such a module:
-// the standing library contains nothing that has not run on the hardware.
+// that is bound at load time).
 #ifndef TMD_COND_NODE
-#define TMD_COND_NODE 0
+#define TMD_COND_NODE 1  // (a module with the device-side switch loaded and ran the whole suite on a B200: round 2, call 2)
 #endif
 // One atom of the per-call preparation: displacement trigger against the positions of the last
 // rebuild, far-position check, refresh of the sorted records (float and fixed-point), largest

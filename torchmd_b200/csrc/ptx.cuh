@@ -101,6 +101,11 @@ __device__ __forceinline__ void mbar_wait(smem_addr bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ unsigned lds_u8(smem_addr a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ unsigned lds_u32(smem_addr a) {
   unsigned v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -146,6 +151,7 @@ inline void mbar_expect_tx(smem_addr, unsigned) {}
 inline void bulk_g2s(smem_addr dst, const void* src, unsigned bytes, smem_addr) { memcpy(const_cast<char*>(dst), src, bytes); }
 inline void mbar_wait(smem_addr, unsigned) {}  // (the host copy above is synchronous)
 inline unsigned lds_u32(smem_addr a) { return *reinterpret_cast<const unsigned*>(a); }
+inline unsigned lds_u8(smem_addr a) { return *reinterpret_cast<const unsigned char*>(a); }
 inline void red_add_f32x4(float4* p, float x, float y, float z) {  // (interpreter threads run one at a time)
   p->x += x;
   p->y += y;

@@ -20,6 +20,7 @@
 #include "neighbor.cuh"
 #include "pair.cuh"
 #include "cluster.cuh"
+#include "fused.cuh"
 
 using namespace tmd;
 
@@ -63,7 +64,7 @@ int fail(int code, const std::string& msg) {
 #define TMD_DEFAULT_COND 0      // TMD_B200_COND: rebuild as a conditional node when captured (needs TMD_COND_NODE)
 #endif
 #ifndef TMD_DEFAULT_GRAPH
-#define TMD_DEFAULT_GRAPH 0     // TMD_B200_GRAPH: tmd_md_steps replays a captured step
+#define TMD_DEFAULT_GRAPH 1     // TMD_B200_GRAPH: tmd_md_steps replays a captured step
 #endif
 #ifndef TMD_DEFAULT_FUSEPREP
 #define TMD_DEFAULT_FUSEPREP 1  // TMD_B200_FUSEPREP: integrate + prepare in one kernel, bonded fold in the second kick
@@ -174,6 +175,13 @@ struct CtxPriv {
   cudaGraphConditionalHandle prepared_cond = 0; // and this handle already handed to the kernel
   bool dirty = true;
   size_t nbr_entries = 0;
+  // cluster path inside tmd_md_steps: the bonded kernel is folded into the second half-kick (fused.cuh)
+  int64_t last_body_launches = 0; // kernels the last captured force call put into the rebuild's conditional body
+  bool defer_bonded = false;      // set by tmd_md_steps for the force call it is about to make
+  bool bonded_deferred = false;   // enqueue_forces left the bonded terms (and the unsort) to enqueue_vv_second
+  double* deferred_energies = nullptr;
+  BondedTables deferred_tables{};
+  const float* deferred_pos = nullptr;
   // cluster path: owned buffers behind ctx->d.cl
   std::vector<void*> cl_bufs;
   int cl_blocks = 0;        // CTAs of k_cpair per replica
@@ -640,7 +648,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
         TMD_CUDA(cudaMemcpy(cl.inv, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
       }
       // launch shape of k_cpair: persistent CTAs, as many as fit
-      pv.cl_smem = (size_t)CL_WARPS * 2 * (cl.mcap + cl.ecap) * sizeof(unsigned) + (size_t)CL_WARPS * d.ntypes * CL_H * sizeof(ClTab);
+      pv.cl_smem = (size_t)CL_WARPS * 2 * ((size_t)(cl.mcap + cl.ecap) * sizeof(unsigned) + cl.mcap) + (size_t)CL_WARPS * d.ntypes * CL_H * sizeof(ClTab);
 #if !defined(TMD_SIMT_HOST)
       if (pv.cl_smem > (size_t)180 * 1024) return fail(TMD_ERR_UNSUPPORTED, "cluster lists too long for the shared-memory staging");
       int nsm = 0, per_sm = 0;
@@ -896,6 +904,8 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       rs = priv(ctx).helper;
       in_body = true;
     }
+    const int64_t body_l0 = ctx->launches;
+    priv(ctx).last_body_launches = 0;
     if (d.cl.on) {
       // cluster path: cell binning as before, then the row-padded sort and the cluster lists (cluster.cuh)
       if (need_bounds) {
@@ -946,6 +956,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_build_list");
     }
     if (in_body) {
+      priv(ctx).last_body_launches = ctx->launches - body_l0;
       cudaGraph_t body = nullptr;
       TMD_CUDA(cudaStreamEndCapture(priv(ctx).helper, &body));
       TMD_CUDA(cudaStreamUpdateCaptureDependencies(st, &cond_node, 1, cudaStreamSetCaptureDependencies));
@@ -985,6 +996,13 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       launch(k_add_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
       TMD_LAUNCHED(ctx, "k_add_bonded");
     }
+  } else if (d.cl.on && ctx->pair_mask && priv(ctx).defer_bonded && d.own_all) {
+    // tmd_md_steps: bonded terms, the trip home from slot order and the second half-kick are one kernel
+    priv(ctx).bonded_deferred = true;
+    if (!have_bonded) memset(&T, 0, sizeof(T));
+    priv(ctx).deferred_tables = T;
+    priv(ctx).deferred_energies = energies;
+    priv(ctx).deferred_pos = pos;
   } else if (have_bonded) {
     // (cluster path: this kernel also brings the pair forces home from slot order)
     launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, d, T, ctx->q, pos, forces, energies, nullptr);
@@ -1033,6 +1051,22 @@ static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, cons
   const unsigned long long* ctr = ctx->d.counters;
   const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-gamma);
   if (ke) TMD_CUDA(cudaMemsetAsync(ke, 0, (size_t)ctx->nrep * sizeof(double), st));
+  if (priv(ctx).bonded_deferred) {
+    CtxPriv& pv = priv(ctx);
+    pv.bonded_deferred = false;
+    float* fw = const_cast<float*>(forces);  // (tmd_md_steps owns this buffer: the force call's output)
+    const dim3 gb = atoms_grid(ctx, BONDED_THREADS);
+    const BondedTables& T = pv.deferred_tables;
+    if (thermo) {
+      if (ke) launch(k_bonded_vv_second<true, true>, gb, BONDED_THREADS, st, ctx->d, T, ctx->q, pv.deferred_pos, fw, pv.deferred_energies, vel, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+      else launch(k_bonded_vv_second<true, false>, gb, BONDED_THREADS, st, ctx->d, T, ctx->q, pv.deferred_pos, fw, pv.deferred_energies, vel, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    } else {
+      if (ke) launch(k_bonded_vv_second<false, true>, gb, BONDED_THREADS, st, ctx->d, T, ctx->q, pv.deferred_pos, fw, pv.deferred_energies, vel, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+      else launch(k_bonded_vv_second<false, false>, gb, BONDED_THREADS, st, ctx->d, T, ctx->q, pv.deferred_pos, fw, pv.deferred_energies, vel, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke);
+    }
+    TMD_LAUNCHED(ctx, "k_bonded_vv_second");
+    return TMD_OK;
+  }
   if (priv(ctx).fold_pending) {
     priv(ctx).fold_pending = false;
     float* fw = const_cast<float*>(forces);  // (tmd_md_steps owns this buffer: it handed it to enqueue_forces as the output)
@@ -1108,6 +1142,12 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
   CtxPriv& pv = priv(ctx);
   pv.prepared = false;
   pv.fold_pending = false;
+  pv.bonded_deferred = false;
+  struct DeferScope {  // only inside tmd_md_steps does a vv_second follow every force call
+    CtxPriv& p;
+    explicit DeferScope(CtxPriv& q) : p(q) { p.defer_bonded = true; }
+    ~DeferScope() { p.defer_bonded = false; }
+  } defer_scope(pv);
   struct FoldScope {  // only inside tmd_md_steps does a vv_second follow every force call
     CtxPriv& p;
     explicit FoldScope(CtxPriv& q, bool on) : p(q) { p.fold_next = on; }
@@ -1139,7 +1179,7 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
           if (rc) return rc;
           if (ce != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
           TMD_CUDA(cudaGraphInstantiate(&pv.exec[k], pv.graph[k], 0));
-          pv.step_launches[k] = ctx->launches - l0;
+          pv.step_launches[k] = ctx->launches - l0 - pv.last_body_launches;  // (the body runs on rebuild steps only: not counted)
           ctx->launches = l0;  // the capture launched nothing; replays are counted below
           ctx->force_calls = f0;
         }
