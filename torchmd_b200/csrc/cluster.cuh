@@ -63,6 +63,29 @@ constexpr int CL_SIMT_MAX_TYPES = 64;       // ... and atom types its static tab
 __device__ __forceinline__ size_t cl_slot_base(const ClusterState& C, int r) { return (size_t)r * (C.slots + 1); }
 __device__ __forceinline__ size_t cl_cluster_base(const ClusterState& C, int r) { return (size_t)r * C.nclusters_cap; }
 
+// ---- rebuild, phase 1: cell of every atom, arrival slot in the cell's bucket ------------------------
+constexpr int CL_BUCKET = 32;  // atoms a cell's bucket holds (cells of ~4 A hold about six in a liquid)
+__global__ void k_cbin(DeviceState S, const float* __restrict__ pos) {
+  const int r = blockIdx.y;
+  const int parity = (int)(S.counters[0] & 1ull);
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const int ncells = S.grid[r].ncells;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.natoms; i += gridDim.x * blockDim.x) {
+    const size_t a = (size_t)r * S.natoms + i;
+    const float x = pos[a * 3 + 0], y = pos[a * 3 + 1], z = pos[a * 3 + 2];
+    int c = cell_of_point(S.grid[r], x, y, z);
+    if (!isfinite(x + y + z)) {  // blown-up coordinates: report, and spread them so no cell degenerates
+      S.flags[r * F_COUNT + F_FARPOS] = 1;
+      c = i % ncells;
+    }
+    S.cell_of[a] = c;
+    const int k = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
+    if (k < CL_BUCKET) S.cl.bucket[((size_t)r * S.max_cells + c) * CL_BUCKET + k] = i;
+    else atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 32);  // a cell this crowded: not a system for this path
+    S.pos_ref[a] = make_float4(x, y, z, 0.0f);
+  }
+}
+
 // ---- rebuild, phase 2: row-padded exclusive scan of the cell counts (one CTA per replica) --------
 // cell_start[c] = first slot of cell c; the last cell of every row (cells of equal y, z) is followed by
 // padding up to a multiple of CL slots.  cl.nslots[r] = slots in use (a multiple of CL).
@@ -118,10 +141,9 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   }
 }
 
-// ---- rebuild, phase 3: scatter + order every cell by x, emit the slot records ---------------------
-// One warp per cell.  (k_bin of neighbor.cuh has left cell_of, rank -- the arrival order inside the cell --
-// and pos_ref.)  Slots of a cell: atoms ordered by folded x (ties by atom index: deterministic), then, for
-// the last cell of a row, the padding records.
+// ---- rebuild, phase 3: order every cell by x, emit the slot records -------------------------------------
+// One warp per cell.  Slots of a cell: its atoms ordered by folded x (ties by atom index: deterministic), then,
+// for the last cell of a row, the padding records.
 __global__ void k_csort(DeviceState S) {
   const int r = blockIdx.y;
   const int parity = (int)(S.counters[0] & 1ull);
@@ -134,96 +156,49 @@ __global__ void k_csort(DeviceState S) {
   const size_t base = (size_t)r * S.natoms, sb = cl_slot_base(C, r);
   int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  int* perm = C.perm + sb;
   for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
-    const int b = start[c], n = cnt[c], cap = start[c + 1] - b;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      // k_cplace scattered the cell's atoms into perm[b ..] in arrival order; here: rank by (folded x, index)
-      int i = -1;
-      float x = 0.f;
-      if (e < n) {
-        i = perm[b + e];
-        const float xr = S.pos_ref[base + i].x;
-        x = g.periodic ? xr - g.L[0] * floorf(xr * g.invL[0]) : xr;
+    const int b = start[c], n = min(cnt[c], CL_BUCKET), cap = start[c + 1] - b;
+    __syncwarp();
+    if (lane == 0) cnt[c] = 0;  // counters clean for the next build
+    int i = -1;
+    float x = 0.f;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) {
+      i = C.bucket[((size_t)r * S.max_cells + c) * CL_BUCKET + lane];
+      p = S.pos_ref[base + i];
+      x = g.periodic ? p.x - g.L[0] * floorf(p.x * g.invL[0]) : p.x;
+    }
+    int rk = 0;
+    for (int q = 0; q < n; ++q) {
+      const float xo = __shfl_sync(0xffffffffu, x, q);
+      const int io = __shfl_sync(0xffffffffu, i, q);
+      rk += (xo < x || (xo == x && io < i)) ? 1 : 0;
+    }
+    if (lane < n) {
+      const int s = b + rk;
+      C.inv[base + i] = s;
+      C.perm[sb + s] = i;
+      C.xq[sb + s] = make_float4(p.x, p.y, p.z, S.q[i]);
+      C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (C.xf)
+        C.xf[sb + s] = make_int4(fx_encode(p.x, g.fx_inv[0]), fx_encode(p.y, g.fx_inv[1]), fx_encode(p.z, g.fx_inv[2]),
+                                 __float_as_int(S.q[i]));
+      float wx = p.x, wy = p.y, wz = p.z;
+      if (g.periodic) {
+        wx -= g.L[0] * floorf(wx * g.invL[0]);
+        wy -= g.L[1] * floorf(wy * g.invL[1]);
+        wz -= g.L[2] * floorf(wz * g.invL[2]);
       }
-      int rk = 0;
-      for (int m0 = 0; m0 < n; m0 += 32) {
-        const int m = m0 + lane;
-        int im = -1;
-        float xm = 0.f;
-        if (m < n) {
-          im = perm[b + m];
-          const float xr = S.pos_ref[base + im].x;
-          xm = g.periodic ? xr - g.L[0] * floorf(xr * g.invL[0]) : xr;
-        }
-        const int lim = min(32, n - m0);
-        for (int q = 0; q < lim; ++q) {
-          const float xo = __shfl_sync(0xffffffffu, xm, q);
-          const int io = __shfl_sync(0xffffffffu, im, q);
-          rk += (xo < x || (xo == x && io < i)) ? 1 : 0;
-        }
-      }
-      if (e < n) {
-        const float4 p = S.pos_ref[base + i];
-        const int s = b + rk;
-        C.inv[base + i] = s;
-        C.tmp[sb + s] = i;  // (perm itself is still being read by the other lanes / chunks)
-        C.xq[sb + s] = make_float4(p.x, p.y, p.z, S.q[i]);
-        C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (C.xf)
-          C.xf[sb + s] = make_int4(fx_encode(p.x, g.fx_inv[0]), fx_encode(p.y, g.fx_inv[1]), fx_encode(p.z, g.fx_inv[2]),
-                                   __float_as_int(S.q[i]));
-        float wx = p.x, wy = p.y, wz = p.z;
-        if (g.periodic) {
-          wx -= g.L[0] * floorf(wx * g.invL[0]);
-          wy -= g.L[1] * floorf(wy * g.invL[1]);
-          wz -= g.L[2] * floorf(wz * g.invL[2]);
-        }
-        C.xw[sb + s] = make_float4(wx, wy, wz, __int_as_float(S.type[i]));
-      }
+      C.xw[sb + s] = make_float4(wx, wy, wz, __int_as_float(S.type[i]));
     }
     for (int e = n + lane; e < cap; e += 32) {  // row padding: finite records that no mask ever selects
-      C.tmp[sb + b + e] = -1;
+      C.perm[sb + b + e] = -1;
       C.xq[sb + b + e] = make_float4(0.f, 0.f, 0.f, 0.f);
       C.f[sb + b + e] = make_float4(0.f, 0.f, 0.f, 0.f);
       C.xw[sb + b + e] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.f);
       if (C.xf) C.xf[sb + b + e] = make_int4(0, 0, 0, 0);
     }
   }
-}
-// counting sort scatter into perm (slot order = arrival order inside a cell, fixed up by k_csort)
-__global__ void k_cplace(DeviceState S) {
-  const int r = blockIdx.y;
-  const int parity = (int)(S.counters[0] & 1ull);
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  const size_t sb = cl_slot_base(S.cl, r);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.natoms; i += gridDim.x * blockDim.x) {
-    const size_t a = (size_t)r * S.natoms + i;
-    S.cl.perm[sb + start[S.cell_of[a]] + S.rank[a]] = i;
-  }
-}
-// perm <- tmp, counters cleared for the next build, dummy record
-__global__ void k_cfinish_sort(DeviceState S) {
-  const int r = blockIdx.y;
-  const int parity = (int)(S.counters[0] & 1ull);
-  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
-  const ClusterState& C = S.cl;
-  const size_t sb = cl_slot_base(C, r);
-  const int ns = C.nslots[r];
-  int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= C.slots; s += gridDim.x * blockDim.x) {
-    if (s < ns) C.perm[sb + s] = C.tmp[sb + s];
-    else {
-      C.perm[sb + s] = -1;
-      C.xq[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);  // incl. the dummy record `slots`
-      C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-      C.xw[sb + s] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.f);
-      if (C.xf) C.xf[sb + s] = make_int4(0, 0, 0, 0);
-    }
-  }
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < S.grid[r].ncells; c += gridDim.x * blockDim.x) cnt[c] = 0;
 }
 
 // ---- rebuild, phase 4: the cluster lists -------------------------------------------------------------
@@ -319,6 +294,14 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       }
     }
     __syncwarp();
+    // slot range of the set: most candidates lie outside it and skip the search
+    int xlo = 0x7fffffff, xhi = -1;
+    for (int k = lane; k < nx; k += 32) {
+      xlo = min(xlo, sh.xslot[w][k]);
+      xhi = max(xhi, sh.xslot[w][k]);
+    }
+    xlo = __reduce_min_sync(0xffffffffu, xlo);
+    xhi = __reduce_max_sync(0xffffffffu, xhi);
     auto excluded_bits = [&](int sj) {
       unsigned m = 0;
       for (int k = 0; k < nx; ++k)
@@ -475,7 +458,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
         tj = (unsigned)__float_as_int(p.w);
       }
       unsigned xb = 0;
-      if (take && nx) xb = excluded_bits(sj);
+      if (take && sj >= xlo && sj <= xhi) xb = excluded_bits(sj);
       const bool plain = take && xb == 0;
       const unsigned m = realmask & ~xb;
       const bool special = take && xb != 0 && m != 0;

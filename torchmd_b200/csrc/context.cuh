@@ -57,7 +57,7 @@ struct ClusterState {
   float4* xw;          // coordinates folded into the box at the last build; .w = atom type (bits)
   int4* xf;            // fixed-point records (physics.cuh, fx_encode) of a periodic box: X, Y, Z + charge bits (every step)
   int* perm;           // slot -> atom (-1: padding)
-  int* tmp;            // scratch of the sort
+  int* bucket;         // [(rep*max_cells + cell) * CL_BUCKET + k] atoms of a cell in arrival order (rebuild scratch)
   int* inv;            // [rep*natoms + i] atom -> slot
   int* nslots;         // [rep] slots in use after the last build
   int2* meta;          // [rep*nclusters_cap + c] (masked entries | mask of real atoms << 24, plain entries), counts padded to 32

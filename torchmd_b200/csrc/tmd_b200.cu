@@ -526,7 +526,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     max_cells = std::max<long long>(max_cells, g.ncells);
     if (ctx->periodic) max_density = std::max(max_density, N / vol);
   }
-  if (!ctx->periodic && has_cut) max_cells = 64 * 64 * 64;
+  if (!ctx->periodic && has_cut) max_cells = use_cluster ? 40 * 40 * 40 : 64 * 64 * 64;  // (cluster path: a bucket per cell)
   d.max_cells = (int)max_cells;
 
   // guard-free minimum image is valid iff no listed pair can be further than 0.45 L apart
@@ -606,7 +606,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     if (use_cluster) {
       long long rows = 1;
       for (int r = 0; r < R; ++r) rows = std::max<long long>(rows, (long long)grids[r].n[1] * grids[r].n[2]);
-      if (!ctx->periodic) rows = 64 * 64;  // the device sizes that grid
+      if (!ctx->periodic) rows = 40 * 40;  // the device sizes that grid
       const long long slots = ((long long)N + rows * (CL - 1) + CL - 1) / CL * CL;
       cl.on = 1;
       cl.slots = (int)slots;
@@ -632,7 +632,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       const size_t ne = C1 * (size_t)(cl.mcap + cl.ecap);
       if (ne * 4 > ((size_t)64 << 30)) return fail(TMD_ERR_UNSUPPORTED, "cluster lists would exceed 64 GiB");
       bool ok = grab(&cl.xq, S1) && grab(&cl.f, S1) && grab(&cl.xw, S1) && (!ctx->periodic || grab(&cl.xf, S1)) &&
-                grab(&cl.perm, S1) && grab(&cl.tmp, S1) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
+                grab(&cl.perm, S1) && grab(&cl.bucket, (size_t)R * d.max_cells * CL_BUCKET) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
                 grab(&cl.meta, C1) && grab(&cl.entries, ne + 64) && grab(&cl.masks, C1 * (size_t)cl.mcap + 64);
       if (!ok) return fail(TMD_ERR_CUDA, "cudaMalloc of the cluster lists failed");
       TMD_CUDA(cudaMemset(cl.xq, 0, S1 * sizeof(float4)));
@@ -914,16 +914,12 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
         launch(k_grid, (R + 63) / 64, 64, rs, d);
         TMD_LAUNCHED(ctx, "k_grid");
       }
-      launch(k_bin, atoms_grid(ctx, 256), 256, rs, d, pos);
-      TMD_LAUNCHED(ctx, "k_bin");
+      launch(k_cbin, dim3(std::min((N + 255) / 256, 148 * 8), R), 256, rs, d, pos);
+      TMD_LAUNCHED(ctx, "k_cbin");
       launch(k_cscan, R, 1024, rs, d);
       TMD_LAUNCHED(ctx, "k_cscan");
-      launch(k_cplace, dim3(std::min((N + 255) / 256, 148 * 8), R), 256, rs, d);
-      TMD_LAUNCHED(ctx, "k_cplace");
       launch(k_csort, dim3(std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8)), R), 256, rs, d);
       TMD_LAUNCHED(ctx, "k_csort");
-      launch(k_cfinish_sort, dim3(std::min((d.cl.slots + 256) / 256, 148 * 8), R), 256, rs, d);
-      TMD_LAUNCHED(ctx, "k_cfinish_sort");
       launch(k_cbuild, dim3(std::max(1, std::min((d.cl.nclusters_cap + CLB_WARPS - 1) / CLB_WARPS, 148 * 16)), R), CLB_WARPS * 32, rs, d);
       TMD_LAUNCHED(ctx, "k_cbuild");
     } else if (ctx->coop_blocks > 0 && !in_body) {
