@@ -352,3 +352,79 @@ def test_bench_replica_sharding_dry_run_gloo():
     assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
     assert line["state"]["replicas"] == 2 and line["state"]["replicas_per_gpu"] == 1
     assert "replicas sharded over 2 GPUs" in line["config"]["parallelism"]
+
+
+def _worker_integrator_cluster(rank, world, port, out):
+    """DecomposedIntegrator on the cluster half-list path (lists only for pairs that touch an owned atom) over gloo,
+    against the undecomposed Integrator: same trajectory up to the summation order of the force reductions."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    import test_simt_kernels as T
+    from test_simt_cluster import CFG, TERMS, tiled_water
+    from torchmd_b200 import Forces, Integrator, System, _lib, maxwell_boltzmann, testsystems
+    from torchmd_b200.domain import DecomposedIntegrator
+
+    class _Stream:
+        cuda_stream = None
+
+    _lib._lib = T.load(os.path.join(T.SIMT_DIR, "libtmd_simt_cl.so"))  # (built by the parent)
+    _lib.on_device = lambda t: True
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.current_device = lambda: 0
+    torch.cuda.synchronize = lambda *a, **k: None
+    sysd = tiled_water(2)
+    n = len(sysd["coords"])
+
+    def make():
+        par = testsystems.water_parameters(sysd)
+        s = System(n, 1, torch.float32, "cpu")
+        s.set_positions(np.array(sysd["coords"], dtype=np.float32))
+        s.set_box(sysd["box"])
+        torch.manual_seed(4)
+        s.set_velocities(maxwell_boltzmann(par.masses, 300.0, 1))
+        return par, s, Forces(par, terms=TERMS, **CFG, skin=0.3)
+
+    par, s1, f1 = make()
+    f1.compute(s1.pos, s1.box, s1.forces)
+    torch.manual_seed(9)
+    single = Integrator(s1, f1, 1.0, "cpu", gamma=0.1, T=300.0)
+    par, s2, f2 = make()
+    f2.compute(s2.pos, s2.box, s2.forces)
+    torch.manual_seed(9)
+    dec = DecomposedIntegrator(s2, f2, 1.0, "cpu", gamma=0.1, T=300.0, use_graph=False)
+    ok = single.seed == dec.integ.seed
+    e1 = single.step(8)
+    e2 = dec.step(8)
+    lo, hi = dec.dec.lo, dec.dec.hi
+    ok = ok and _lib.lib().tmd_pair_kernel(f2._ctx) == 4 and _lib.lib().tmd_pair_kernel(f1._ctx) == 4
+    ok = ok and (s1.pos - s2.pos).abs().max().item() < 5e-5 and (s1.vel[:, lo:hi] - s2.vel[:, lo:hi]).abs().max().item() < 5e-4
+    ok = ok and abs(e1[1][0] - e2[1][0]) <= 1e-5 * abs(e1[1][0]) + 2e-2
+    ok = ok and f2.stats()["rebuilds"] >= 2
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_decomposed_integrator_cluster_path_gloo():
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_simt_kernels as T
+
+    T.build_simt("_cl", T.VARIANTS["_cl"])
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_integrator_cluster, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    results = dict(out.get(timeout=10) for _ in range(world))
+    assert results == {0: True, 1: True}

@@ -188,3 +188,36 @@ def test_cluster_md_steps_follow_the_full_list_trajectory(host_cl, monkeypatch):
     assert (out[0][0] - out[1][0]).abs().max().item() < 5e-5
     assert (out[0][1] - out[1][1]).abs().max().item() < 5e-4
     assert abs(out[0][3][0] - out[1][3][0]) < 1e-5 * abs(out[1][3][0]) + 5e-3
+
+
+def test_cluster_path_with_owned_atom_ranges(host_cl):
+    """Decomposed runs: a context that owns a range of atoms builds lists only for the pairs that touch an owned atom;
+    its forces on the owned atoms are the full forces, and the ranks' energy shares add up to the total."""
+    from torchmd_b200 import Forces, System, _lib, testsystems
+
+    sysd = tiled_water(2)
+    coords = np.array(sysd["coords"], dtype=np.float32)
+    system, forces, e_full = _compute(sysd, coords, host_cl)
+    assert host_cl.tmd_pair_kernel(forces._ctx) == 4
+    F_full = system.forces.clone()
+    n = len(coords)
+    world = 3
+    chunk = -(-n // world)
+    e_sum = {k: 0.0 for k in TERMS}
+    for rank in range(world):
+        lo, hi = rank * chunk, min(n, (rank + 1) * chunk)
+        par = testsystems.water_parameters(sysd, device="cpu")
+        s2 = System(n, 1, torch.float32, "cpu")
+        s2.set_positions(coords)
+        s2.set_box(sysd["box"])
+        f2 = Forces(par, terms=TERMS, **CFG)
+        ctx = f2._ensure_ctx(s2.pos)
+        f2._ensure_box(s2.box)
+        _lib.check(host_cl.tmd_set_owned_atoms(ctx, lo, hi - lo))
+        e = f2.compute(s2.pos, s2.box, s2.forces, returnDetails=True)[0]
+        assert host_cl.tmd_pair_kernel(ctx) == 4
+        assert (s2.forces[0, lo:hi] - F_full[0, lo:hi]).abs().max().item() < 3e-5
+        for k in TERMS:
+            e_sum[k] += e[k]
+    for k in TERMS:
+        assert abs(e_sum[k] - e_full[k]) <= 1e-6 * abs(e_full[k]) + 2e-3, (k, e_sum[k], e_full[k])

@@ -80,6 +80,7 @@ __global__ void k_cbin(DeviceState S, const float* __restrict__ pos) {
     }
     S.cell_of[a] = c;
     const int k = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
+    if (!S.own_all && i >= S.own_lo && i < S.own_lo + S.own_n) atomicAdd(S.cl.cell_owned + (size_t)r * (S.max_cells + 1) + c, 1);
     if (k < CL_BUCKET) S.cl.bucket[((size_t)r * S.max_cells + c) * CL_BUCKET + k] = i;
     else atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 32);  // a cell this crowded: not a system for this path
     S.pos_ref[a] = make_float4(x, y, z, 0.0f);
@@ -134,6 +135,19 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
     }
     run += (t + CL - 1) / CL * CL;
   }
+  if (!S.own_all) {
+    // decomposed run: inclusive running count of OWNED atoms inside each row (owned_pre[c] = owned atoms of the row's
+    // cells 0..c), so that the list build can drop a stretch of cells that holds none
+    const int* ow = S.cl.cell_owned + (size_t)r * (S.max_cells + 1);
+    int* op = S.cl.owned_pre + (size_t)r * (S.max_cells + 1);
+    for (int row = rb; row < re; ++row) {
+      int t = 0;
+      for (int c = 0; c < n0; ++c) {
+        t += ow[row * n0 + c];
+        op[row * n0 + c] = t;
+      }
+    }
+  }
   if (re == nrows && rb < nrows) {
     start[nrows * n0] = run;
     S.cl.nslots[r] = run;
@@ -159,7 +173,10 @@ __global__ void k_csort(DeviceState S) {
   for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
     const int b = start[c], n = min(cnt[c], CL_BUCKET), cap = start[c + 1] - b;
     __syncwarp();
-    if (lane == 0) cnt[c] = 0;  // counters clean for the next build
+    if (lane == 0) {  // counters clean for the next build
+      cnt[c] = 0;
+      if (!S.own_all) S.cl.cell_owned[(size_t)r * (S.max_cells + 1) + c] = 0;
+    }
     int i = -1;
     float x = 0.f;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,6 +278,14 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       continue;
     }
     const int first = __ffs(realmask) - 1;
+    // decomposed run: does the cluster hold an atom this rank owns?  If not, only owned partners matter.
+    bool owned_lane = true;
+    if (!S.own_all) {
+      const int a = (lane < CL && real) ? C.perm[sb + s0 + lane] : -1;
+      owned_lane = a >= S.own_lo && a < S.own_lo + S.own_n;
+    }
+    const bool o_c = S.own_all || __any_sync(0xffffffffu, owned_lane && lane < CL && real);
+    const int* owned_pre = S.cl.owned_pre + (size_t)r * (S.max_cells + 1);
     // a list holds pairs up to rl + (cluster extent) apart along an axis: that must stay below half the box
     if (lane == 0 && g.periodic &&
         (hi[0] - lo[0] > C.max_extent || hi[1] - lo[1] > C.max_extent || hi[2] - lo[2] > C.max_extent))
@@ -316,7 +341,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
     {
       unsigned m = 0;
       unsigned en = 0;
-      if (lane >= 1 && lane < CL && real) {
+      if (lane >= 1 && lane < CL && real && o_c) {
         m = (realmask & ((1u << lane) - 1u)) & ~excluded_bits(s0 + lane);
         en = (unsigned)(s0 + lane) | ((unsigned)__float_as_int(pw.w) << 24);
       }
@@ -383,7 +408,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
             if (!g.periodic) {
               cx0 = max(cx0, 0);
               cx1 = min(cx1, n0 - 1);
-              if (cx0 <= cx1) {
+              if (cx0 <= cx1 && (o_c || owned_pre[rr * n0 + cx1] - (cx0 ? owned_pre[rr * n0 + cx0 - 1] : 0) > 0)) {
                 sbeg[1] = start[rr * n0 + cx0];
                 slen[1] = start[rr * n0 + cx1 + 1] - sbeg[1];
               }
@@ -392,7 +417,7 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
 #pragma unroll
               for (int k = -1; k <= 1; ++k) {
                 const int a0 = max(cx0, k * n0) - k * n0, a1 = min(cx1, (k + 1) * n0 - 1) - k * n0;
-                if (a0 <= a1) {
+                if (a0 <= a1 && (o_c || owned_pre[rr * n0 + a1] - (a0 ? owned_pre[rr * n0 + a0 - 1] : 0) > 0)) {
                   sbeg[k + 1] = start[rr * n0 + a0];
                   slen[k + 1] = start[rr * n0 + a1 + 1] - sbeg[k + 1];
                   shx[k + 1] = k * g.L[0];
@@ -456,6 +481,10 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
           take = take && dd != 0 && (2 * dd < row_ncl || (2 * dd == row_ncl && cj > ci_row));
         }
         tj = (unsigned)__float_as_int(p.w);
+        if (take && !o_c) {  // a cluster without owned atoms keeps the partners this rank owns
+          const int aj = C.perm[sb + sj];
+          take = aj >= S.own_lo && aj < S.own_lo + S.own_n;
+        }
       }
       unsigned xb = 0;
       if (take && sj >= xlo && sj <= xhi) xb = excluded_bits(sj);
@@ -553,6 +582,8 @@ struct ClExactArgs {
   const Grid* g;
   const float2* AB;
   int mcap, slots, c, ntypes;
+  const int* perm;       // decomposed runs: energy share by ownership
+  int own_lo, own_n, own_all;
   unsigned terms;
   float s_lo, s_hi, s_max;
 };
@@ -593,8 +624,13 @@ __device__ __noinline__ float2 cl_exact_pass(ClExactArgs a, int2 mt, SwitchConst
             red_add_f32x4(a.f + si, wx * nc.x, wy * nc.x, wz * nc.x);
             red_add_f32x4(a.f + sj, -wx * nc.x, -wy * nc.x, -wz * nc.x);
             if (ENERGY) {
-              e_lj += elj.x;
-              e_el -= neel.x;
+              float wgt = 1.0f;
+              if (!a.own_all) {
+                const int ai = a.perm[si], aj = a.perm[sj];
+                wgt = 0.5f * ((ai >= a.own_lo && ai < a.own_lo + a.own_n) ? 1.f : 0.f) + 0.5f * ((aj >= a.own_lo && aj < a.own_lo + a.own_n) ? 1.f : 0.f);
+              }
+              e_lj += wgt * elj.x;
+              e_el -= wgt * neel.x;
             }
           }
         }
@@ -694,6 +730,21 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
 
     const int s0 = c * CL;
     const unsigned imask = (unsigned)mt_cur.x >> 24;
+    if (entries_of(mt_cur) == 0) {  // (decomposed runs: most clusters far from the owned atoms have nothing to do)
+      which ^= 1;
+      continue;
+    }
+    // decomposed run, energies: a pair counts by the share of its atoms this rank owns (the other rank adds the rest)
+    float own_i[CL];
+#pragma unroll
+    for (int k = 0; k < CL; ++k) own_i[k] = 1.0f;
+    if (ENERGY && !S.own_all) {
+#pragma unroll
+      for (int k = 0; k < CL; ++k) {
+        const int a = C.perm[sb + s0 + k];
+        own_i[k] = (a >= S.own_lo && a < S.own_lo + S.own_n) ? 0.5f : 0.0f;
+      }
+    }
     // ---- the cluster's atoms, two by two: float records without a box, fixed-point records with one
     F2 XI[CL_H], YI[CL_H], ZI[CL_H], NQI[CL_H];
     int IX[CL], IY[CL], IZ[CL];
@@ -758,6 +809,11 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
       const unsigned tj = entry >> 24;
       const unsigned jslot = entry & 0xffffffu;
       const float qj = __int_as_float(rj.w);
+      float own_j = 0.f;
+      if (ENERGY && !S.own_all) {
+        const int aj = jslot < nslots_cap ? C.perm[sb + jslot] : -1;
+        own_j = (aj >= S.own_lo && aj < S.own_lo + S.own_n) ? 0.5f : 0.0f;
+      }
       F2 GX = f2(0.f), GY = f2(0.f), GZ = f2(0.f);
 #pragma unroll
       for (int p = 0; p < CL_H; ++p) {
@@ -800,8 +856,14 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
           GY = f2_fma(dy, nc, GY);
           GZ = f2_fma(dz, nc, GZ);
           if (ENERGY) {
-            ELJ = f2_add(ELJ, f2(in0 ? elj.x : 0.f, in1 ? elj.y : 0.f));
-            NEEL = f2_add(NEEL, f2(in0 ? neel.x : 0.f, in1 ? neel.y : 0.f));
+            F2 e1 = f2(in0 ? elj.x : 0.f, in1 ? elj.y : 0.f), e2 = f2(in0 ? neel.x : 0.f, in1 ? neel.y : 0.f);
+            if (!S.own_all) {
+              const F2 wgt = f2(own_i[2 * p] + own_j, own_i[2 * p + 1] + own_j);
+              e1 = f2_mul(e1, wgt);
+              e2 = f2_mul(e2, wgt);
+            }
+            ELJ = f2_add(ELJ, e1);
+            NEEL = f2_add(NEEL, e2);
           }
         }
       }
@@ -858,6 +920,10 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
       a.slots = C.slots;
       a.c = c;
       a.ntypes = S.ntypes;
+      a.perm = C.perm + sb;
+      a.own_lo = S.own_lo;
+      a.own_n = S.own_n;
+      a.own_all = S.own_all;
       a.terms = S.pp.terms;
       a.s_lo = s_in;
       a.s_hi = s_hi;

@@ -477,7 +477,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   const double cl_extent = 8.0;  // a periodic box must leave room for clusters at least this long (A)
   bool use_cluster = env_switch("TMD_B200_CLUSTER", TMD_DEFAULT_CLUSTER) == 1 && !ctx->cluster_failed && has_cut &&
                      ctx->pair_mask != 0 && (ctx->pair_mask & ~(T_LJ | T_ELEC)) == 0 && !ctx->exact_gradient &&
-                     d.ntypes <= CL_MAXT && d.own_all && N < (1 << 24) - 4096 * CL;
+                     d.ntypes <= CL_MAXT && N < (1 << 24) - 4096 * CL;
   double cl_max_extent = INFINITY;
   if (use_cluster && ctx->periodic) {
     // pair (i, j) of a list: |x_i - x_j| <= rl + (cluster extent) + skin along every axis, and that must stay below
@@ -632,7 +632,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       const size_t ne = C1 * (size_t)(cl.mcap + cl.ecap);
       if (ne * 4 > ((size_t)64 << 30)) return fail(TMD_ERR_UNSUPPORTED, "cluster lists would exceed 64 GiB");
       bool ok = grab(&cl.xq, S1) && grab(&cl.f, S1) && grab(&cl.xw, S1) && (!ctx->periodic || grab(&cl.xf, S1)) &&
-                grab(&cl.perm, S1) && grab(&cl.bucket, (size_t)R * d.max_cells * CL_BUCKET) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
+                grab(&cl.perm, S1) && grab(&cl.bucket, (size_t)R * d.max_cells * CL_BUCKET) &&
+                grab(&cl.cell_owned, (size_t)R * (d.max_cells + 1)) && grab(&cl.owned_pre, (size_t)R * (d.max_cells + 1)) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
                 grab(&cl.meta, C1) && grab(&cl.entries, ne + 64) && grab(&cl.masks, C1 * (size_t)cl.mcap + 64);
       if (!ok) return fail(TMD_ERR_CUDA, "cudaMalloc of the cluster lists failed");
       TMD_CUDA(cudaMemset(cl.xq, 0, S1 * sizeof(float4)));
@@ -640,6 +641,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       if (cl.xf) TMD_CUDA(cudaMemset(cl.xf, 0, S1 * sizeof(int4)));
       TMD_CUDA(cudaMemset(cl.perm, 0xFF, S1 * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.nslots, 0, (size_t)R * sizeof(int)));
+      TMD_CUDA(cudaMemset(cl.cell_owned, 0, (size_t)R * (d.max_cells + 1) * sizeof(int)));
+      TMD_CUDA(cudaMemset(cl.owned_pre, 0, (size_t)R * (d.max_cells + 1) * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.meta, 0, C1 * sizeof(int2)));
       {
         std::vector<int> ident((size_t)R * N);
@@ -1266,6 +1269,7 @@ int tmd_set_owned_atoms(tmd_ctx* ctx, int first_atom, int count) {
   ctx->d.own_lo = first_atom;
   ctx->d.own_n = count;
   ctx->d.own_all = (first_atom == 0 && count == ctx->natoms) ? 1 : 0;
+  if (ctx->d.cl.on) priv(ctx).dirty = true;  // the cluster lists are built for the owned atoms: start over
   return TMD_OK;
 }
 
