@@ -205,7 +205,7 @@ class DecomposedIntegrator:
                 g = torch.cuda.CUDAGraph()
                 # TMD_B200_COND=1: the library edits the graph under capture (conditional node for the
                 # rebuild kernels, body captured from a helper stream) -- relaxed mode permits that
-                mode = "relaxed" if os.environ.get("TMD_B200_COND", "")[:1] == "1" else "global"
+                mode = "relaxed"  # (the library turns the rebuild into a conditional node of the graph under capture)
                 with torch.cuda.graph(g, capture_error_mode=mode):
                     self._enqueue_step(with_energy, parity)
                 # the capture only records; state was not advanced
@@ -317,11 +317,19 @@ def bench_decomposed(args, world, rank, local, config):
     launches = torch.tensor([nl], dtype=torch.int64, device=dev)
     dist.all_reduce(launches)
 
-    # in-cutoff pairs: every rank counts the pairs of its owned atoms (i<j, or j foreign)
+    # in-cutoff pairs of the whole system, each counted once: a rank evaluates every pair that touches one of its
+    # atoms (pairs across a boundary on both sides), and counts those whose lower atom index it owns
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     dummy = torch.zeros(2, dtype=torch.int32, device=dev)
     _lib.check(L.tmd_export_pairs(forces._ctx, system.pos.data_ptr(), 0, dummy.data_ptr(), 0, count.data_ptr(), stream))
+    evaluated = int(count.item())
+    buf = torch.empty((max(evaluated, 1), 2), dtype=torch.int32, device=dev)
+    _lib.check(L.tmd_export_pairs(forces._ctx, system.pos.data_ptr(), 0, buf.data_ptr(), buf.shape[0], count.data_ptr(), stream))
+    first = buf[: int(count.item()), 0]
+    count = ((first >= integ.dec.lo) & (first < integ.dec.hi)).sum().to(torch.int64).reshape(1)
     dist.all_reduce(count)
+    evaluated_t = torch.tensor([evaluated], dtype=torch.int64, device=dev)
+    dist.all_reduce(evaluated_t)
 
     # end to end: host-resident positions in and out every step
     e2e_steps = min(args.steps, args.e2e_steps)
@@ -380,7 +388,7 @@ def bench_decomposed(args, world, rank, local, config):
         },
         "gpu_launches": int(launches.item()),
         "roofline": {
-            "kernel": "k_pair (non-bonded pair kernel), slowest rank; timed over %d eager steps after the graph-replayed timed region" % nprof,
+            "kernel": "non-bonded pair kernel (id %d: 4 = cluster half list, 2 = packed full rows), slowest rank; timed over %d eager steps after the graph-replayed timed region" % (int(L.tmd_pair_kernel(forces._ctx)), nprof),
             "bound": "hbm",
             "achieved": (32.0 * n / world + 4.0 * int(count.item()) / world) / (pair_avg_ms * 1e-3) / 1e9 if pair_avg_ms > 0 else 0.0,
             "peak": peak,
@@ -388,7 +396,9 @@ def bench_decomposed(args, world, rank, local, config):
             "frac": ((32.0 * n / world + 4.0 * int(count.item()) / world) / (pair_avg_ms * 1e-3) / 1e9 / peak) if pair_avg_ms > 0 else 0.0,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "algorithmic_bytes": 32.0 * n / world + 4.0 * int(count.item()) / world,
+            "pairs_in_cutoff": int(count.item()),
             "pair_entries_counted": int(count.item()),
+            "pairs_evaluated_all_ranks": int(evaluated_t.item()),
             "avg_kernel_ms": pair_avg_ms,
             "share_of_step": pair_avg_ms / ms_per_step,
             "traffic": None,
