@@ -89,26 +89,35 @@ __global__ void k_cbin(DeviceState S, const float* __restrict__ pos) {
 
 // ---- rebuild, phase 2: row-padded exclusive scan of the cell counts (one CTA per replica) --------
 // cell_start[c] = first slot of cell c; the last cell of every row (cells of equal y, z) is followed by
-// padding up to a multiple of CL slots.  cl.nslots[r] = slots in use (a multiple of CL).
+// padding up to a multiple of CL slots, filled here with records no mask ever selects.
+// cl.nslots[r] = slots in use (a multiple of CL).  A warp takes rows in turn: the row's cells are read
+// with coalesced loads and scanned with shuffles.
 __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   const int r = blockIdx.x;
   const int parity = (int)(S.counters[0] & 1ull);
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   __shared__ int warp_tot[32];
+  const ClusterState& C = S.cl;
   const Grid& g = S.grid[r];
   const int n0 = g.n[0], nrows = g.n[1] * g.n[2];
   const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  int* rtot = C.row_tot + (size_t)r * (C.max_rows + 1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // pass 1: padded atom count of every row
+  for (int row = wid; row < nrows; row += nw) {
+    int t = 0;
+    for (int c = lane; c < n0; c += 32) t += cnt[row * n0 + c];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) rtot[row] = (t + CL - 1) / CL * CL;
+  }
+  __syncthreads();
+  // pass 2: exclusive scan of the row totals (each thread a contiguous chunk of rows)
   const int nt = blockDim.x;
   const int chunk = (nrows + nt - 1) / nt;
   const int rb = threadIdx.x * chunk, re = min(nrows, rb + chunk);
   int sum = 0;
-  for (int row = rb; row < re; ++row) {
-    int t = 0;
-    for (int c = 0; c < n0; ++c) t += cnt[row * n0 + c];
-    sum += (t + CL - 1) / CL * CL;
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = nt >> 5;
+  for (int row = rb; row < re; ++row) sum += rtot[row];
   int incl = sum;
   for (int o = 1; o < 32; o <<= 1) {
     int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -128,93 +137,99 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   __syncthreads();
   int run = warp_tot[wid] + incl - sum;
   for (int row = rb; row < re; ++row) {
-    int t = 0;
-    for (int c = 0; c < n0; ++c) {
-      start[row * n0 + c] = run + t;
-      t += cnt[row * n0 + c];
-    }
-    run += (t + CL - 1) / CL * CL;
-  }
-  if (!S.own_all) {
-    // decomposed run: inclusive running count of OWNED atoms inside each row (owned_pre[c] = owned atoms of the row's
-    // cells 0..c), so that the list build can drop a stretch of cells that holds none
-    const int* ow = S.cl.cell_owned + (size_t)r * (S.max_cells + 1);
-    int* op = S.cl.owned_pre + (size_t)r * (S.max_cells + 1);
-    for (int row = rb; row < re; ++row) {
-      int t = 0;
-      for (int c = 0; c < n0; ++c) {
-        t += ow[row * n0 + c];
-        op[row * n0 + c] = t;
-      }
-    }
+    const int t = rtot[row];
+    rtot[row] = run;  // the row's first slot
+    run += t;
   }
   if (re == nrows && rb < nrows) {
     start[nrows * n0] = run;
-    S.cl.nslots[r] = run;
-    if (run > S.cl.slots) atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 16);  // (cannot happen: slots >= N + rows * (CL-1))
+    C.nslots[r] = run;
+    if (run > C.slots) atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 16);  // (cannot happen: slots >= N + rows * (CL-1))
+  }
+  __syncthreads();
+  // pass 3: cell offsets inside every row, the padding records behind the row's atoms, owned-atom running counts
+  const size_t sb = cl_slot_base(C, r);
+  for (int row = wid; row < nrows; row += nw) {
+    int base = rtot[row];
+    int obase = 0;
+    for (int c0 = 0; c0 < n0; c0 += 32) {
+      const int c = c0 + lane;
+      const int v = c < n0 ? cnt[row * n0 + c] : 0;
+      int inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (c < n0) start[row * n0 + c] = base + inc - v;
+      base += __shfl_sync(0xffffffffu, inc, 31);
+      if (!S.own_all) {
+        const int ov = c < n0 ? C.cell_owned[(size_t)r * (S.max_cells + 1) + row * n0 + c] : 0;
+        int oi = ov;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, oi, o);
+          if (lane >= o) oi += u;
+        }
+        if (c < n0) C.owned_pre[(size_t)r * (S.max_cells + 1) + row * n0 + c] = obase + oi;
+        obase += __shfl_sync(0xffffffffu, oi, 31);
+      }
+    }
+    const int pad_end = (base + CL - 1) / CL * CL;  // == the next row's first slot
+    for (int s = base + lane; s < pad_end; s += 32) {
+      C.perm[sb + s] = -1;
+      C.xq[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      C.xw[sb + s] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.f);
+      if (C.xf) C.xf[sb + s] = make_int4(0, 0, 0, 0);
+    }
   }
 }
 
 // ---- rebuild, phase 3: order every cell by x, emit the slot records -------------------------------------
-// One warp per cell.  Slots of a cell: its atoms ordered by folded x (ties by atom index: deterministic), then,
-// for the last cell of a row, the padding records.
+// One thread per atom: its slot is the cell's first slot plus the number of atoms of the cell's bucket that
+// precede it by (folded x, atom index) -- deterministic whatever order the atoms arrived in.
 __global__ void k_csort(DeviceState S) {
   const int r = blockIdx.y;
   const int parity = (int)(S.counters[0] & 1ull);
   if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
   const ClusterState& C = S.cl;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
   const Grid& g = S.grid[r];
-  const int ncells = g.ncells;
   const size_t base = (size_t)r * S.natoms, sb = cl_slot_base(C, r);
-  int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
+  const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   const int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
-  for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < ncells; c += warps_per_grid) {
-    const int b = start[c], n = min(cnt[c], CL_BUCKET), cap = start[c + 1] - b;
-    __syncwarp();
-    if (lane == 0) {  // counters clean for the next build
-      cnt[c] = 0;
-      if (!S.own_all) S.cl.cell_owned[(size_t)r * (S.max_cells + 1) + c] = 0;
-    }
-    int i = -1;
-    float x = 0.f;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) {
-      i = C.bucket[((size_t)r * S.max_cells + c) * CL_BUCKET + lane];
-      p = S.pos_ref[base + i];
-      x = g.periodic ? p.x - g.L[0] * floorf(p.x * g.invL[0]) : p.x;
-    }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.natoms; i += gridDim.x * blockDim.x) {
+    const int c = S.cell_of[base + i];
+    const int n = min(cnt[c], CL_BUCKET);
+    const float4 p = S.pos_ref[base + i];
+    const float x = g.periodic ? p.x - g.L[0] * floorf(p.x * g.invL[0]) : p.x;
+    const int* bk = C.bucket + ((size_t)r * S.max_cells + c) * CL_BUCKET;
     int rk = 0;
-    for (int q = 0; q < n; ++q) {
-      const float xo = __shfl_sync(0xffffffffu, x, q);
-      const int io = __shfl_sync(0xffffffffu, i, q);
-      rk += (xo < x || (xo == x && io < i)) ? 1 : 0;
-    }
-    if (lane < n) {
-      const int s = b + rk;
-      C.inv[base + i] = s;
-      C.perm[sb + s] = i;
-      C.xq[sb + s] = make_float4(p.x, p.y, p.z, S.q[i]);
-      C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (C.xf)
-        C.xf[sb + s] = make_int4(fx_encode(p.x, g.fx_inv[0]), fx_encode(p.y, g.fx_inv[1]), fx_encode(p.z, g.fx_inv[2]),
-                                 __float_as_int(S.q[i]));
-      float wx = p.x, wy = p.y, wz = p.z;
-      if (g.periodic) {
-        wx -= g.L[0] * floorf(wx * g.invL[0]);
-        wy -= g.L[1] * floorf(wy * g.invL[1]);
-        wz -= g.L[2] * floorf(wz * g.invL[2]);
+    bool listed = false;
+    for (int k = 0; k < n; ++k) {
+      const int j = bk[k];
+      if (j == i) {
+        listed = true;
+        continue;
       }
-      C.xw[sb + s] = make_float4(wx, wy, wz, __int_as_float(S.type[i]));
+      const float xr = S.pos_ref[base + j].x;
+      const float xo = g.periodic ? xr - g.L[0] * floorf(xr * g.invL[0]) : xr;
+      rk += (xo < x || (xo == x && j < i)) ? 1 : 0;
     }
-    for (int e = n + lane; e < cap; e += 32) {  // row padding: finite records that no mask ever selects
-      C.perm[sb + b + e] = -1;
-      C.xq[sb + b + e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      C.f[sb + b + e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      C.xw[sb + b + e] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.f);
-      if (C.xf) C.xf[sb + b + e] = make_int4(0, 0, 0, 0);
+    if (!listed) continue;  // (bucket overflow, already flagged: the build is discarded)
+    const int s = start[c] + rk;
+    C.inv[base + i] = s;
+    C.perm[sb + s] = i;
+    C.xq[sb + s] = make_float4(p.x, p.y, p.z, S.q[i]);
+    C.f[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (C.xf)
+      C.xf[sb + s] = make_int4(fx_encode(p.x, g.fx_inv[0]), fx_encode(p.y, g.fx_inv[1]), fx_encode(p.z, g.fx_inv[2]),
+                               __float_as_int(S.q[i]));
+    float wx = p.x, wy = p.y, wz = p.z;
+    if (g.periodic) {
+      wx -= g.L[0] * floorf(wx * g.invL[0]);
+      wy -= g.L[1] * floorf(wy * g.invL[1]);
+      wz -= g.L[2] * floorf(wz * g.invL[2]);
     }
+    C.xw[sb + s] = make_float4(wx, wy, wz, __int_as_float(S.type[i]));
   }
 }
 
@@ -248,6 +263,13 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
   const float rl = S.rlist, rl2 = S.rlist2;
   const int stride_e = C.mcap + C.ecap;
   if (blockIdx.x == 0 && threadIdx.x == 0) fl[F_NREBUILD] += 1;
+  {  // the cell counters have served this build: clean for the next one
+    int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
+    for (int cc = blockIdx.x * blockDim.x + threadIdx.x; cc < g.ncells; cc += gridDim.x * blockDim.x) {
+      cnt[cc] = 0;
+      if (!S.own_all) C.cell_owned[(size_t)r * (S.max_cells + 1) + cc] = 0;
+    }
+  }
 
   for (int c = blockIdx.x * CLB_WARPS + w; c < C.nclusters_cap; c += gridDim.x * CLB_WARPS) {
     if (c >= ncl) {

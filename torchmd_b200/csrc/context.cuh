@@ -58,6 +58,8 @@ struct ClusterState {
   int4* xf;            // fixed-point records (physics.cuh, fx_encode) of a periodic box: X, Y, Z + charge bits (every step)
   int* perm;           // slot -> atom (-1: padding)
   int* bucket;         // [(rep*max_cells + cell) * CL_BUCKET + k] atoms of a cell in arrival order (rebuild scratch)
+  int* row_tot;        // [rep*(max_rows+1) + row] scan scratch: padded atoms of a cell row, then its first slot
+  int max_rows;
   int* cell_owned;     // decomposed runs: owned atoms per cell (rebuild scratch), and
   int* owned_pre;      //   their running count inside each cell row
   int* inv;            // [rep*natoms + i] atom -> slot

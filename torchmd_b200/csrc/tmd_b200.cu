@@ -609,6 +609,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       if (!ctx->periodic) rows = 40 * 40;  // the device sizes that grid
       const long long slots = ((long long)N + rows * (CL - 1) + CL - 1) / CL * CL;
       cl.on = 1;
+      cl.max_rows = (int)rows;
       cl.slots = (int)slots;
       cl.nclusters_cap = (int)(slots / CL);
       cl.max_extent = (float)cl_max_extent;
@@ -633,7 +634,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       if (ne * 4 > ((size_t)64 << 30)) return fail(TMD_ERR_UNSUPPORTED, "cluster lists would exceed 64 GiB");
       bool ok = grab(&cl.xq, S1) && grab(&cl.f, S1) && grab(&cl.xw, S1) && (!ctx->periodic || grab(&cl.xf, S1)) &&
                 grab(&cl.perm, S1) && grab(&cl.bucket, (size_t)R * d.max_cells * CL_BUCKET) &&
-                grab(&cl.cell_owned, (size_t)R * (d.max_cells + 1)) && grab(&cl.owned_pre, (size_t)R * (d.max_cells + 1)) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
+                grab(&cl.row_tot, (size_t)R * (rows + 1)) && grab(&cl.cell_owned, (size_t)R * (d.max_cells + 1)) && grab(&cl.owned_pre, (size_t)R * (d.max_cells + 1)) && grab(&cl.inv, (size_t)R * N) && grab(&cl.nslots, (size_t)R) &&
                 grab(&cl.meta, C1) && grab(&cl.entries, ne + 64) && grab(&cl.masks, C1 * (size_t)cl.mcap + 64);
       if (!ok) return fail(TMD_ERR_CUDA, "cudaMalloc of the cluster lists failed");
       TMD_CUDA(cudaMemset(cl.xq, 0, S1 * sizeof(float4)));
@@ -921,7 +922,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_cbin");
       launch(k_cscan, R, 1024, rs, d);
       TMD_LAUNCHED(ctx, "k_cscan");
-      launch(k_csort, dim3(std::max(1, std::min((d.max_cells + 7) / 8, 148 * 8)), R), 256, rs, d);
+      launch(k_csort, dim3(std::min((N + 255) / 256, 148 * 8), R), 256, rs, d);
       TMD_LAUNCHED(ctx, "k_csort");
       launch(k_cbuild, dim3(std::max(1, std::min((d.cl.nclusters_cap + CLB_WARPS - 1) / CLB_WARPS, 148 * 16)), R), CLB_WARPS * 32, rs, d);
       TMD_LAUNCHED(ctx, "k_cbuild");
