@@ -28,7 +28,7 @@ VARIANTS = {  # tag -> defines; every interpreter build the tests use (built tog
     "_graph": ["TMD_COND_NODE=1"],  # the device-side switch of the rebuild's conditional node compiled in
     # every opt-in path as the default (what round 2 switches on once the B200 has confirmed it)
     "_r2": ["BT_CULL=1", "BT_PAIRED=1", "TMD_COND_NODE=1", "TMD_DEFAULT_FX=2", "TMD_DEFAULT_OVERLAP=1", "TMD_DEFAULT_FUSEPREP=1", "TMD_DEFAULT_GRAPH=1", "TMD_DEFAULT_CLUSTER=1"],
-    "_cl": ["TMD_DEFAULT_CLUSTER=1", "TMD_COND_NODE=1", "TMD_DEFAULT_GRAPH=1", "TMD_DEFAULT_FUSEPREP=1"],  # the cluster half-list path (cluster.cuh) over the plain kernels
+    "_cl": ["TMD_DEFAULT_CLUSTER=1", "TMD_COND_NODE=1", "TMD_DEFAULT_GRAPH=1", "TMD_DEFAULT_FUSEPREP=1", "TMD_DEFAULT_OVERLAP=1"],  # the cluster half-list path (cluster.cuh) over the plain kernels
     "_t2": ["FX_SMALLT_MAX_N=2"],
     "_fxu4": ["PAIR_FX_UNROLL=4"],
     "_fx2u2": ["PAIR_FX2_UNROLL=2"],

@@ -52,9 +52,13 @@ constexpr int CL_WARPS = CL_WARPS_N;
 #ifndef CL_BRANCHFREE
 #define CL_BRANCHFREE 1  // evaluate every packed pair (no per-pair branch): the two pairs of a lane interleave
 #endif
+#ifndef CL_UNROLL
+#define CL_UNROLL 1  // batches per loop iteration
+#endif
 #ifndef CL_MINBLOCKS
 #define CL_MINBLOCKS 2  // 120 registers, no spills: 205 us against 217 us at 3 CTAs/SM with spills (B200, profiles/r02_cluster_call5.txt)
 #endif
+constexpr int CL_UNROLL_N = CL_UNROLL;
 constexpr int CLB_WARPS = 4;   // list build: warps per CTA
 constexpr int CLB_MAXSEG = 160;
 constexpr int CL_SIMT_MAX_ENTRIES = 4096;  // interpreter build (tests/simt): entries per cluster its static buffer holds
@@ -80,6 +84,7 @@ __global__ void k_cbin(DeviceState S, const float* __restrict__ pos) {
     }
     S.cell_of[a] = c;
     const int k = atomicAdd(S.cell_count + (size_t)r * (S.max_cells + 1) + c, 1);
+    atomicAdd(S.cl.row_tot + (size_t)r * (S.cl.max_rows + 1) + c / S.grid[r].n[0], 1);  // atoms per cell row
     if (!S.own_all && i >= S.own_lo && i < S.own_lo + S.own_n) atomicAdd(S.cl.cell_owned + (size_t)r * (S.max_cells + 1) + c, 1);
     if (k < CL_BUCKET) S.cl.bucket[((size_t)r * S.max_cells + c) * CL_BUCKET + k] = i;
     else atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 32);  // a cell this crowded: not a system for this path
@@ -87,11 +92,8 @@ __global__ void k_cbin(DeviceState S, const float* __restrict__ pos) {
   }
 }
 
-// ---- rebuild, phase 2: row-padded exclusive scan of the cell counts (one CTA per replica) --------
-// cell_start[c] = first slot of cell c; the last cell of every row (cells of equal y, z) is followed by
-// padding up to a multiple of CL slots, filled here with records no mask ever selects.
-// cl.nslots[r] = slots in use (a multiple of CL).  A warp takes rows in turn: the row's cells are read
-// with coalesced loads and scanned with shuffles.
+// ---- rebuild, phase 2: first slot of every cell row (one CTA per replica), then of every cell ------
+// Rows (cells of equal y, z) are padded to a multiple of CL slots.  k_cbin counted the atoms per row.
 __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   const int r = blockIdx.x;
   const int parity = (int)(S.counters[0] & 1ull);
@@ -100,24 +102,14 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   const ClusterState& C = S.cl;
   const Grid& g = S.grid[r];
   const int n0 = g.n[0], nrows = g.n[1] * g.n[2];
-  const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
   int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
   int* rtot = C.row_tot + (size_t)r * (C.max_rows + 1);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // pass 1: padded atom count of every row
-  for (int row = wid; row < nrows; row += nw) {
-    int t = 0;
-    for (int c = lane; c < n0; c += 32) t += cnt[row * n0 + c];
-    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) rtot[row] = (t + CL - 1) / CL * CL;
-  }
-  __syncthreads();
-  // pass 2: exclusive scan of the row totals (each thread a contiguous chunk of rows)
   const int nt = blockDim.x;
   const int chunk = (nrows + nt - 1) / nt;
   const int rb = threadIdx.x * chunk, re = min(nrows, rb + chunk);
   int sum = 0;
-  for (int row = rb; row < re; ++row) sum += rtot[row];
+  for (int row = rb; row < re; ++row) sum += (rtot[row] + CL - 1) / CL * CL;
   int incl = sum;
   for (int o = 1; o < 32; o <<= 1) {
     int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -137,20 +129,34 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
   __syncthreads();
   int run = warp_tot[wid] + incl - sum;
   for (int row = rb; row < re; ++row) {
-    const int t = rtot[row];
+    const int t = (rtot[row] + CL - 1) / CL * CL;
     rtot[row] = run;  // the row's first slot
     run += t;
   }
   if (re == nrows && rb < nrows) {
+    rtot[nrows] = run;
     start[nrows * n0] = run;
     C.nslots[r] = run;
     if (run > C.slots) atomicOr(S.flags + r * F_COUNT + F_CLFAIL, 16);  // (cannot happen: slots >= N + rows * (CL-1))
   }
-  __syncthreads();
-  // pass 3: cell offsets inside every row, the padding records behind the row's atoms, owned-atom running counts
+}
+// A warp per row: cell offsets inside the row (coalesced loads, shuffle scan), the padding records behind the
+// row's atoms, the running count of owned atoms (decomposed runs).
+__global__ void k_ccells(DeviceState S) {
+  const int r = blockIdx.y;
+  const int parity = (int)(S.counters[0] & 1ull);
+  if (!S.flags[r * F_COUNT + F_REBUILD0 + parity]) return;
+  const ClusterState& C = S.cl;
+  const Grid& g = S.grid[r];
+  const int n0 = g.n[0], nrows = g.n[1] * g.n[2];
+  const int* cnt = S.cell_count + (size_t)r * (S.max_cells + 1);
+  int* start = S.cell_start + (size_t)r * (S.max_cells + 1);
+  const int* rtot = C.row_tot + (size_t)r * (C.max_rows + 1);
+  const int lane = threadIdx.x & 31;
   const size_t sb = cl_slot_base(C, r);
-  for (int row = wid; row < nrows; row += nw) {
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += gridDim.x * (blockDim.x >> 5)) {
     int base = rtot[row];
+    const int pad_end = rtot[row + 1];
     int obase = 0;
     for (int c0 = 0; c0 < n0; c0 += 32) {
       const int c = c0 + lane;
@@ -173,7 +179,6 @@ __global__ void __launch_bounds__(1024) k_cscan(DeviceState S) {
         obase += __shfl_sync(0xffffffffu, oi, 31);
       }
     }
-    const int pad_end = (base + CL - 1) / CL * CL;  // == the next row's first slot
     for (int s = base + lane; s < pad_end; s += 32) {
       C.perm[sb + s] = -1;
       C.xq[sb + s] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -269,6 +274,8 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       cnt[cc] = 0;
       if (!S.own_all) C.cell_owned[(size_t)r * (S.max_cells + 1) + cc] = 0;
     }
+    for (int rr = blockIdx.x * blockDim.x + threadIdx.x; rr <= C.max_rows; rr += gridDim.x * blockDim.x)
+      C.row_tot[(size_t)r * (C.max_rows + 1) + rr] = 0;
   }
 
   for (int c = blockIdx.x * CLB_WARPS + w; c < C.nclusters_cap; c += gridDim.x * CLB_WARPS) {
@@ -381,10 +388,14 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
     const int row_c = S.cell_of[base + C.perm[sb + s0 + first]] / n0;
     const int cy = row_c % n1, cz = row_c / n1;
     const int ry = n1 > 1 ? g.reach[1] : 0, rz = n2 > 1 ? g.reach[2] : 0;
-    const int nrows_total = n1 * n2;
     const int row_s = start[row_c * n0], row_ncl = (start[(row_c + 1) * n0] - row_s) / CL;  // the own row's clusters
     const int ci_row = (s0 - row_s) / CL;
-    const int nry = 2 * ry + 1, nrows_c = nry * (2 * rz + 1);
+    // Which of two clusters lists a pair?  The one that sees the other's row at an offset in the "upper" half-space
+    // (dz > 0, or dz == 0 and dy > 0; inside the own row: the next half of the cyclic cluster order, see the sweep).
+    // Offsets are unique (the box holds at least 2 * reach + 1 rows), so the rule is antisymmetric, and every cluster
+    // gets the same half of its surroundings wherever it sits -- a plain "later slots" rule gives the first planes of
+    // a periodic box twice the work of the middle ones and the last planes none.
+    const int nry = 2 * ry + 1, nrows_c = rz * nry + ry + 1;
     int nseg = 0;
     for (int q0 = 0; q0 < nrows_c; q0 += 32) {
       const int q = q0 + lane;
@@ -393,7 +404,8 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       float shx[3] = {0.f, 0.f, 0.f}, shy = 0.f, shz = 0.f;
       bool own_row = false;
       if (q < nrows_c) {
-        const int dy = q % nry - ry, dz = q / nry - rz;
+        const int dz = q <= ry ? 0 : 1 + (q - ry - 1) / nry;
+        const int dy = q <= ry ? q : (q - ry - 1) % nry - ry;
         int yy = cy + dy, zz = cz + dz;
         bool ok = true;
         if (g.periodic) {
@@ -407,15 +419,8 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
           ok = yy >= 0 && yy < n1 && zz >= 0 && zz < n2;
         }
         const int rr = zz * n1 + yy;
-        // Which of two clusters lists the pair?  The one from which the other lies in the NEXT half of the cyclic row
-        // order (the own row: of the cyclic cluster order inside it, see the sweep).  Antisymmetric, and every
-        // cluster gets about half of its surroundings wherever it sits -- a plain "later slots" rule gives the first
-        // planes of a periodic box twice the work of the middle ones and the last planes none.
-        int dr = rr - row_c;
-        if (dr < 0) dr += nrows_total;
-        const bool mine = rr == row_c || 2 * dr < nrows_total || (2 * dr == nrows_total && rr > row_c);
-        own_row = ok && rr == row_c;
-        if (ok && mine) {
+        own_row = ok && q == 0;
+        if (ok) {
           // distance in y, z between the box and the row's slab (with a margin for the binning's rounding)
           const float ylo = g.origin[1] + yy * wy + shy - 1.0e-3f, yhi = ylo + wy + 2.0e-3f;
           const float zlo = g.origin[2] + zz * wz + shz - 1.0e-3f, zhi = zlo + wz + 2.0e-3f;
@@ -901,6 +906,7 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
       unsigned en = lds_u32(ebuf + 4u * lane);
       unsigned mk = 0 < nbA ? mask_of(lane) : 0xffu;
       int4 rj = record_of(en);
+#pragma unroll CL_UNROLL_N
       for (int b = 0; b < nb; ++b) {
         unsigned en_n = en, mk_n = 0xffu;
         int4 rj_n = rj;

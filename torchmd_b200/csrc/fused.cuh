@@ -57,4 +57,63 @@ k_bonded_vv_second(DeviceState S, BondedTables T, const float* __restrict__ q_sc
   if (energies && T.atom_ptr) bonded_energy_reduce(S, T, r, E, energies, red);
 }
 
+// The bonded kernel ran beside the pair kernel on a second stream and left its fp64 sums in `scratch`
+// (tmd_b200.cu, enqueue_forces): total force = pair force of the atom's slot + bonded sum, rounded once.
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_cadd_bonded(DeviceState S, float* __restrict__ forces, const double* __restrict__ scratch) {
+  const int r = blockIdx.y;
+  const int i = S.own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.own_lo + S.own_n) return;
+  const size_t slot = (size_t)r * S.natoms + i;
+  const float4 pf = S.cl.f[(size_t)r * (S.cl.slots + 1) + S.cl.inv[slot]];
+  const double sx = scratch ? scratch[slot * 3] : 0.0, sy = scratch ? scratch[slot * 3 + 1] : 0.0, sz = scratch ? scratch[slot * 3 + 2] : 0.0;
+  forces[slot * 3 + 0] = (float)((double)pf.x + sx);
+  forces[slot * 3 + 1] = (float)((double)pf.y + sy);
+  forces[slot * 3 + 2] = (float)((double)pf.z + sz);
+}
+
+// ... and the same folded into the second half-kick (tmd_md_steps)
+template <bool THERMOSTAT, bool KINETIC>
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_cvv_second_fold(DeviceState S, float* __restrict__ vel, float* __restrict__ forces, const float* __restrict__ masses, float dt,
+                  float hdt, float neg_gamma, const float* __restrict__ vcoeff, const float* __restrict__ noise, uint64_t seed,
+                  uint64_t step_offset, double* __restrict__ ke, const double* __restrict__ scratch) {
+  const int r = blockIdx.y;
+  const int i = S.own_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t step = step_offset + S.counters[1];
+  double ek = 0.0;
+  if (i < S.own_lo + S.own_n) {
+    const size_t slot = (size_t)r * S.natoms + i;
+    const size_t a = slot * 3;
+    const float4 pf = S.cl.f[(size_t)r * (S.cl.slots + 1) + S.cl.inv[slot]];
+    const float f[3] = {(float)((double)pf.x + scratch[a]), (float)((double)pf.y + scratch[a + 1]), (float)((double)pf.z + scratch[a + 2])};
+    const float m = masses[i];
+    float xi[3] = {0.f, 0.f, 0.f};
+    float vc = 0.f;
+    if (THERMOSTAT) {
+      vc = vcoeff[i];
+      if (noise) {
+        xi[0] = noise[a]; xi[1] = noise[a + 1]; xi[2] = noise[a + 2];
+      } else {
+        normal3(seed, step, slot, xi);
+      }
+    }
+    float v2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      forces[a + d] = f[d];
+      float v = vel[a + d];
+      if (THERMOSTAT) v = add_rn(v, add_rn(mul_rn(mul_rn(neg_gamma, v), dt), mul_rn(xi[d], vc)));
+      v = add_rn(v, mul_rn(hdt, div_rn(f[d], m)));
+      vel[a + d] = v;
+      v2 += v * v;
+    }
+    if (KINETIC) ek = 0.5 * (double)m * (double)v2;
+  }
+  if (KINETIC) {
+    __shared__ double red[INTEG_THREADS / 32];
+    block_accumulate<INTEG_THREADS / 32>(ek, ke + r, red);
+  }
+}
+
 }  // namespace tmd

@@ -643,6 +643,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       TMD_CUDA(cudaMemset(cl.perm, 0xFF, S1 * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.nslots, 0, (size_t)R * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.cell_owned, 0, (size_t)R * (d.max_cells + 1) * sizeof(int)));
+      TMD_CUDA(cudaMemset(cl.row_tot, 0, (size_t)R * (rows + 1) * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.owned_pre, 0, (size_t)R * (d.max_cells + 1) * sizeof(int)));
       TMD_CUDA(cudaMemset(cl.meta, 0, C1 * sizeof(int2)));
       {
@@ -856,7 +857,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   }
   // fork: the bonded terms need only the positions, so they run on a second stream while the
   // list check and the pair kernel run here; joined by k_add_bonded below
-  const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr && !d.cl.on;
+  const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr;
   if (overlap) {
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaEventRecord(pv.ev_fork, st));
@@ -922,6 +923,8 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
       TMD_LAUNCHED(ctx, "k_cbin");
       launch(k_cscan, R, 1024, rs, d);
       TMD_LAUNCHED(ctx, "k_cscan");
+      launch(k_ccells, dim3(std::max(1, std::min((d.cl.max_rows + 7) / 8, 148 * 4)), R), 256, rs, d);
+      TMD_LAUNCHED(ctx, "k_ccells");
       launch(k_csort, dim3(std::min((N + 255) / 256, 148 * 8), R), 256, rs, d);
       TMD_LAUNCHED(ctx, "k_csort");
       launch(k_cbuild, dim3(std::max(1, std::min((d.cl.nclusters_cap + CLB_WARPS - 1) / CLB_WARPS, 148 * 16)), R), CLB_WARPS * 32, rs, d);
@@ -992,6 +995,9 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_join, 0));
     if (pv.fold_next) {  // the integrator kernel that follows adds them (enqueue_vv_second)
       pv.fold_pending = true;
+    } else if (d.cl.on) {
+      launch(k_cadd_bonded, owned_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, d, forces, pv.bonded_scratch);
+      TMD_LAUNCHED(ctx, "k_cadd_bonded");
     } else {
       launch(k_add_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, N, d.own_lo, d.own_n, forces, pv.bonded_scratch);
       TMD_LAUNCHED(ctx, "k_add_bonded");
@@ -1071,6 +1077,17 @@ static int enqueue_vv_second(tmd_ctx* ctx, float* vel, const float* forces, cons
     priv(ctx).fold_pending = false;
     float* fw = const_cast<float*>(forces);  // (tmd_md_steps owns this buffer: it handed it to enqueue_forces as the output)
     const double* sc = priv(ctx).bonded_scratch;
+    if (ctx->d.cl.on) {  // cluster path: the pair forces come home from slot order on the way
+      if (thermo) {
+        if (ke) launch(k_cvv_second_fold<true, true>, g, INTEG_THREADS, st, ctx->d, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+        else launch(k_cvv_second_fold<true, false>, g, INTEG_THREADS, st, ctx->d, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+      } else {
+        if (ke) launch(k_cvv_second_fold<false, true>, g, INTEG_THREADS, st, ctx->d, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+        else launch(k_cvv_second_fold<false, false>, g, INTEG_THREADS, st, ctx->d, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
+      }
+      TMD_LAUNCHED(ctx, "k_cvv_second_fold");
+      return TMD_OK;
+    }
     if (thermo) {
       if (ke) launch(k_vv_second_fold<true, true>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
       else launch(k_vv_second_fold<true, false>, g, INTEG_THREADS, st, ctx->natoms, lo, cnt, ctr, vel, fw, masses, fdt, hdt, ng, vcoeff, noise, seed, step, ke, sc);
