@@ -151,7 +151,8 @@ struct tmd_ctx {
   int last_pair_kernel = 0;          // tmd_pair_kernel(): 0 float (k_pair), 1 k_pair_fx, 2 k_pair_fx2, 3 k_pair2_open
   bool fx_packed = false;            // TMD_B200_FX=2: k_pair_fx2 (packed fp32x2 arithmetic) where it applies
   int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
-  bool cluster_failed = false;       // the cluster path reported F_CLFAIL once: this context stays on the full rows
+  bool cluster_failed = false;       // the cluster path reported F_CLFAIL: full rows until cluster_retry_at force calls
+  int64_t cluster_retry_at = 0, cluster_retry_after = 0;
   // peer-to-peer position exchange (tmd_dd_*): one cudaMalloc holding [pos0 | pos1 | flags | sync]
   int dd_rank = -1, dd_world = 0;
   bool dd_connected = false;

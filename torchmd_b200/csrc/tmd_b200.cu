@@ -481,10 +481,12 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   double cl_max_extent = INFINITY;
   if (use_cluster && ctx->periodic) {
     // pair (i, j) of a list: |x_i - x_j| <= rl + (cluster extent) + skin along every axis, and that must stay below
-    // 0.45 L for the image count of the pair to be the one taken from the cluster's centre (cluster.cuh)
+    // half a box length (cluster.cuh)
     float lmin = INFINITY;
     for (int e = 0; e < R * 3; ++e) lmin = std::min(lmin, ctx->box_host[e]);
-    cl_max_extent = 0.45 * (double)lmin - rl - ctx->skin - 0.01;
+    // (the fixed-point separations wrap to the minimum image by themselves: a listed pair only has to stay below
+    //  half a box length, rl + extent + skin < L / 2)
+    cl_max_extent = 0.5 * (double)lmin - rl - ctx->skin - 0.05;
     use_cluster = cl_max_extent >= cl_extent;
   }
   {
@@ -1506,6 +1508,10 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
       return fail(TMD_ERR_UNSUPPORTED,
                   "a position is more than 2000 box lengths from the origin: wrap the coordinates "
                   "(torchmd Wrapper) -- results since the last check are not reliable");
+  if (ctx->cluster_failed && ctx->force_calls >= ctx->cluster_retry_at && !priv(ctx).dirty) {
+    ctx->cluster_failed = false;  // try the cluster lists again from the next force call on
+    priv(ctx).dirty = true;
+  }
   if (ctx->d.cl.on) {
     int maxa = 0, maxb = 0;
     bool clfail = false;
@@ -1520,9 +1526,12 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
       fprintf(stderr, "  (slots %d, ecap %d, mcap %d)\n", ctx->d.cl.slots, ctx->d.cl.ecap, ctx->d.cl.mcap);
     }
     if (clfail) {
-      // a cluster too large for one image count per partner, or an exclusion set / segment table overflow:
-      // this context continues on the full Verlet rows
+      // a cluster too long for the box (a lattice start, a void), or an exclusion set / segment table / cell bucket
+      // overflow: this context continues on the full Verlet rows -- and tries the cluster lists again later (a lattice
+      // start has melted by then), with the waiting time doubling at every failure
       ctx->cluster_failed = true;
+      ctx->cluster_retry_after = std::min<int64_t>(std::max<int64_t>(2 * ctx->cluster_retry_after, 1000), 1 << 20);
+      ctx->cluster_retry_at = ctx->force_calls + ctx->cluster_retry_after;
       priv(ctx).dirty = true;
       return fail(TMD_ERR_OVERFLOW, "cluster lists do not fit this system; switched to full neighbour rows, recompute required");
     }
