@@ -75,6 +75,7 @@ struct DeviceState {
   int row_cap;      // neighbour entries reserved per atom
   int max_cells;    // capacity of the cell arrays per replica
   int nsub;         // cells per list radius
+  int build_split;  // full-row list build: CTAs that share one cell (grids of a few cells)
   int own_lo, own_n, own_all;  // atoms (original indices) whose forces this context computes; all by default
   unsigned long long* counters;  // [0] force calls (parity of the rebuild flag), [1] vv_first calls (Philox position)
   unsigned long long cond;       // cudaGraphConditionalHandle of the rebuild body when this launch is a graph node; 0 otherwise

@@ -775,9 +775,14 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
   const int ny = 2 * g.reach[1] + 1, nz = 2 * g.reach[2] + 1;
   const int nrows = ny * nz;  // <= 25, two run slots each
 
-  for (int c = bx; c < g.ncells; c += nbx) {
+  // Grids of a few cells (small boxes, no cutoff): `split` CTAs share a cell, each taking every split-th pass of 64 of
+  // its atoms, so that a 688-atom single-cell system is built by eleven CTAs instead of one.
+  const int split = max(1, S.build_split);
+  const int pass = split > 1 ? 64 : BT_MAXI;
+  for (int wi = bx; wi < g.ncells * split; wi += nbx) {
+    const int c = wi / split, sub = wi % split;
     const int b0c = start[c], ni = start[c + 1] - b0c;
-    if (ni == 0) continue;  // block-uniform
+    if (ni == 0 || sub * pass >= ni) continue;  // block-uniform
     if (!S.own_all) {       // decomposed run: skip cells without an owned atom
       int mine = 0;
       for (int t = tid; t < ni; t += nthr) {
@@ -836,8 +841,8 @@ __device__ __forceinline__ void phase_build(const DeviceState& S, int r, int bx,
     }
     __syncthreads();
     const int M = roff[BT_MAXRUN];
-    for (int i0 = 0; i0 < ni; i0 += BT_MAXI) {
-      const int nib = min(BT_MAXI, ni - i0);
+    for (int i0 = sub * pass; i0 < ni; i0 += split * pass) {
+      const int nib = min(pass, ni - i0);
       const int b0 = b0c + i0;
       for (int t = tid; t < nib; t += nthr) counts[t] = 0;
       for (int t0 = 0; t0 < M; t0 += BT_TILE) {

@@ -530,6 +530,8 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   }
   if (!ctx->periodic && has_cut) max_cells = use_cluster ? 40 * 40 * 40 : 64 * 64 * 64;  // (cluster path: a bucket per cell)
   d.max_cells = (int)max_cells;
+  // full-row list build: a grid of a few cells is shared out over more CTAs than cells
+  d.build_split = (ctx->periodic && max_cells < 148) ? (int)std::min<long long>(64, (148 + max_cells - 1) / max_cells) : 1;
 
   // guard-free minimum image is valid iff no listed pair can be further than 0.45 L apart
   ctx->safe_image = false;
@@ -957,7 +959,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
         launch(k_sort_pack, dim3(blocks, R), 256, rs, d);
         TMD_LAUNCHED(ctx, "k_sort_pack");
       }
-      launch(k_build_list, dim3(std::max(1, std::min(d.max_cells, 148 * 12)), R), BT_WARPS * 32, rs, d);
+      launch(k_build_list, dim3(std::max(1, std::min(d.max_cells * std::max(1, d.build_split), 148 * 12)), R), BT_WARPS * 32, rs, d);
       TMD_LAUNCHED(ctx, "k_build_list");
     }
     if (in_body) {
