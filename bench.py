@@ -42,6 +42,8 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 WORKLOADS = {
     "water100k": "synthetic TIP3P water box, 33333 waters = 99999 atoms, L=99.93 A, LJ(switch 7.5)+RF electrostatics cutoff 9 A, "
                  "flexible bonds+angles, Langevin 300 K gamma 0.1/ps, dt 1 fs, 1 replica (BASELINE config 4)",
+    "water800k": "synthetic TIP3P water box, 266664 waters = 799992 atoms, L=199.87 A, same settings as water100k: eight times the "
+                 "headline box, the weak-scaling companion of the 8-GPU line (about one headline box of work per GPU)",
     "water10k": "synthetic TIP3P water box, 3333 waters = 9999 atoms, L=46.39 A, same settings as water100k: the largest size "
                 "the reference's all-pairs path runs in seconds per step, so BOTH arms are timed on it",
     "water291": "the reference's tests/water fixture: 97 waters = 291 atoms, L=16.9 A, 2 replicas, LJ(switch 6.0)+RF cutoff 7.3 A, "
@@ -61,8 +63,8 @@ def build_workload(name, device, precision=None, nrep=None):
     from torchmd_b200 import testsystems
 
     precision = precision or torch.float32
-    if name in ("water100k", "water10k"):
-        sysd = testsystems.water_box(N_WATERS if name == "water100k" else 3333, seed=0)
+    if name in ("water100k", "water10k", "water800k"):
+        sysd = testsystems.water_box({"water100k": N_WATERS, "water10k": 3333, "water800k": 266664}[name], seed=0)
         par = testsystems.water_parameters(sysd, precision=precision, device=device)
         return par, np.asarray(sysd["coords"], np.float32), np.asarray(sysd["box"], np.float32), list(TERMS), dict(CFG), nrep or 1, True
     golden = {"water291": ("water291_rf_switch", 2), "ala2": ("ala2_xsc_rf", 1), "thrombin16": ("thrombin_nobox_rf", 16)}[name]
@@ -220,6 +222,7 @@ def reference_arm(args):
 METRICS = {
     "water100k": "MD steps/sec (100k-atom water, fp32)",
     "water10k": "MD steps/sec (9,999-atom water, fp32)",
+    "water800k": "MD steps/sec (799,992-atom water, fp32)",
     "water291": "MD steps/sec (tests/water fixture, 291 atoms x 2 replicas, fp32)",
     "ala2": "MD steps/sec (alanine dipeptide in water, 688 atoms, AMBER, fp32)",
     "thrombin16": "MD steps/sec (thrombin-ligand, 4676 atoms x 16 replicas, fp32)",
@@ -230,7 +233,7 @@ def workload_config(ngpus, workload="water100k"):
     replicated = workload in ("thrombin16", "water291")
     return {
         "workload": WORKLOADS[workload],
-        "natoms": {"water100k": 3 * N_WATERS, "water10k": 9999, "water291": 291, "ala2": 688, "thrombin16": 4676}[workload],
+        "natoms": {"water100k": 3 * N_WATERS, "water800k": 799992, "water10k": 9999, "water291": 291, "ala2": 688, "thrombin16": 4676}[workload],
         "pair_kernel": "cluster half list, packed fp32x2 arithmetic on fixed-point separations (cluster.cuh) where it applies; "
                        "TMD_B200_CLUSTER=0: full Verlet rows",
         "parallelism": "single GPU" if ngpus == 1 else (
@@ -318,8 +321,8 @@ def gpu_arm(args):
     if DEVICE_OVERRIDE is None:
         torch.cuda.set_device(local)
     if world > 1 and not replicated:
-        if wl != "water100k":
-            raise SystemExit(f"--gpus > 1 runs water100k (spatial decomposition) or the replicated workloads, not {wl}")
+        if wl not in ("water100k", "water800k"):
+            raise SystemExit(f"--gpus > 1 runs water100k / water800k (spatial decomposition) or the replicated workloads, not {wl}")
         from torchmd_b200 import domain  # spatial decomposition driver
 
         try:
@@ -514,7 +517,7 @@ def gpu_arm(args):
         "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
-        "data": "synthetic" if wl.startswith("water1") else "the reference's own test system (coordinates and parameters from its fixtures), random velocities",
+        "data": "synthetic" if wl in ("water100k", "water10k", "water800k") else "the reference's own test system (coordinates and parameters from its fixtures), random velocities",
         "config": workload_config(world, wl),
         "clocks": clocks,
         "e2e": e2e,

@@ -29,4 +29,8 @@ if [ "$MODE" = full ]; then
   bench "N=$N full rows, p2p push" fr_p2p water100k 3000 TMD_B200_EXCHANGE=p2p TMD_B200_CLUSTER=0
 fi
 bench "N=$N thrombin16 replicas sharded" thr16 thrombin16 2000 X=1
+if [ "$N" -ge 4 ]; then
+  bench "N=$N water800k (weak scaling), p2p" w800_p2p water800k 2000 TMD_B200_EXCHANGE=p2p
+  bench "N=$N water800k (weak scaling), all-gather" w800_ag water800k 2000 TMD_B200_EXCHANGE=allgather
+fi
 tail -3 gpurun_out/multi_cl_ag_$N.err 2>/dev/null | cut -c1-300
