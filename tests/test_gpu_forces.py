@@ -340,3 +340,68 @@ def test_nonperiodic_cutoff_with_distinct_replicas():
         assert (F2[0] - F[0]).abs().max().item() < tol and (F2[2] - F[2]).abs().max().item() < tol
     else:
         assert torch.equal(F2[0], F[0]) and torch.equal(F2[2], F[2])
+
+
+def _lj_coulomb_parameters(n, prec, dev):
+    from torchmd_b200.parameters import TopologyParameters
+
+    return TopologyParameters(atom_types=np.zeros(n, int), type_sigma=[1.2], type_epsilon=[0.05], charges=np.where(np.arange(n) % 2, 0.2, -0.2).astype(np.float32),
+                              masses=np.full(n, 12.0, np.float32), precision=prec, device=dev)
+
+
+def test_a_fresh_box_tensor_per_call_is_always_taken():
+    """A new box tensor for every call (one per frame of a trajectory, per batch of a data loader): the caching
+    allocator hands the same address back with version 0; the upload must not be skipped."""
+    from torchmd_b200 import Forces
+
+    n = 120
+    rng = np.random.default_rng(5)
+    lattice = np.stack(np.meshgrid(*[np.arange(5)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * 4.4 + 1.0
+    coords = torch.tensor((lattice + rng.normal(0, 0.4, lattice.shape))[None], dtype=torch.float32)
+    terms, cfg = ["lj", "electrostatics"], dict(cutoff=9.0, rfa=True, solventDielectric=78.5)
+    f = Forces(_lj_coulomb_parameters(n, torch.float32, DEV), terms=terms, **cfg)
+    o = refmd.OracleForces(_lj_coulomb_parameters(n, torch.float64, "cpu"), terms, decision_dtype=torch.float32, **cfg)
+    p = coords.to(DEV)
+    F = torch.zeros_like(p)
+    seen = set()
+    for L in (22.0, 23.5, 25.0, 22.0):
+        box = (torch.eye(3) * L)[None].to(DEV)  # fresh tensor; the previous one was dropped at the end of the last turn
+        seen.add(box.data_ptr())
+        E = f.compute(p, box, F, returnDetails=True)
+        F64 = torch.zeros(1, n, 3, dtype=torch.float64)
+        E64 = o.compute(coords.double(), (torch.eye(3, dtype=torch.float64) * L)[None], F64)
+        assert float((F.cpu().double() - F64).abs().max()) < force_tol(F64.numpy()), L
+        assert abs(E[0]["electrostatics"] - E64[0]["electrostatics"]) < 1e-3, L
+        del box
+    # (whether the allocator really recycled the address is up to it: len(seen) == 1 on the B200 runs so far)
+
+
+def test_dense_cluster_in_a_large_box_without_the_numpy_outputs():
+    """Row capacities are sized from the MEAN density: 240 atoms in a 12 A blob inside a 90 A box overflow them on the
+    first build.  The toNumpy=False, autograd and vmap callers must get complete lists too (grown and recomputed)."""
+    from torchmd_b200 import Forces
+
+    n = 240
+    rng = np.random.default_rng(11)
+    g = np.stack(np.meshgrid(*[np.arange(7)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * 1.7 + 40.0
+    coords = torch.tensor((g + rng.normal(0, 0.05, g.shape))[None], dtype=torch.float32)
+    box = (torch.eye(3) * 90.0)[None]
+    terms, cfg = ["lj", "electrostatics"], dict(cutoff=9.0, rfa=True, solventDielectric=78.5)
+    o = refmd.OracleForces(_lj_coulomb_parameters(n, torch.float64, "cpu"), terms, decision_dtype=torch.float32, **cfg)
+    F64 = torch.zeros(1, n, 3, dtype=torch.float64)
+    E64 = o.compute(coords.double(), box.double(), F64)
+    want = sum(E64[0].values()) if isinstance(E64[0], dict) else float(E64[0])
+
+    f = Forces(_lj_coulomb_parameters(n, torch.float32, DEV), terms=terms, **cfg)
+    p, b = coords.to(DEV), box.to(DEV)
+    F = torch.zeros_like(p)
+    E = f.compute(p, b, F, toNumpy=False)  # first call of a new context, device outputs
+    assert f.stats()["max_neighbours"] <= f.stats()["row_capacity"]
+    assert float((F.cpu().double() - F64).abs().max()) < force_tol(F64.numpy())
+    assert abs(float(E[0]) - want) < 2e-3 + 1e-5 * abs(want)
+
+    f2 = Forces(_lj_coulomb_parameters(n, torch.float32, DEV), terms=terms, **cfg)
+    q = p.clone().requires_grad_(True)
+    e = f2.compute(q, b, torch.zeros_like(p), toNumpy=False, explicit_forces=False)  # first call: the autograd path
+    e.sum().backward()
+    assert float((-q.grad.cpu().double() - F64).abs().max()) < force_tol(F64.numpy())

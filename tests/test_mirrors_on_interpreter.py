@@ -71,6 +71,13 @@ def test_forces_api_formats_errors_replicas_and_skin(hostsim):
     G.test_molecules_several_boxes_away_meet_the_plain_yardstick()  # (gated on the GPU until its first B200 run)
 
 
+def test_box_upload_and_overflow_checks_on_every_path(hostsim):
+    import test_gpu_forces as G
+
+    G.test_a_fresh_box_tensor_per_call_is_always_taken()
+    G.test_dense_cluster_in_a_large_box_without_the_numpy_outputs()
+
+
 def test_repulsion_terms(hostsim):
     import test_gpu_zz_more_terms as M
 

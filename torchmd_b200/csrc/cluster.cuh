@@ -61,6 +61,9 @@ constexpr int CL_WARPS = CL_WARPS_N;
 constexpr int CL_UNROLL_N = CL_UNROLL;
 constexpr int CLB_WARPS = 4;   // list build: warps per CTA
 constexpr int CLB_MAXSEG = 160;
+#ifndef CLB_EXACT
+#define CLB_EXACT 1  // list test against the cluster's atoms (1) or its bounding box (0)
+#endif
 constexpr int CL_SIMT_MAX_ENTRIES = 4096;  // interpreter build (tests/simt): entries per cluster its static buffer holds
 constexpr int CL_SIMT_MAX_TYPES = 64;       // ... and atom types its static table holds
 
@@ -302,6 +305,17 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
       lo[d] = __shfl_sync(0xffffffffu, lo[d], 0);
       hi[d] = __shfl_sync(0xffffffffu, hi[d], 0);
     }
+#if CLB_EXACT
+    float ax[CL], ay[CL], az[CL];
+#pragma unroll
+    for (int k = 0; k < CL; ++k) {
+      ax[k] = __shfl_sync(0xffffffffu, pw.x, k);
+      if (!((realmask >> k) & 1u)) ax[k] = 1.0e15f;
+      ay[k] = __shfl_sync(0xffffffffu, pw.y, k);
+      az[k] = __shfl_sync(0xffffffffu, pw.z, k);
+    }
+    const float rl2x = rl2 * 1.00001f;  // (rounding of the float test must never drop a pair the skin argument counts on)
+#endif
     if (realmask == 0) {  // (cannot happen: padding only ever completes a cluster)
       if (lane == 0) C.meta[cb + c] = make_int2(0, 0);
       continue;
@@ -498,9 +512,21 @@ __global__ void __launch_bounds__(CLB_WARPS * 32) k_cbuild(DeviceState S) {
         sj = sgm.begin + (idx - sh.pre[w][sg]);
         const float4 p = C.xw[sb + sj];
         const float x = p.x + sgm.sx, y = p.y + sgm.sy, z = p.z + sgm.sz;
+#if CLB_EXACT
+        // within the list radius of one of the cluster's atoms (a bounding-box test keeps ~15 % more partners: the
+        // corners of the box hold no atom); padding records are 1e30 away, a missing cluster atom is at 1e15
+        float d2 = INFINITY;
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+          const float ux = x - ax[k], uy = y - ay[k], uz = z - az[k];
+          d2 = fminf(d2, fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
+        }
+        take = d2 < rl2x;
+#else
         const float ex = fmaxf(fmaxf(lo[0] - x, x - hi[0]), 0.f), ey = fmaxf(fmaxf(lo[1] - y, y - hi[1]), 0.f),
                     ez = fmaxf(fmaxf(lo[2] - z, z - hi[2]), 0.f);
         take = ex * ex + ey * ey + ez * ez < rl2;  // (padding records are 1e30 away)
+#endif
         if (sgm.own) {  // own row: the clusters in the next half of the row's cyclic order
           const int cj = (sj - row_s) / CL;
           int dd = cj - ci_row;

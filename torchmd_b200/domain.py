@@ -113,6 +113,7 @@ class DecomposedIntegrator:
         self.use_graph = use_graph
         self._graphs = {}
         self._parity = 0  # p2p: which of the two position buffers holds the current positions
+        self._marks = None  # bench.py: list that collects the phase events of eagerly issued steps
         if self.exchange == "p2p" and not self._connect_peers():
             self.exchange = "allgather"
 
@@ -162,35 +163,52 @@ class DecomposedIntegrator:
         return self._all_ok(err, "mapping the peers' buffers")
 
     # one MD step on the current stream; with_energy: also this rank's energy / KE share
-    def _enqueue_step_p2p(self, with_energy, parity):
-        s, ig, L = self.system, self.integ, _lib.lib()
-        stream = torch.cuda.current_stream(s.pos.device).cuda_stream
-        thermostat = bool(ig.T)
-        gamma = float(ig.gamma) if thermostat else -1.0
-        vcoeff = ig.vcoeff.data_ptr() if thermostat else None
-        _lib.check(L.tmd_dd_vv_first_push(self.ctx, parity, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
-        _lib.check(L.tmd_dd_wait(self.ctx, stream))
-        _lib.check(L.tmd_dd_forces(self.ctx, 1 - parity, s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
-        _lib.check(
-            L.tmd_vv_second(self.ctx, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, gamma, vcoeff,
-                            None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
-        )
+    def _mark(self, marks):
+        """Phase boundary of an eagerly issued step (bench.py's per-phase breakdown): a CUDA event on the stream."""
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
 
-    def _enqueue_step(self, with_energy, parity=0):
-        if self.exchange == "p2p":
-            return self._enqueue_step_p2p(with_energy, parity)
+    def _enqueue_step_p2p(self, with_energy, parity, marks=None):
         s, ig, L = self.system, self.integ, _lib.lib()
         stream = torch.cuda.current_stream(s.pos.device).cuda_stream
         thermostat = bool(ig.T)
         gamma = float(ig.gamma) if thermostat else -1.0
         vcoeff = ig.vcoeff.data_ptr() if thermostat else None
-        _lib.check(L.tmd_vv_first(self.ctx, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
-        self.dec.gather(self.buf, self.send, self.group)  # the exchange step: new positions to everyone
-        _lib.check(L.tmd_forces(self.ctx, s.pos.data_ptr(), s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
+        self._mark(marks)
+        _lib.check(L.tmd_dd_vv_first_push(self.ctx, parity, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
+        self._mark(marks)
+        _lib.check(L.tmd_dd_wait(self.ctx, stream))
+        self._mark(marks)
+        _lib.check(L.tmd_dd_forces(self.ctx, 1 - parity, s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
+        self._mark(marks)
         _lib.check(
             L.tmd_vv_second(self.ctx, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, gamma, vcoeff,
                             None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
         )
+        self._mark(marks)
+
+    def _enqueue_step(self, with_energy, parity=0, marks=None):
+        if self.exchange == "p2p":
+            return self._enqueue_step_p2p(with_energy, parity, marks)
+        s, ig, L = self.system, self.integ, _lib.lib()
+        stream = torch.cuda.current_stream(s.pos.device).cuda_stream
+        thermostat = bool(ig.T)
+        gamma = float(ig.gamma) if thermostat else -1.0
+        vcoeff = ig.vcoeff.data_ptr() if thermostat else None
+        self._mark(marks)
+        _lib.check(L.tmd_vv_first(self.ctx, s.pos.data_ptr(), s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, stream))
+        self._mark(marks)
+        self.dec.gather(self.buf, self.send, self.group)  # the exchange step: new positions to everyone
+        self._mark(marks)
+        _lib.check(L.tmd_forces(self.ctx, s.pos.data_ptr(), s.forces.data_ptr(), self.ene.data_ptr() if with_energy else None, stream))
+        self._mark(marks)
+        _lib.check(
+            L.tmd_vv_second(self.ctx, s.vel.data_ptr(), s.forces.data_ptr(), ig.masses.data_ptr(), ig.dt, gamma, vcoeff,
+                            None, ig.seed, 0, self.ke.data_ptr() if with_energy else None, stream)
+        )
+        self._mark(marks)
 
     def _graph(self, with_energy, parity=0):
         """Capture one step (kernels + exchange) once per variant; None if capture is not possible.
@@ -233,7 +251,7 @@ class DecomposedIntegrator:
             if g is not None:
                 g.replay()
             else:
-                self._enqueue_step(last, self._parity)
+                self._enqueue_step(last, self._parity, self._marks)
             if p2p:
                 self._parity ^= 1
         if p2p:
@@ -308,9 +326,21 @@ def bench_decomposed(args, world, rank, local, config):
     eager.use_graph, eager._graphs = False, {}
     nprof = min(100, args.steps)
     _lib.check(L.tmd_profile_begin(forces._ctx, nprof))
+    eager._marks = []
     eager.step(niter=nprof)
     pair_ms, pair_n = C.c_double(), C.c_int()
     _lib.check(L.tmd_profile_end(forces._ctx, C.byref(pair_ms), C.byref(pair_n), stream))
+    # phases of the eagerly issued steps (5 events per step): this rank's averages, then the slowest rank of each
+    phase_names = ["integrate_first_half" + ("+push" if integ.exchange == "p2p" else ""), "exchange_wait" if integ.exchange == "p2p" else "exchange_allgather",
+                   "forces_total(prepare+rebuild+pair+bonded)", "integrate_second_half"]
+    phases = torch.zeros(4, dtype=torch.float64, device=dev)
+    mk = eager._marks
+    if B.DEVICE_OVERRIDE is None and len(mk) == 5 * nprof:
+        for k in range(nprof):
+            for q in range(4):
+                phases[q] += mk[5 * k + q].elapsed_time(mk[5 * k + q + 1])
+        phases /= nprof
+    dist.all_reduce(phases, op=dist.ReduceOp.MAX)
     t = torch.tensor([ev0.elapsed_time(ev1), pair_ms.value / max(1, pair_n.value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank
     ms_total, pair_avg_ms = float(t[0]), float(t[1])
@@ -410,6 +440,8 @@ def bench_decomposed(args, world, rank, local, config):
             "epot": float(pot[0]),
             "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
             "cuda_graph": bool(integ.use_graph),
+            "phase_ms_eager_slowest_rank": {k: float(v) for k, v in zip(phase_names, phases.tolist())},
+            "phase_note": "CUDA events between the calls of %d steps issued kernel by kernel after the timed region (the timed steps are graph replays); per phase the maximum over ranks, so the sum exceeds one step of the slowest rank" % nprof,
             "collective": "one all-gather of positions per step (NCCL)" if integ.exchange == "allgather"
             else "none: positions stored into every rank's buffer by the integration kernel (NVLink peer memory) + flag wait",
         },

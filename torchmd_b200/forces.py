@@ -109,6 +109,7 @@ class Forces:
         self._ctx = None
         self._ctx_key = None
         self._box_key = None
+        self._box_ref = None  # the tensor _box_key describes (held so that its storage is not recycled)
         self._scratch_forces = None
         self._exact_gradient = False  # force convention currently set in the context
 
@@ -166,7 +167,7 @@ class Forces:
         _lib.check(L.tmd_create(C.byref(handle), key[0], self.natoms, nrep))
         ctx = handle
         self._configure(L, ctx, _lib.check)
-        self._ctx, self._ctx_key, self._box_key = ctx, key, None
+        self._ctx, self._ctx_key, self._box_key, self._box_ref = ctx, key, None, None
         self._exact_gradient = False
         return ctx
 
@@ -237,19 +238,23 @@ class Forces:
             check(L.tmd_set_pairs14(ctx, len(idx), _lib.ptr(idx), _lib.ptr(prm)))
 
     def _ensure_box(self, box):
-        """Hand the box diagonal to the context when the tensor changed (one D2H copy)."""
-        key = (box.data_ptr(), box._version, tuple(box.shape))
-        if key == self._box_key:
+        """Hand the box diagonal to the context when the tensor changed (one D2H copy).  The tensor the
+        key was taken from is kept alive: its storage cannot go back to the caching allocator, so a
+        fresh box tensor can never reproduce the (address, version) of the one already uploaded."""
+        key = (box.data_ptr(), box._version, tuple(box.shape), tuple(box.stride()))
+        if key == self._box_key and self._box_ref is not None:
             return
         diag = np.ascontiguousarray(torch.diagonal(box, dim1=1, dim2=2).detach().cpu().numpy().astype(np.float32))
         _lib.check(_lib.lib().tmd_set_box(self._ctx, _lib.ptr(diag)))
-        self._box_key = key
+        self._box_key, self._box_ref = key, box
 
     # ------------------------------------------------------------------ compute
     def _evaluate(self, pos, box, forces, sync=True, exact_gradient=False):
         """One pass of the kernels: forces (R,N,3) overwritten, returns the (R, NUM_ENERGIES) fp64
-        device energies.  ``sync``: check the neighbour rows now (synchronises; a row overflow
-        grows the capacity and recomputes) instead of at the next ``stats()``.
+        device energies.  The list-overflow flags are read after every pass (one small D2H read; a
+        row or cluster-list overflow grows the capacity and recomputes, so no caller -- the autograd,
+        vmap and toNumpy=False paths included -- ever sees a truncated list).  ``sync=False`` skips
+        that read; only for a second pass over positions whose lists the first pass just checked.
         ``exact_gradient``: the switched-LJ force as the true derivative of the energy (what the
         reference's autograd path yields) instead of its explicit formula (forces.py:410-412)."""
         self._check_tensor(pos, "pos")
@@ -312,7 +317,7 @@ class Forces:
             sel, F = _EnergyFunction.apply(pos, box, self)
             if forces is not None:
                 if explicit_forces:  # the buffer gets the explicit-formula forces, the graph the true gradient
-                    self._evaluate(pos.detach(), box, forces, sync=False, exact_gradient=False)
+                    self._evaluate(pos.detach(), box, forces, exact_gradient=False)
                 else:
                     forces.copy_(F)
             ext = None
@@ -330,7 +335,7 @@ class Forces:
             if self._scratch_forces is None or self._scratch_forces.shape != pos_in.shape:
                 self._scratch_forces = torch.empty_like(pos_in)
             forces = self._scratch_forces
-        ene = self._evaluate(pos_in, box, forces, sync=toNumpy, exact_gradient=calculateForces and not explicit_forces)
+        ene = self._evaluate(pos_in, box, forces, exact_gradient=calculateForces and not explicit_forces)
 
         ext = None
         if self.external:
@@ -387,7 +392,7 @@ class Forces:
         st = _lib.Stats()
         import ctypes as C
 
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.current_stream(torch.device("cuda", self._ctx_key[0])).cuda_stream  # of the context's device, not the current one
         _lib.check(_lib.lib().tmd_get_stats(self._ctx, C.byref(st), stream))
         return {
             "rebuilds": st.rebuilds,
@@ -438,7 +443,7 @@ class _EnergyFunction(torch.autograd.Function):
     def forward(pos, box, owner):
         F = torch.empty_like(pos, memory_format=torch.contiguous_format)
         p = pos.detach().contiguous()
-        ene = owner._evaluate(p, box.detach().contiguous(), F, sync=False, exact_gradient=True)
+        ene = owner._evaluate(p, box.detach().contiguous(), F, exact_gradient=True)
         return ene[:, owner._energy_columns()].to(pos.dtype), F
 
     @staticmethod

@@ -133,6 +133,9 @@ class Integrator:
         if native and niter > 0:
             f = self.forces
             f._ensure_box(s.box)
+            if f._exact_gradient:  # left behind by an autograd-path compute(): MD uses the reference's explicit forces
+                _lib.check(L.tmd_set_force_convention(ctx, 0))
+                f._exact_gradient = False
             ene = torch.empty((nrep, _lib.NUM_ENERGIES), dtype=torch.float64, device=s.pos.device)
             # A neighbour list that outgrows its reserved capacity inside the fused call invalidates the call (the
             # kernels truncate, the library grows the capacity at the stats() check).  The state is three small

@@ -84,7 +84,7 @@ class Wrapper:
             h = C.c_void_p()
             _lib.check(_lib.lib().tmd_wrapper_create(C.byref(h), pos.device.index or 0, self.natoms, len(self._ptr) - 1,
                                                      self._ptr.ctypes.data, self._atoms.ctypes.data))
-            self._handle = h
+            self._handle, self._device = h, pos.device
         return self._handle
 
     def wrap(self, pos, box, wrapidx=None):
@@ -100,6 +100,8 @@ class Wrapper:
         if not pos.is_contiguous() or not box.is_contiguous():
             raise RuntimeError("wrap: pos and box must be contiguous")
         h = self._ensure(pos)
+        if not _lib.on_device(pos) or not _lib.on_device(box) or pos.device != self._device or box.device != pos.device:
+            raise RuntimeError(f"wrap: pos and box must both live on {self._device} (got {pos.device} and {box.device})")
         stream = torch.cuda.current_stream(pos.device).cuda_stream
         _lib.check(_lib.lib().tmd_wrapper_wrap(h, pos.data_ptr(), box.data_ptr(), pos.shape[0], stream))
 
