@@ -190,6 +190,39 @@ def test_cluster_md_steps_follow_the_full_list_trajectory(host_cl, monkeypatch):
     assert abs(out[0][3][0] - out[1][3][0]) < 1e-5 * abs(out[1][3][0]) + 5e-3
 
 
+@pytest.mark.parametrize("graph", ["0", "1"])
+def test_step_boundary_kernel_reproduces_the_two_kernel_sequence(host_cl, monkeypatch, graph):
+    """TMD_B200_FUSESTEP: the second half of a step and the first half of the next in one kernel (k_cstep_boundary), with
+    the Langevin draws of the step it closes -- the same trajectory, bit for bit, as second-half kernel + first-half
+    kernel (the interpreter sums in a fixed order), through rebuilds, eagerly issued and as captured steps."""
+    from torchmd_b200 import Forces, Integrator, System, maxwell_boltzmann, testsystems
+
+    sysd = tiled_water(2)
+    monkeypatch.setenv("TMD_B200_GRAPH", graph)
+    out = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("TMD_B200_FUSESTEP", fuse)
+        par = testsystems.water_parameters(sysd, device="cpu")
+        system = System(len(sysd["coords"]), 1, torch.float32, "cpu")
+        system.set_positions(np.array(sysd["coords"], dtype=np.float32))
+        system.set_box(sysd["box"])
+        torch.manual_seed(3)
+        system.set_velocities(maxwell_boltzmann(par.masses, 300.0, 1))
+        forces = Forces(par, terms=TERMS, **CFG, skin=0.3)
+        integ = Integrator(system, forces, 1.0, "cpu", gamma=0.5, T=300.0)
+        l0 = 0
+        res = []
+        for niter in (1, 2, 7):  # one step (no boundary), first+last, first+middle+last
+            ekin, pot, temp = integ.step(niter=niter)
+            res.append((float(ekin[0]), float(pot[0])))
+        st = forces.stats()
+        assert host_cl.tmd_pair_kernel(forces._ctx) == 4 and st["rebuilds"] >= 2, st
+        out.append((system.pos.clone(), system.vel.clone(), system.forces.clone(), res, st["kernel_launches"]))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert out[0][3] == out[1][3]
+    assert out[0][4] < out[1][4]  # fewer launches
+
+
 def test_cluster_path_with_owned_atom_ranges(host_cl):
     """Decomposed runs: a context that owns a range of atoms builds lists only for the pairs that touch an owned atom;
     its forces on the owned atoms are the full forces, and the ranks' energy shares add up to the total."""

@@ -708,7 +708,10 @@ k_cpair(DeviceState S, SwitchConsts sc, double* __restrict__ energies) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const size_t sb = cl_slot_base(C, r), cb = cl_cluster_base(C, r);
   const int stride_e = C.mcap + C.ecap;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[0] += 1;  // next call: other flag
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    S.counters[0] += 1;              // next call: other flag
+    S.counters[2] = S.counters[1];   // this step's Philox position, for k_cstep_boundary (which advances [1] while it reads)
+  }
   const size_t buf_bytes_h = (size_t)stride_e * 4 + C.mcap;  // entry words + mask bytes of one buffer
   unsigned char* buf0 = cl_dyn + (size_t)w * 2 * buf_bytes_h;
   ClTab* tab = reinterpret_cast<ClTab*>(cl_dyn + (size_t)CL_WARPS * 2 * buf_bytes_h) + (size_t)w * S.ntypes * CL_H;

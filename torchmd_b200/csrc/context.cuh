@@ -77,7 +77,7 @@ struct DeviceState {
   int nsub;         // cells per list radius
   int build_split;  // full-row list build: CTAs that share one cell (grids of a few cells)
   int own_lo, own_n, own_all;  // atoms (original indices) whose forces this context computes; all by default
-  unsigned long long* counters;  // [0] force calls (parity of the rebuild flag), [1] vv_first calls (Philox position)
+  unsigned long long* counters;  // [0] force calls (parity of the rebuild flag), [1] vv_first calls (Philox position), [2] copy of [1] taken by the cluster pair kernel
   unsigned long long cond;       // cudaGraphConditionalHandle of the rebuild body when this launch is a graph node; 0 otherwise
   int check_far;    // flag positions beyond 2000 box lengths (guard-free minimum image in use)
   // per-atom static data (original order)
@@ -154,6 +154,7 @@ struct tmd_ctx {
   int4* xf_buf = nullptr;            // fixed-point records (periodic pair kernel), owned; d.xf_s points here when in use
   bool cluster_failed = false;       // the cluster path reported F_CLFAIL: full rows until cluster_retry_at force calls
   int64_t cluster_retry_at = 0, cluster_retry_after = 0;
+  int64_t rebuilds_before = 0;  // list builds counted before the last (re-)finalisation cleared the device flags
   // peer-to-peer position exchange (tmd_dd_*): one cudaMalloc holding [pos0 | pos1 | flags | sync]
   int dd_rank = -1, dd_world = 0;
   bool dd_connected = false;

@@ -116,4 +116,50 @@ k_cvv_second_fold(DeviceState S, float* __restrict__ vel, float* __restrict__ fo
   }
 }
 
+// Between two steps of one tmd_md_steps call, the second half of step n and the first half of step n+1 touch the
+// same atoms with nothing in between (integrator.py:115-120 then :112-114 of the next iteration): one pass brings
+// the pair force home, adds the bonded sum, finishes the kick of step n, kicks and drifts for step n+1 and prepares
+// the next force call (list check, slot records) from the position it still holds -- k_cvv_second_fold followed by
+// k_vv_first_prepare without the round trip of forces and velocities through memory and without the second launch.
+// The forces buffer is not written: the last step of the call ends with k_cvv_second_fold, which stores it.
+// Philox position of step n: counters[2], the copy of counters[1] that step n's pair kernel took (this kernel
+// advances counters[1] for step n+1 while its other threads are still reading).
+template <bool THERMOSTAT>
+__global__ void __launch_bounds__(INTEG_THREADS)
+k_cstep_boundary(DeviceState S, float* __restrict__ pos, float* __restrict__ vel, const float* __restrict__ masses, float dt,
+                 float hdt, float neg_gamma, const float* __restrict__ vcoeff, uint64_t seed, uint64_t step_offset,
+                 const double* __restrict__ scratch) {
+  const int parity = (int)(S.counters[0] & 1ull);
+  const int r = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // whole system
+  const uint64_t step = step_offset + S.counters[2];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S.counters[1] += 1;  // Philox position of step n+1
+  if (i == 0) S.flags[r * F_COUNT + F_REBUILD0 + (parity ^ 1)] = 0;
+  if (i >= S.natoms) return;
+  const size_t slot = (size_t)r * S.natoms + i;
+  const size_t a = slot * 3;
+  const float4 pf = S.cl.f[(size_t)r * (S.cl.slots + 1) + S.cl.inv[slot]];
+  const float f[3] = {(float)((double)pf.x + scratch[a]), (float)((double)pf.y + scratch[a + 1]), (float)((double)pf.z + scratch[a + 2])};
+  const float m = masses[i];
+  float xi[3] = {0.f, 0.f, 0.f};
+  float vc = 0.f;
+  if (THERMOSTAT) {
+    vc = vcoeff[i];
+    normal3(seed, step, slot, xi);
+  }
+  float x[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float v = vel[a + d];
+    if (THERMOSTAT) v = add_rn(v, add_rn(mul_rn(mul_rn(neg_gamma, v), dt), mul_rn(xi[d], vc)));
+    const float acc = div_rn(f[d], m);
+    v = add_rn(v, mul_rn(hdt, acc));  // end of step n
+    const float drift = add_rn(mul_rn(v, dt), mul_rn(mul_rn(mul_rn(0.5f, acc), dt), dt));
+    x[d] = add_rn(pos[a + d], drift);
+    pos[a + d] = x[d];
+    vel[a + d] = add_rn(v, mul_rn(hdt, acc));
+  }
+  prepare_atom(S, r, i, parity, x[0], x[1], x[2]);
+}
+
 }  // namespace tmd

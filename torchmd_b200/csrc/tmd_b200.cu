@@ -66,6 +66,9 @@ int fail(int code, const std::string& msg) {
 #ifndef TMD_DEFAULT_GRAPH
 #define TMD_DEFAULT_GRAPH 1     // TMD_B200_GRAPH: tmd_md_steps replays a captured step
 #endif
+#ifndef TMD_DEFAULT_FUSESTEP
+#define TMD_DEFAULT_FUSESTEP 1  // TMD_B200_FUSESTEP: second half of a step and first half of the next one in one kernel
+#endif
 #ifndef TMD_DEFAULT_FUSEPREP
 #define TMD_DEFAULT_FUSEPREP 1  // TMD_B200_FUSEPREP: integrate + prepare in one kernel, bonded fold in the second kick
 #endif
@@ -154,8 +157,13 @@ struct CtxPriv {
   bool use_graph = false;
   cudaStream_t gstream = nullptr;    // capture + replay stream (the caller's may be the legacy default stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaGraphExec_t exec[2] = {nullptr, nullptr};
-  cudaGraph_t graph[2] = {nullptr, nullptr};
+  // [0] a whole step, [1] a whole step with the energy outputs (the last, or only, step of a call);
+  // TMD_B200_FUSESTEP=1 (cluster path): [2] the first step of a call without its second half-kick, [3] a middle
+  // step that opens with k_cstep_boundary (second half of the step before + first half of this one), [4] the last
+  // step: boundary, force call with energies, second half-kick with the kinetic energy
+  static constexpr int NGRAPH = 5;
+  cudaGraphExec_t exec[NGRAPH] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaGraph_t graph[NGRAPH] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   struct StepKey {
     float *pos, *vel, *forces;
     const float *masses, *vcoeff;
@@ -165,10 +173,12 @@ struct CtxPriv {
   } step_key{};
   DeviceState step_state{};          // the kernel arguments baked into the captured steps
   bool steps_valid = false;
-  int64_t step_launches[2] = {0, 0};  // kernels of one captured step (rebuild body included)
+  int64_t step_launches[5] = {0, 0, 0, 0, 0};  // kernels of one captured step (rebuild body included)
   // TMD_B200_FUSEPREP=1: tmd_md_steps moves the atoms and prepares the force call in one kernel
   // (k_vv_first_prepare); the handle of the rebuild's conditional node is then made before that launch
   bool fuse_prepare = false;
+  bool flags_live = false;  // the device flags hold counts of this context (set by the first finalisation)
+  bool fuse_step = false;   // TMD_B200_FUSESTEP=1: k_cstep_boundary between the steps of one tmd_md_steps call
   bool fold_next = false;                       // tmd_md_steps: the vv_second that follows folds the bonded sums in (k_vv_second_fold)
   bool fold_pending = false;                    // set by enqueue_forces when it left them in the scratch buffer
   bool prepared = false;                        // the next enqueue_forces finds k_prepare's work done
@@ -255,8 +265,8 @@ int tmd_create(tmd_ctx** out, int device, int natoms, int nreplicas) {
   if ((rc = device_alloc(&d.flags, (size_t)nreplicas * F_COUNT))) return rc;
   if ((rc = device_alloc(&d.grid, (size_t)nreplicas))) return rc;
   if ((rc = device_alloc(&d.bounds, (size_t)nreplicas * 6))) return rc;
-  if ((rc = device_alloc(&d.counters, (size_t)2))) return rc;
-  TMD_CUDA(cudaMemset(d.counters, 0, 2 * sizeof(unsigned long long)));
+  if ((rc = device_alloc(&d.counters, (size_t)4))) return rc;
+  TMD_CUDA(cudaMemset(d.counters, 0, 4 * sizeof(unsigned long long)));
   d.own_lo = 0;
   d.own_n = natoms;
   d.own_all = 1;
@@ -285,7 +295,7 @@ int tmd_destroy(tmd_ctx* ctx) {
   dd_release(ctx);
   for (void* b : priv(ctx).cl_bufs) cudaFree(b);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < CtxPriv::NGRAPH; ++k) {
     if (priv(ctx).exec[k]) cudaGraphExecDestroy(priv(ctx).exec[k]);
     if (priv(ctx).graph[k]) cudaGraphDestroy(priv(ctx).graph[k]);
   }
@@ -675,6 +685,12 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
   }
   TMD_CUDA(cudaMemcpy(d.grid, grids.data(), (size_t)R * sizeof(Grid), cudaMemcpyHostToDevice));
   TMD_CUDA(cudaMemset(d.pos_ref, 0xFF, (size_t)R * N * sizeof(float4)));  // NaN: forces a build
+  if (priv(ctx).flags_live) {  // a re-finalisation (grown lists, another pair path): the build count carries over
+    std::vector<int> fl((size_t)R * F_COUNT);
+    TMD_CUDA(cudaMemcpy(fl.data(), d.flags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < R; ++r) ctx->rebuilds_before += fl[r * F_COUNT + F_NREBUILD];
+  }
+  priv(ctx).flags_live = true;
   TMD_CUDA(cudaMemset(d.flags, 0, (size_t)R * F_COUNT * sizeof(int)));
   TMD_CUDA(cudaMemset(d.counters, 0, sizeof(unsigned long long)));  // flag parity restarts with the flags
   {
@@ -767,6 +783,7 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
       TMD_CUDA(cudaEventCreateWithFlags(&pv.ev_out, cudaEventDisableTiming));
     }
     pv.fuse_prepare = env_switch("TMD_B200_FUSEPREP", TMD_DEFAULT_FUSEPREP) == 1;
+    pv.fuse_step = env_switch("TMD_B200_FUSESTEP", TMD_DEFAULT_FUSESTEP) == 1;
     pv.steps_valid = false;  // buffers may have moved: captured steps are rebuilt
   }
   priv(ctx).dirty = false;
@@ -1024,8 +1041,15 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
   return TMD_OK;
 }
 
+// the step boundary of tmd_md_steps (fused.cuh, k_cstep_boundary): what enqueue_vv_second + enqueue_vv_first would do
+struct BoundaryArgs {
+  double gamma;
+  const float* vcoeff;
+  uint64_t seed, step;
+};
+
 static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* forces, const float* masses,
-                            double dt, cudaStream_t st, bool forces_follow = false) {
+                            double dt, cudaStream_t st, bool forces_follow = false, const BoundaryArgs* boundary = nullptr) {
   CtxPriv& pv = priv(ctx);
   if (forces_follow && pv.fuse_prepare && ctx->d.own_all && ctx->pair_mask) {
     // the force call that follows on this stream finds its preparation done
@@ -1039,6 +1063,16 @@ static int enqueue_vv_first(tmd_ctx* ctx, float* pos, float* vel, const float* f
         TMD_CUDA(cudaGraphConditionalHandleCreate(&pv.prepared_cond, cap_graph, 0, cudaGraphCondAssignDefault));
         dp.cond = (unsigned long long)pv.prepared_cond;
       }
+    }
+    if (boundary) {  // the force call before left its fold to us (fold_pending)
+      pv.fold_pending = false;
+      const bool thermo = (boundary->gamma >= 0.0) && boundary->vcoeff != nullptr;
+      const float fdt = (float)dt, hdt = (float)(0.5 * dt), ng = (float)(-boundary->gamma);
+      if (thermo) launch(k_cstep_boundary<true>, atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, dp, pos, vel, masses, fdt, hdt, ng, boundary->vcoeff, boundary->seed, boundary->step, pv.bonded_scratch);
+      else launch(k_cstep_boundary<false>, atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, dp, pos, vel, masses, fdt, hdt, ng, boundary->vcoeff, boundary->seed, boundary->step, pv.bonded_scratch);
+      TMD_LAUNCHED(ctx, "k_cstep_boundary");
+      pv.prepared = true;
+      return TMD_OK;
     }
     launch(k_vv_first_prepare, atoms_grid(ctx, INTEG_THREADS), INTEG_THREADS, st, dp, pos, vel, forces, masses, (float)dt,
            (float)(0.5 * dt));
@@ -1174,6 +1208,11 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
     explicit FoldScope(CtxPriv& q, bool on) : p(q) { p.fold_next = on; }
     ~FoldScope() { p.fold_next = false; }
   } fold_scope(pv, pv.fuse_prepare);
+  // TMD_B200_FUSESTEP: inside one call the second half of a step and the first half of the next are one kernel
+  // (cluster path with the bonded kernel on the side stream: the force call leaves its fold to the integrator)
+  const bool fuse = pv.fuse_step && pv.fuse_prepare && ctx->d.cl.on && ctx->d.own_all && ctx->pair_mask && !noise &&
+                    ctx->bonded_nentries > 0 && pv.side != nullptr && niter >= 2;
+  const BoundaryArgs bargs{gamma, vcoeff, seed, first_step};
   if (pv.use_graph && !noise && !pv.profiling && niter > 0) {
     // One MD step captured once (with and without the energy outputs) and replayed: one graph
     // launch per step, the rebuild kernels inside a conditional node.  Everything that changes
@@ -1184,26 +1223,43 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
     if (cs == cudaStreamCaptureStatusNone) {
       const CtxPriv::StepKey key{pos, vel, forces, masses, vcoeff, dt, gamma, seed, first_step, energies, ke};
       if (!pv.steps_valid || memcmp(&key, &pv.step_key, sizeof(key)) != 0 || memcmp(&ctx->d, &pv.step_state, sizeof(DeviceState)) != 0) {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < CtxPriv::NGRAPH; ++k) {
           if (pv.exec[k]) cudaGraphExecDestroy(pv.exec[k]);
           if (pv.graph[k]) cudaGraphDestroy(pv.graph[k]);
           pv.exec[k] = nullptr;
           pv.graph[k] = nullptr;
-          const bool with_e = (k == 1);
-          const int64_t l0 = ctx->launches, f0 = ctx->force_calls;
-          TMD_CUDA(cudaStreamBeginCapture(pv.gstream, cudaStreamCaptureModeRelaxed));
-          rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, pv.gstream, true);
-          if (!rc) rc = enqueue_forces(ctx, pos, forces, with_e ? energies : nullptr, pv.gstream);
-          if (!rc) rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, nullptr, seed, first_step,
-                                          with_e ? ke : nullptr, pv.gstream);
-          cudaError_t ce = cudaStreamEndCapture(pv.gstream, &pv.graph[k]);
-          if (rc) return rc;
-          if (ce != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-          TMD_CUDA(cudaGraphInstantiate(&pv.exec[k], pv.graph[k], 0));
-          pv.step_launches[k] = ctx->launches - l0 - pv.last_body_launches;  // (the body runs on rebuild steps only: not counted)
-          ctx->launches = l0;  // the capture launched nothing; replays are counted below
-          ctx->force_calls = f0;
         }
+        pv.steps_valid = false;
+      }
+      // variants: 0 whole step, 1 whole step + energies, 2 first step without its second half-kick,
+      // 3 boundary + force call, 4 boundary + force call with energies + second half-kick with the kinetic energy
+      auto capture = [&](int k) -> int {
+        if (pv.exec[k]) return TMD_OK;
+        const bool with_e = (k == 1 || k == 4), opens_with_boundary = (k >= 3), closes = (k != 2 && k != 3);
+        const int64_t l0 = ctx->launches, f0 = ctx->force_calls;
+        TMD_CUDA(cudaStreamBeginCapture(pv.gstream, cudaStreamCaptureModeRelaxed));
+        int rc2 = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, pv.gstream, true, opens_with_boundary ? &bargs : nullptr);
+        if (!rc2) rc2 = enqueue_forces(ctx, pos, forces, with_e ? energies : nullptr, pv.gstream);
+        if (!rc2 && closes) rc2 = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, nullptr, seed, first_step,
+                                                    with_e ? ke : nullptr, pv.gstream);
+        pv.fold_pending = false;  // (variants 2 and 3 leave the fold to the graph that follows)
+        cudaError_t ce = cudaStreamEndCapture(pv.gstream, &pv.graph[k]);
+        if (rc2) return rc2;
+        if (ce != cudaSuccess) return fail(TMD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        TMD_CUDA(cudaGraphInstantiate(&pv.exec[k], pv.graph[k], 0));
+        pv.step_launches[k] = ctx->launches - l0 - pv.last_body_launches;  // (the body runs on rebuild steps only: not counted)
+        ctx->launches = l0;  // the capture launched nothing; replays are counted below
+        ctx->force_calls = f0;
+        return TMD_OK;
+      };
+      if (fuse) {
+        for (int k : {2, 3, 4})
+          if ((rc = capture(k))) return rc;
+      } else {
+        if (niter > 1 && (rc = capture(0))) return rc;
+        if ((rc = capture(1))) return rc;
+      }
+      if (!pv.steps_valid) {
         memset(&pv.step_key, 0, sizeof(pv.step_key));
         pv.step_key = key;
         pv.step_state = ctx->d;
@@ -1211,18 +1267,22 @@ int tmd_md_steps(tmd_ctx* ctx, int niter, float* pos, float* vel, float* forces,
       }
       TMD_CUDA(cudaEventRecord(pv.ev_in, st));
       TMD_CUDA(cudaStreamWaitEvent(pv.gstream, pv.ev_in, 0));
-      for (int it = 0; it < niter; ++it) TMD_CUDA(cudaGraphLaunch(pv.exec[it == niter - 1 ? 1 : 0], pv.gstream));
+      for (int it = 0; it < niter; ++it) {
+        const int k = fuse ? (it == 0 ? 2 : (it == niter - 1 ? 4 : 3)) : (it == niter - 1 ? 1 : 0);
+        TMD_CUDA(cudaGraphLaunch(pv.exec[k], pv.gstream));
+        ctx->launches += pv.step_launches[k];
+      }
       TMD_CUDA(cudaEventRecord(pv.ev_out, pv.gstream));
       TMD_CUDA(cudaStreamWaitEvent(st, pv.ev_out, 0));
       ctx->force_calls += niter;
-      ctx->launches += (int64_t)(niter - 1) * pv.step_launches[0] + pv.step_launches[1];
       return TMD_OK;
     }
   }
   for (int it = 0; it < niter; ++it) {
     const bool last = (it == niter - 1);
-    if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st, true))) return rc;
+    if ((rc = enqueue_vv_first(ctx, pos, vel, forces, masses, dt, st, true, fuse && it > 0 ? &bargs : nullptr))) return rc;
     if ((rc = enqueue_forces(ctx, pos, forces, last ? energies : nullptr, st))) return rc;
+    if (fuse && !last) continue;  // the next iteration's boundary kernel finishes this step
     if ((rc = enqueue_vv_second(ctx, vel, forces, masses, dt, gamma, vcoeff, noise ? noise + it * per_step : nullptr,
                                 seed, first_step, last ? ke : nullptr, st)))
       return rc;
@@ -1489,6 +1549,7 @@ int tmd_get_stats(tmd_ctx* ctx, tmd_stats* out, tmd_stream stream) {
   out->force_calls = ctx->force_calls;
   out->kernel_launches = ctx->launches;
   out->row_capacity = ctx->d.row_cap;
+  out->rebuilds = ctx->rebuilds_before;
   if (priv(ctx).dirty || !ctx->d.flags) return TMD_OK;
   std::vector<int> fl((size_t)ctx->nrep * F_COUNT);
   TMD_CUDA(cudaMemcpy(fl.data(), ctx->d.flags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
