@@ -177,6 +177,9 @@ struct CtxPriv {
   // TMD_B200_FUSEPREP=1: tmd_md_steps moves the atoms and prepares the force call in one kernel
   // (k_vv_first_prepare); the handle of the rebuild's conditional node is then made before that launch
   bool fuse_prepare = false;
+  double* term_forces = nullptr;  // k_bonded_terms -> k_bonded_sum: force of every (term, slot), fp64 (R x slots x 3)
+  size_t term_forces_len = 0;
+  bool bonded_terms = true;       // TMD_B200_BONDED_TERMS=0: the one-kernel atom-centric k_bonded
   bool flags_live = false;  // the device flags hold counts of this context (set by the first finalisation)
   bool fuse_step = false;   // TMD_B200_FUSESTEP=1: k_cstep_boundary between the steps of one tmd_md_steps call
   bool fold_next = false;                       // tmd_md_steps: the vv_second that follows folds the bonded sums in (k_vv_second_fold)
@@ -294,6 +297,7 @@ int tmd_destroy(tmd_ctx* ctx) {
     if (b) cudaFree(b);
   dd_release(ctx);
   for (void* b : priv(ctx).cl_bufs) cudaFree(b);
+  if (priv(ctx).term_forces) cudaFree(priv(ctx).term_forces);
   for (cudaEvent_t e : priv(ctx).ev) cudaEventDestroy(e);
   for (int k = 0; k < CtxPriv::NGRAPH; ++k) {
     if (priv(ctx).exec[k]) cudaGraphExecDestroy(priv(ctx).exec[k]);
@@ -739,6 +743,16 @@ static int finalize(tmd_ctx* ctx, cudaStream_t stream) {
     ctx->bonded_nentries = ptr[N];
     if ((rc = upload(&ctx->bonded_atom_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = upload(&ctx->bonded_entries, ent.data(), ent.size()))) return rc;
+    CtxPriv& pv = priv(ctx);
+    pv.bonded_terms = env_switch("TMD_B200_BONDED_TERMS", 1) == 1;
+    const size_t need = pv.bonded_terms ? (size_t)R * ptr[N] * 3 : 0;  // one slot per (term, atom of the term) = per entry
+    if (need > pv.term_forces_len) {
+      if (pv.term_forces) cudaFree(pv.term_forces);
+      pv.term_forces = nullptr;
+      pv.term_forces_len = 0;
+      if ((rc = device_alloc(&pv.term_forces, need))) return rc;
+      pv.term_forces_len = need;
+    }
   }
   // cooperative rebuild kernel: as many CTAs as can be co-resident, split over the replicas
   ctx->coop_blocks = 0;
@@ -876,6 +890,32 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     if (!(bm & TMD_TERM(TMD_E_IMPROPERS))) T.torsions[1].n = 0;
     if (!(bm & TMD_TERM(TMD_E_14))) T.pairs14.n = 0;
   }
+  // bonded forces of the owned atoms: terms in parallel, then the fixed-order sum per atom (bonded.cuh)
+  auto launch_bonded = [&](cudaStream_t bs, double* scratch) -> int {
+    CtxPriv& pv = priv(ctx);
+    if (!pv.bonded_terms) {
+      launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, bs, d, T, ctx->q, pos, forces, energies, scratch);
+      TMD_LAUNCHED(ctx, "k_bonded");
+      return TMD_OK;
+    }
+    TermLayout lay;
+    const int cnt[5] = {T.bonds.n, T.angles.n, T.torsions[0].n, T.torsions[1].n, T.pairs14.n};
+    int nt = 0, ns = 0;
+    for (int k = 0; k < 5; ++k) {
+      lay.first[k] = nt;
+      lay.slot0[k] = ns;
+      nt += cnt[k];
+      ns += cnt[k] * term_arity(k);
+    }
+    lay.nterms = nt;
+    lay.nslots = ns;
+    launch(k_bonded_terms, dim3((std::max(nt, 1) + BONDED_THREADS - 1) / BONDED_THREADS, R), BONDED_THREADS, bs, d, T, lay, ctx->q, pos,
+           energies, pv.term_forces);
+    TMD_LAUNCHED(ctx, "k_bonded_terms");
+    launch(k_bonded_sum, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, bs, d, T, lay, pv.term_forces, forces, scratch);
+    TMD_LAUNCHED(ctx, "k_bonded_sum");
+    return TMD_OK;
+  };
   // fork: the bonded terms need only the positions, so they run on a second stream while the
   // list check and the pair kernel run here; joined by k_add_bonded below
   const bool overlap = have_bonded && ctx->pair_mask && priv(ctx).side != nullptr;
@@ -883,8 +923,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     CtxPriv& pv = priv(ctx);
     TMD_CUDA(cudaEventRecord(pv.ev_fork, st));
     TMD_CUDA(cudaStreamWaitEvent(pv.side, pv.ev_fork, 0));
-    launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, pv.side, d, T, ctx->q, pos, forces, energies, pv.bonded_scratch);
-    TMD_LAUNCHED(ctx, "k_bonded");
+    if (int brc = launch_bonded(pv.side, pv.bonded_scratch)) return brc;
     TMD_CUDA(cudaEventRecord(pv.ev_join, pv.side));
   }
 
@@ -1032,8 +1071,7 @@ static int enqueue_forces(tmd_ctx* ctx, const float* pos, float* forces, double*
     priv(ctx).deferred_pos = pos;
   } else if (have_bonded) {
     // (cluster path: this kernel also brings the pair forces home from slot order)
-    launch(k_bonded, owned_grid(ctx, BONDED_THREADS), BONDED_THREADS, st, d, T, ctx->q, pos, forces, energies, nullptr);
-    TMD_LAUNCHED(ctx, "k_bonded");
+    if (int brc = launch_bonded(st, nullptr)) return brc;
   } else if (d.cl.on && ctx->pair_mask) {
     launch(k_cunsort, atoms_grid(ctx, 256), 256, st, d, forces);
     TMD_LAUNCHED(ctx, "k_cunsort");
