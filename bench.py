@@ -351,6 +351,11 @@ def gpu_arm(args):
         for _ in range(args.equil // 100):
             eq.step(niter=100)
             equil_done += 100
+        if equil_done:
+            # A lattice start can be refused by the cluster lists (its 4-atom clusters are too long for a small box) and the
+            # context then waits >= 1000 force calls before it tries them again: the melted configuration gets a fresh one.
+            forces = Forces(par, terms=terms, **cfg)
+            forces.compute(system.pos, system.box, system.forces)
     integ = Integrator(system, forces, TIMESTEP_FS, dev, gamma=GAMMA_PS, T=TEMPERATURE)
     sampler = ClockSampler(local) if rank == 0 else None  # runs through the warm-up too (same load)
     t_w = time.perf_counter()
