@@ -77,6 +77,7 @@ class Integrator:
         self.seed = int(torch.randint(0, 2**62, (1,)).item())
         self._step_index = 0
         self._own_ctx = None
+        self._out = None  # (ke, energies) device buffers, kept between calls: the captured steps hold their addresses
 
     def __del__(self):
         try:
@@ -127,7 +128,10 @@ class Integrator:
             if tuple(noise.shape) != (niter,) + tuple(s.vel.shape):
                 raise RuntimeError("noise must have shape (niter, nreplicas, natoms, 3)")
             noise = noise.to(device=s.pos.device, dtype=torch.float32).contiguous()
-        ke = torch.empty(nrep, dtype=torch.float64, device=s.pos.device)
+        if self._out is None or self._out[0].shape[0] != nrep or self._out[0].device != s.pos.device:
+            self._out = (torch.empty(nrep, dtype=torch.float64, device=s.pos.device),
+                         torch.empty((nrep, _lib.NUM_ENERGIES), dtype=torch.float64, device=s.pos.device))
+        ke = self._out[0]
         native = isinstance(self.forces, Forces) and not self.forces.external
         pot = None
         if native and niter > 0:
@@ -136,7 +140,7 @@ class Integrator:
             if f._exact_gradient:  # left behind by an autograd-path compute(): MD uses the reference's explicit forces
                 _lib.check(L.tmd_set_force_convention(ctx, 0))
                 f._exact_gradient = False
-            ene = torch.empty((nrep, _lib.NUM_ENERGIES), dtype=torch.float64, device=s.pos.device)
+            ene = self._out[1]
             # A neighbour list that outgrows its reserved capacity inside the fused call invalidates the call (the
             # kernels truncate, the library grows the capacity at the stats() check).  The state is three small
             # tensors: keep a copy and run the call again from it instead of giving up.
