@@ -16,3 +16,14 @@ except Exception as e:
     print(sys.argv[1], "no result", e)
 PY
 done
+if [ "$2" = thr ]; then
+  timeout -s KILL 200 $RUN --master-port 29584 bench.py --gpus $N --workload thrombin16 --steps 2000 --warmup 200 --no-cpu-baseline --e2e-steps 50 > gpurun_out/scale_thr16_$N.json 2> gpurun_out/scale_thr16_$N.err
+  python - $N <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open("gpurun_out/scale_thr16_%s.json" % sys.argv[1]) if l.startswith("{")][-1])
+    print("N=%s thrombin16 steps/s %7.0f ms/step %.4f pair_ms %.4f e2e %5.0f replicas/gpu %s" % (sys.argv[1], d["value"], d["ms_per_step"], d["roofline"]["avg_kernel_ms"], d["e2e"]["value"], d["state"].get("replicas_per_gpu")))
+except Exception as e:
+    print("thrombin16 no result", e)
+PY
+fi
