@@ -115,6 +115,37 @@ def test_autograd_path(hostsim):
     A.test_gpu_energy_backward_and_vmap()
 
 
+def test_minimizers_over_the_kernels(hostsim, capsys):
+    """minimize_pytorch_bfgs (the autograd path: Epot.sum().backward() through the kernel pass) and minimize_cg
+    (plain compute calls) on the water fixture: both lower the potential energy and leave finite coordinates."""
+    from conftest import golden_cfg, load_golden, params_from_golden
+    from torchmd_b200 import Forces, System
+    from torchmd_b200.minimizers import minimize_cg, minimize_pytorch_bfgs
+
+    g = load_golden("water291_rf_switch")
+    terms = [str(x) for x in g["terms"]]
+    n = len(g["coords"])
+
+    def fresh():
+        system = System(n, 1, torch.float32, "cpu")
+        system.pos[:] = torch.tensor(np.asarray(g["coords"], np.float32))[None]
+        system.box[0] = torch.diag(torch.tensor(np.asarray(g["box"], np.float32).reshape(-1)[:3]))
+        forces = Forces(params_from_golden(g, device="cpu"), terms=terms, **golden_cfg(g))
+        e0 = forces.compute(system.pos, system.box, system.forces)[0]
+        return system, forces, e0
+
+    system, forces, e0 = fresh()
+    minimize_pytorch_bfgs(system, forces, steps=2, max_iter=4)
+    e1 = forces.compute(system.pos, system.box, system.forces)[0]
+    assert e1 < e0 - 1.0 and bool(torch.isfinite(system.pos).all()), (e0, e1)
+    assert capsys.readouterr().out.splitlines()[0].split() == ["Iter", "Epot", "fmax"]
+
+    system, forces, e0 = fresh()
+    minimize_cg(system, forces, steps=3, update_system=True)
+    e2 = forces.compute(system.pos, system.box, system.forces)[0]
+    assert e2 < e0 - 1.0 and bool(torch.isfinite(system.pos).all()), (e0, e2)
+
+
 def test_smoke_entry_point(hostsim, capsys):
     """__graft_entry__.smoke(), the function the driver runs on the B200 before the bench."""
     import __graft_entry__ as g

@@ -64,7 +64,7 @@ def minimize_pytorch_bfgs(system, calculator, steps=10, max_iter=20, tolerance_c
         total = epot.sum()
         total.backward()
         fmax = np.max(np.linalg.norm(flat.grad.detach().cpu().numpy(), axis=1))
-        print("{0:4d}   {1: 3.6f}   {2: 3.6f}".format(count[0], float(total), fmax))
+        print("{0:4d}   {1: 3.6f}   {2: 3.6f}".format(count[0], float(total.detach()), fmax))
         count[0] += 1
         return total
 
