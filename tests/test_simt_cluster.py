@@ -223,6 +223,19 @@ def test_step_boundary_kernel_reproduces_the_two_kernel_sequence(host_cl, monkey
     assert out[0][4] < out[1][4]  # fewer launches
 
 
+@pytest.mark.parametrize("seed", [108, 109])
+def test_cluster_fuzz_sample(host_cl, seed):
+    """Two seeds of scripts/fuzz_cluster.py that take the cluster path: an open system with bonds inside and across
+    clusters, and two replicas of a periodic box with atoms whole boxes away -- first evaluation, list reuse, rebuild."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("fuzz_cluster", os.path.join(T.ROOT, "scripts", "fuzz_cluster.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ok, kern, desc = mod.one(seed)
+    assert kern == 4 and ok, desc
+
+
 def test_cluster_path_with_owned_atom_ranges(host_cl):
     """Decomposed runs: a context that owns a range of atoms builds lists only for the pairs that touch an owned atom;
     its forces on the owned atoms are the full forces, and the ranks' energy shares add up to the total."""
