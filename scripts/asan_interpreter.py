@@ -45,7 +45,57 @@ def main():
     T.test_exact_gradient_convention(L)
     T.test_owned_atom_range_forces_match_the_full_evaluation(L, L, "packed")
     T.test_tiny_systems(L)
+    cluster_cases()
     print("asan: no report")
+
+
+def cluster_cases():
+    """The cluster half-list path (round 2) under ASan: the tests of tests/test_simt_cluster.py on an ASan build with the
+    cluster path as the default -- list build and pair kernel in a periodic box (atoms thrown boxes away), band pairs,
+    systems without a box, capacity growth and the fall-back, fused MD steps with the step boundary kernel (issued
+    eagerly and as captured steps), the term-parallel bonded kernels, owned-atom ranges."""
+    import torch
+    from _pytest.monkeypatch import MonkeyPatch
+
+    import test_simt_cluster as TC
+    import test_simt_kernels as T
+    from torchmd_b200 import _lib
+
+    lib = T.load(T.build_simt("_asan_cl", list(T.VARIANTS["_cl"]) + ["TMD_SIMT_ASAN=1"]))
+
+    class _Stream:
+        cuda_stream = None
+
+    mp = MonkeyPatch()
+    try:
+        mp.setattr(_lib, "_lib", lib)
+        mp.setattr(_lib, "on_device", lambda t: True)
+        mp.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+        mp.setattr(torch.cuda, "current_device", lambda: 0)
+        mp.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+        for thrown in (0, 3):
+            TC.test_cluster_path_periodic_water(lib, thrown)
+        print("cluster: periodic water clean", flush=True)
+        TC.test_cluster_exact_pass_decides_band_pairs(lib)
+        for name in ("ala2_nobox_rf", "thrombin_nobox_rf"):
+            TC.test_cluster_path_without_a_box(lib, name)
+        print("cluster: band pairs, no-box systems clean", flush=True)
+        def with_env(fn, *args):  # the tests set environment switches through their monkeypatch fixture: undo per test
+            env = MonkeyPatch()
+            try:
+                fn(lib, env, *args)
+            finally:
+                env.undo()
+
+        with_env(TC.test_cluster_list_capacity_grows_and_lattice_falls_back)
+        with_env(TC.test_cluster_md_steps_follow_the_full_list_trajectory)
+        for graph in ("0", "1"):
+            with_env(TC.test_step_boundary_kernel_reproduces_the_two_kernel_sequence, graph)
+        print("cluster: capacity growth, MD steps, step boundary clean", flush=True)
+        TC.test_cluster_path_with_owned_atom_ranges(lib)
+        print("cluster: owned ranges clean", flush=True)
+    finally:
+        mp.undo()
 
 
 if __name__ == "__main__":
