@@ -6,7 +6,8 @@
 Device memory is host memory in that build, so an out-of-bounds index in a kernel (global or shared) is an ASan
 report and a non-zero exit.  Covers the default, fixed-point, packed and no-box pair kernels, the culled list build,
 row overflow and regrowth, >32 exclusions, the wrap kernel, fused MD steps, the bonded overlap, the exact-gradient
-convention, owned-atom ranges and the in-process peer-to-peer exchange with three ranks.  Takes about ten minutes.
+convention, owned-atom ranges, the in-process peer-to-peer exchange with three ranks, and (cluster_cases) the cluster
+half-list path of round 2.  Takes about half an hour.
 """
 import os
 import subprocess
